@@ -1,0 +1,298 @@
+// cgs.cu — fused tall-skinny Gram-Schmidt passes over the device-resident Krylov basis.
+//
+// Replaces the dot/axpy pairs of LanczosBase::orthogonalize (lanczos.hpp:143-146, called c times per
+// step at :416-418) and ArnoldiBase's MGS loop (arnoldi.hpp:380-383) by classical Gram-Schmidt with
+// reorthogonalisation (CGS2) in three passes, each streaming the basis once:
+//   DOT          h  = V^H x
+//   UPDATE_DOT   y  = x - V hin ;  h = V^H y      (both from the same shared-memory tile)
+//   UPDATE_NORM  y  = x - V hin ;  nrm2 = ||y||^2
+// HBM-bound (0.25 flop/B): no tensor cores.  One persistent CTA per SM; one producer thread feeds a
+// ring of shared-memory stages with TMA (2D tiled loads of a [T rows x NC cols] box of V, 1D bulk
+// copy of the x tile); 8 consumer warps each own a column group (CG columns held in registers for
+// both the update and the dot) and a row group; per-column sums live in registers across all tiles of
+// the CTA and are reduced once at the end: warp shuffle -> shared memory -> per-CTA partial -> the last
+// CTA to finish sums the partials in CTA order (deterministic, no floating-point atomics).
+//
+// All vectors are double arrays of padded length ld (multiple of 512, pads are zero), a complex vector
+// being ld/2 interleaved (re,im) pairs; a lane always holds one double2 per column, i.e. one complex
+// element or two real rows.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace cmb {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;
+
+template <int CG, int WC>
+struct CgsCfg {
+  static constexpr int WR = kConsumerWarps / WC;
+  static constexpr int T = 64 * WR;                   // rows (doubles) per tile
+  static constexpr int NC = CG * WC;                  // columns per tile
+  static constexpr int BOXR = T < 256 ? T : 256;      // TMA box rows
+  static constexpr int NBOX = T / BOXR;
+  static constexpr int V_BYTES = NC * T * 8;
+  static constexpr int X_BYTES = T * 8;
+  static constexpr int STAGE_BYTES = V_BYTES + X_BYTES;
+  static constexpr int PW_BYTES = (WC > 1) ? 2 * WC * T * 8 : 0;
+  static constexpr int RED_BYTES = WR * NC * 2 * 8;
+};
+
+template <int CG, int WC, bool CPLX, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x, double* __restrict__ y,
+           const double* __restrict__ hin, double* __restrict__ hout, double* __restrict__ partial,
+           unsigned* __restrict__ ticket, const int* __restrict__ halt, int ncols, int ntiles, int stages) {
+  using Cfg = CgsCfg<CG, WC>;
+  constexpr int T = Cfg::T, NC = Cfg::NC, WR = Cfg::WR;
+  constexpr int ES = CPLX ? 2 : 1;  // doubles per coefficient
+  if (*halt) return;
+
+  extern __shared__ __align__(1024) unsigned char smem[];
+  double* stage_base = reinterpret_cast<double*>(smem);
+  unsigned char* tail = smem + size_t(stages) * Cfg::STAGE_BYTES;
+  double* pw = reinterpret_cast<double*>(tail);
+  double* red = reinterpret_cast<double*>(tail + Cfg::PW_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail + Cfg::PW_BYTES + Cfg::RED_BYTES);
+  uint64_t* empty = full + stages;
+  __shared__ int s_last;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kConsumerWarps) {
+    // ===== producer: one thread issues every TMA of this CTA =====
+    if (lane == 0) {
+      prefetch_tmap(&tmV);
+      const uint32_t bytes = Cfg::V_BYTES + (x ? Cfg::X_BYTES : 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (it / stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], bytes);
+        double* vs = stage_base + size_t(s) * (Cfg::STAGE_BYTES / 8);
+#pragma unroll
+        for (int b = 0; b < Cfg::NBOX; ++b)
+          tma_load_2d(vs + size_t(b) * NC * Cfg::BOXR, &tmV, tile * T + b * Cfg::BOXR, 0, &full[s]);
+        if (x) bulk_load_1d(vs + NC * T, x + size_t(tile) * T, Cfg::X_BYTES, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const int gc = warp % WC;  // column group
+  const int gr = warp / WC;  // row group (64 doubles each)
+  const int row = gr * 64 + 2 * lane;                                  // first of this lane's two doubles in the tile
+  const int vofs = (row / Cfg::BOXR) * NC * Cfg::BOXR + (row % Cfg::BOXR);  // offset inside the V tile for column 0
+
+  double hr[CG], hi[CPLX ? CG : 1];
+  if (MODE >= 1) {
+#pragma unroll
+    for (int j = 0; j < CG; ++j) {
+      const int col = gc * CG + j;
+      hr[j] = col < ncols ? hin[col * ES] : 0.0;
+      if (CPLX) hi[j] = col < ncols ? hin[col * ES + 1] : 0.0;
+    }
+  }
+  double ar[CG], ai[CPLX ? CG : 1];
+#pragma unroll
+  for (int j = 0; j < CG; ++j) {
+    ar[j] = 0.0;
+    if (CPLX) ai[j] = 0.0;
+  }
+  double nrm = 0.0;
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int s = it % stages;
+    const uint32_t ph = (it / stages) & 1;
+    mbar_wait(&full[s], ph);
+    const double* vs = stage_base + size_t(s) * (Cfg::STAGE_BYTES / 8);
+    double2 xv = make_double2(0.0, 0.0);
+    if (x) xv = *reinterpret_cast<const double2*>(vs + NC * T + row);
+    double2 v[CG];
+#pragma unroll
+    for (int j = 0; j < CG; ++j)
+      v[j] = *reinterpret_cast<const double2*>(vs + vofs + (gc * CG + j) * Cfg::BOXR);
+
+    double2 yv = xv;
+    if (MODE >= 1) {
+      double2 p = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < CG; ++j) {
+        if (CPLX) {
+          p.x = fma(v[j].x, hr[j], p.x);
+          p.x = fma(-v[j].y, hi[j], p.x);
+          p.y = fma(v[j].x, hi[j], p.y);
+          p.y = fma(v[j].y, hr[j], p.y);
+        } else {
+          p.x = fma(v[j].x, hr[j], p.x);
+          p.y = fma(v[j].y, hr[j], p.y);
+        }
+      }
+      if (WC > 1) {
+        double* buf = pw + size_t(it & 1) * WC * T;
+        *reinterpret_cast<double2*>(buf + gc * T + row) = p;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + gr), "r"(WC * 32) : "memory");
+        p = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int g = 0; g < WC; ++g) {
+          const double2 q = *reinterpret_cast<const double2*>(buf + g * T + row);
+          p.x += q.x;
+          p.y += q.y;
+        }
+      }
+      yv.x = xv.x - p.x;
+      yv.y = xv.y - p.y;
+      if (gc == 0) *reinterpret_cast<double2*>(y + size_t(tile) * T + row) = yv;
+    }
+    if (MODE <= 1) {
+#pragma unroll
+      for (int j = 0; j < CG; ++j) {
+        if (CPLX) {  // conj(v) * y
+          ar[j] = fma(v[j].x, yv.x, ar[j]);
+          ar[j] = fma(v[j].y, yv.y, ar[j]);
+          ai[j] = fma(v[j].x, yv.y, ai[j]);
+          ai[j] = fma(-v[j].y, yv.x, ai[j]);
+        } else {
+          ar[j] = fma(v[j].x, yv.x, ar[j]);
+          ar[j] = fma(v[j].y, yv.y, ar[j]);
+        }
+      }
+    } else if (gc == 0) {
+      nrm = fma(yv.x, yv.x, nrm);
+      nrm = fma(yv.y, yv.y, nrm);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // ===== CTA-level reduction =====
+  constexpr int NRED = (MODE <= 1) ? NC * ES : 1;  // values per CTA
+  if (MODE <= 1) {
+#pragma unroll
+    for (int j = 0; j < CG; ++j) {
+      const double sr = warp_sum(ar[j]);
+      double si = 0.0;
+      if (CPLX) si = warp_sum(ai[j]);
+      if (lane == 0) {
+        red[gr * NC * ES + (gc * CG + j) * ES] = sr;
+        if (CPLX) red[gr * NC * ES + (gc * CG + j) * ES + 1] = si;
+      }
+    }
+  } else {
+    const double sn = warp_sum(nrm);
+    if (lane == 0 && gc == 0) red[gr] = sn;
+  }
+  asm volatile("bar.sync 9, %0;" ::"r"(kConsumerWarps * 32) : "memory");
+  const int nout = (MODE <= 1) ? ncols * ES : 1;
+  for (int t = threadIdx.x; t < NRED; t += kConsumerWarps * 32) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int g = 0; g < WR; ++g) sacc += (MODE <= 1) ? red[g * NC * ES + t] : red[g];
+    if (t < nout) partial[size_t(blockIdx.x) * kPartialStride + t] = sacc;
+  }
+  // ===== last CTA sums the per-CTA partials in CTA order =====
+  __threadfence();
+  asm volatile("bar.sync 9, %0;" ::"r"(kConsumerWarps * 32) : "memory");
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(ticket, 1u);
+    s_last = (prev == gridDim.x - 1);
+  }
+  asm volatile("bar.sync 9, %0;" ::"r"(kConsumerWarps * 32) : "memory");
+  if (s_last) {
+    __threadfence();
+    for (int t = threadIdx.x; t < nout; t += kConsumerWarps * 32) {
+      double sacc = 0.0;
+      for (int b = 0; b < int(gridDim.x); ++b) sacc += __ldcg(&partial[size_t(b) * kPartialStride + t]);
+      hout[t] = sacc;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+template <int CG, int WC, bool CPLX, int MODE>
+static int launch_cfg(cmb_ctx* ctx, const CgsPass& a) {
+  using Cfg = CgsCfg<CG, WC>;
+  const int64_t ntiles64 = a.ld / Cfg::T;
+  CMB_REQUIRE(a.ld % Cfg::T == 0 && ntiles64 < (int64_t(1) << 31) / Cfg::T, "padded length not tileable");
+  const int ntiles = int(ntiles64);
+  const int fixed = Cfg::PW_BYTES + Cfg::RED_BYTES + 2 * 8 * 16 + 64;
+  int stages = (200 * 1024 - fixed) / Cfg::STAGE_BYTES;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  const size_t smem = size_t(stages) * Cfg::STAGE_BYTES + Cfg::PW_BYTES + Cfg::RED_BYTES + size_t(2) * stages * 8;
+
+  // tensor map over the chunk of V: dim0 = rows (doubles, contiguous), dim1 = columns
+  CUtensorMap tm;
+  cuuint64_t gdim[2] = {cuuint64_t(a.ld), cuuint64_t(a.ncols)};
+  cuuint64_t gstr[1] = {cuuint64_t(a.col_stride) * 8};
+  cuuint32_t box[2] = {cuuint32_t(Cfg::BOXR), cuuint32_t(Cfg::NC)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult cr = get_encode_tiled()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(a.V), gdim, gstr, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) ld=%lld ncols=%d", int(cr), (long long)a.ld, a.ncols);
+    return CMB_ERR_CUDA;
+  }
+  auto kern = cgs_kernel<CG, WC, CPLX, MODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  int grid = ctx->num_sms;
+  if (grid > ntiles) grid = ntiles;
+  if (grid > kMaxGrid) grid = kMaxGrid;
+  static const char* fam[3] = {"cgs_dot", "cgs_update_dot", "cgs_update_norm"};
+  {
+    LaunchScope ls(ctx, a.family ? a.family : fam[MODE]);
+    kern<<<grid, kThreads, smem, ctx->stream>>>(tm, a.x, a.y, a.hin, a.hout, ctx->d_partial, ctx->d_ticket, a.halt,
+                                                a.ncols, ntiles, stages);
+  }
+  CMB_CUDA(cudaGetLastError());
+  return CMB_OK;
+}
+
+template <bool CPLX, int MODE>
+static int launch_mode(cmb_ctx* ctx, const CgsPass& a) {
+  const int c = a.ncols;
+  if (c <= 1) return launch_cfg<1, 1, CPLX, MODE>(ctx, a);
+  if (c <= 2) return launch_cfg<2, 1, CPLX, MODE>(ctx, a);
+  if (c <= 4) return launch_cfg<4, 1, CPLX, MODE>(ctx, a);
+  if (c <= 8) return launch_cfg<8, 1, CPLX, MODE>(ctx, a);
+  if (c <= 16) return launch_cfg<8, 2, CPLX, MODE>(ctx, a);
+  if (c <= 32) return launch_cfg<8, 4, CPLX, MODE>(ctx, a);
+  if (c <= 64) return launch_cfg<8, 8, CPLX, MODE>(ctx, a);
+  if constexpr (!CPLX) {
+    if (c <= 128) return launch_cfg<16, 8, CPLX, MODE>(ctx, a);
+  }
+  set_error("cgs pass: %d columns exceed the per-pass maximum", c);
+  return CMB_ERR_INVALID;
+}
+
+int cgs_pass(cmb_ctx* ctx, bool cplx, int mode, const CgsPass& a) {
+  CMB_REQUIRE(a.ncols >= 1 && a.ncols <= cgs_max_cols(cplx), "bad column count");
+  CMB_REQUIRE(mode >= 0 && mode <= 2, "bad mode");
+  if (cplx) {
+    if (mode == 0) return launch_mode<true, 0>(ctx, a);
+    if (mode == 1) return launch_mode<true, 1>(ctx, a);
+    return launch_mode<true, 2>(ctx, a);
+  }
+  if (mode == 0) return launch_mode<false, 0>(ctx, a);
+  if (mode == 1) return launch_mode<false, 1>(ctx, a);
+  return launch_mode<false, 2>(ctx, a);
+}
+
+}  // namespace cmb

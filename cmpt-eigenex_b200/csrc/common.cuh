@@ -1,0 +1,185 @@
+// common.cuh — shared internals of libcmpt_b200.so (context, error plumbing, TMA / mbarrier wrappers).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <complex>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "cmpt_b200.h"
+
+namespace cmb {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define CMB_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::cmb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return CMB_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+#define CMB_TRY(expr)        \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != CMB_OK) return _r; \
+  } while (0)
+
+#define CMB_REQUIRE(cond, msg)                                         \
+  do {                                                                 \
+    if (!(cond)) {                                                     \
+      ::cmb::set_error("%s:%d: %s (%s)", __FILE__, __LINE__, msg, #cond); \
+      return CMB_ERR_INVALID;                                          \
+    }                                                                  \
+  } while (0)
+
+// ---- NCCL, loaded at run time (libnccl.so.2) so that single-GPU use needs no NCCL at all --------
+struct NcclId {
+  char internal[128];
+};
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId /* ncclUniqueId, by value */, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+int nccl_load(NcclApi** api);  // CMB_OK or CMB_ERR_NCCL
+enum { kNcclFloat64 = 8, kNcclInt8 = 0, kNcclSum = 0 };
+
+struct ProfEntry {
+  double ms = 0.0;
+  uint64_t launches = 0;
+};
+
+}  // namespace cmb
+
+// ---- the context ---------------------------------------------------------------------------------
+struct cmb_ctx {
+  int device = 0;
+  int rank = 0;
+  int nranks = 1;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;  // every kernel of the library runs here
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  uint64_t launches = 0;
+  void* nccl_comm = nullptr;
+  cmb::NcclApi* nccl = nullptr;
+  // cross-CTA reduction workspace: partial sums [kMaxGrid][kPartialStride] and a ticket counter
+  double* d_partial = nullptr;
+  unsigned* d_ticket = nullptr;
+  // L2 flush buffer
+  void* d_flush = nullptr;
+  size_t flush_bytes = 0;
+  // per-family profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  struct Pending {
+    std::string family;
+    cudaEvent_t a, b;
+  };
+  std::vector<Pending> pending;
+  std::map<std::string, cmb::ProfEntry> prof;
+};
+
+namespace cmb {
+
+constexpr int kMaxGrid = 148 * 8;      // upper bound on persistent grids that use d_partial
+constexpr int kPartialStride = 2 * 136; // doubles per CTA row of d_partial (complex: re,im per column)
+
+// RAII-ish launch bracket: counts the launch and, when profiling, records events around it.
+struct LaunchScope {
+  cmb_ctx* ctx;
+  cudaEvent_t a = nullptr, b = nullptr;
+  const char* family;
+  LaunchScope(cmb_ctx* c, const char* fam);
+  ~LaunchScope();
+};
+int resolve_profile(cmb_ctx* ctx);
+
+int allreduce_sum_f64(cmb_ctx* ctx, double* dev_ptr, size_t count);  // no-op when nranks == 1
+
+// driver entry point for tensor-map encoding (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled();
+
+template <class T>
+inline T* dalloc(size_t n) {
+  T* p = nullptr;
+  if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+  return p;
+}
+
+#ifdef __CUDACC__
+// ---- device-side PTX wrappers: mbarrier + TMA -----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 2D tiled TMA load: coordinates {c0 (innermost: row), c1 (column)}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+// 1D bulk copy global -> shared (16-byte aligned, size multiple of 16)
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif  // __CUDACC__
+
+}  // namespace cmb

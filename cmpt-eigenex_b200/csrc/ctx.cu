@@ -1,0 +1,316 @@
+// ctx.cu — context (one GPU / one rank), error strings, NCCL loader, timers, profiling brackets.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cmb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int nccl_load(NcclApi** out) {
+  static NcclApi api;
+  static int state = 0;  // 0 = not tried, 1 = ok, -1 = failed
+  if (state == 0) {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) {
+      state = -1;
+    } else {
+      auto sym = [&](const char* s) { return dlsym(api.handle, s); };
+      api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+      api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+      api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+      api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+      api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+      api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+      api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+      api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+      state = (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Send && api.Recv &&
+               api.GroupStart && api.GroupEnd)
+                  ? 1
+                  : -1;
+    }
+  }
+  if (state != 1) {
+    set_error("NCCL (libnccl.so.2) could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
+    return CMB_ERR_NCCL;
+  }
+  *out = &api;
+  return CMB_OK;
+}
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+LaunchScope::LaunchScope(cmb_ctx* c, const char* fam) : ctx(c), family(fam) {
+  ctx->launches++;
+  if (ctx->profiling) {
+    auto get = [&]() {
+      cudaEvent_t e = nullptr;
+      if (!ctx->ev_pool.empty()) {
+        e = ctx->ev_pool.back();
+        ctx->ev_pool.pop_back();
+      } else {
+        cudaEventCreate(&e);
+      }
+      return e;
+    };
+    a = get();
+    b = get();
+    cudaEventRecord(a, ctx->stream);
+  }
+}
+LaunchScope::~LaunchScope() {
+  if (a) {
+    cudaEventRecord(b, ctx->stream);
+    ctx->pending.push_back({family, a, b});
+  }
+}
+
+int resolve_profile(cmb_ctx* ctx) {
+  if (ctx->pending.empty()) return CMB_OK;
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& p : ctx->pending) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    auto& e = ctx->prof[p.family];
+    e.ms += ms;
+    e.launches++;
+    ctx->ev_pool.push_back(p.a);
+    ctx->ev_pool.push_back(p.b);
+  }
+  ctx->pending.clear();
+  return CMB_OK;
+}
+
+int allreduce_sum_f64(cmb_ctx* ctx, double* p, size_t count) {
+  if (ctx->nranks == 1) return CMB_OK;
+  int r = ctx->nccl->AllReduce(p, p, count, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
+  if (r != 0) {
+    set_error("ncclAllReduce failed: %s", ctx->nccl->GetErrorString ? ctx->nccl->GetErrorString(r) : "?");
+    return CMB_ERR_NCCL;
+  }
+  return CMB_OK;
+}
+
+static int ctx_init_common(cmb_ctx* c, int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device is visible: libcmpt_b200 has no CPU fallback");
+    return CMB_ERR_NO_DEVICE;
+  }
+  CMB_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+  c->device = device;
+  CMB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CMB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return CMB_ERR_UNSUPPORTED;
+  }
+  c->num_sms = prop.multiProcessorCount;
+  CMB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CMB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CMB_CUDA(cudaEventCreate(&c->t0));
+  CMB_CUDA(cudaEventCreate(&c->t1));
+  CMB_CUDA(cudaMalloc(&c->d_partial, sizeof(double) * size_t(kMaxGrid) * kPartialStride));
+  CMB_CUDA(cudaMalloc(&c->d_ticket, sizeof(unsigned) * 16));
+  CMB_CUDA(cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned) * 16, c->stream));
+  if (!get_encode_tiled()) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return CMB_ERR_CUDA;
+  }
+  return CMB_OK;
+}
+
+}  // namespace cmb
+
+using namespace cmb;
+
+extern "C" {
+
+const char* cmb_version(void) { return "cmpt_b200 0.1 (sm_100a)"; }
+const char* cmb_last_error(void) { return get_error(); }
+
+int cmb_device_count(int* count) {
+  CMB_REQUIRE(count, "null argument");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *count = n;
+  return CMB_OK;
+}
+
+int cmb_ctx_create(int device, cmb_ctx** out) {
+  CMB_REQUIRE(out, "null argument");
+  *out = nullptr;
+  cmb_ctx* c = new (std::nothrow) cmb_ctx();
+  if (!c) return CMB_ERR_NOMEM;
+  int r = ctx_init_common(c, device);
+  if (r != CMB_OK) {
+    delete c;
+    return r;
+  }
+  *out = c;
+  return CMB_OK;
+}
+
+int cmb_nccl_unique_id(void* id128) {
+  CMB_REQUIRE(id128, "null argument");
+  NcclApi* api = nullptr;
+  CMB_TRY(nccl_load(&api));
+  NcclId id;
+  int r = api->GetUniqueId(&id);
+  if (r != 0) {
+    set_error("ncclGetUniqueId failed (%d)", r);
+    return CMB_ERR_NCCL;
+  }
+  memcpy(id128, &id, sizeof(id));
+  return CMB_OK;
+}
+
+int cmb_ctx_create_dist(int device, int rank, int nranks, const void* nccl_id, cmb_ctx** out) {
+  CMB_REQUIRE(out, "null argument");
+  *out = nullptr;
+  CMB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+  CMB_REQUIRE((nranks & (nranks - 1)) == 0, "nranks must be a power of two");
+  cmb_ctx* c = new (std::nothrow) cmb_ctx();
+  if (!c) return CMB_ERR_NOMEM;
+  int r = ctx_init_common(c, device);
+  if (r != CMB_OK) {
+    delete c;
+    return r;
+  }
+  c->rank = rank;
+  c->nranks = nranks;
+  if (nranks > 1) {
+    if (!nccl_id) {
+      set_error("nccl_id is required when nranks > 1");
+      delete c;
+      return CMB_ERR_INVALID;
+    }
+    r = nccl_load(&c->nccl);
+    if (r != CMB_OK) {
+      delete c;
+      return r;
+    }
+    NcclId id;
+    memcpy(&id, nccl_id, sizeof(id));
+    int nr = c->nccl->CommInitRank(&c->nccl_comm, nranks, id, rank);
+    if (nr != 0) {
+      set_error("ncclCommInitRank failed: %s", c->nccl->GetErrorString ? c->nccl->GetErrorString(nr) : "?");
+      delete c;
+      return CMB_ERR_NCCL;
+    }
+  }
+  *out = c;
+  return CMB_OK;
+}
+
+int cmb_ctx_destroy(cmb_ctx* c) {
+  if (!c) return CMB_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->nccl_comm && c->nccl) c->nccl->CommDestroy(c->nccl_comm);
+  for (auto& p : c->pending) {
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  if (c->d_partial) cudaFree(c->d_partial);
+  if (c->d_ticket) cudaFree(c->d_ticket);
+  if (c->d_flush) cudaFree(c->d_flush);
+  if (c->t0) cudaEventDestroy(c->t0);
+  if (c->t1) cudaEventDestroy(c->t1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+  return CMB_OK;
+}
+
+int cmb_ctx_rank(const cmb_ctx* c) { return c ? c->rank : 0; }
+int cmb_ctx_nranks(const cmb_ctx* c) { return c ? c->nranks : 1; }
+
+int cmb_ctx_sync(cmb_ctx* c) {
+  CMB_REQUIRE(c, "null context");
+  CMB_CUDA(cudaSetDevice(c->device));
+  CMB_CUDA(cudaStreamSynchronize(c->stream));
+  return CMB_OK;
+}
+
+int cmb_ctx_timer_start(cmb_ctx* c) {
+  CMB_REQUIRE(c, "null context");
+  CMB_CUDA(cudaSetDevice(c->device));
+  CMB_CUDA(cudaEventRecord(c->t0, c->stream));
+  return CMB_OK;
+}
+
+int cmb_ctx_timer_stop(cmb_ctx* c, double* ms) {
+  CMB_REQUIRE(c && ms, "null argument");
+  CMB_CUDA(cudaSetDevice(c->device));
+  CMB_CUDA(cudaEventRecord(c->t1, c->stream));
+  CMB_CUDA(cudaEventSynchronize(c->t1));
+  float f = 0.f;
+  CMB_CUDA(cudaEventElapsedTime(&f, c->t0, c->t1));
+  *ms = f;
+  return CMB_OK;
+}
+
+uint64_t cmb_ctx_launch_count(const cmb_ctx* c) { return c ? c->launches : 0; }
+
+int cmb_ctx_profile(cmb_ctx* c, int enable) {
+  CMB_REQUIRE(c, "null context");
+  CMB_TRY(resolve_profile(c));
+  c->profiling = enable != 0;
+  if (enable) c->prof.clear();
+  return CMB_OK;
+}
+
+int cmb_ctx_profile_get(cmb_ctx* c, const char* family, double* total_ms, uint64_t* launches) {
+  CMB_REQUIRE(c && family, "null argument");
+  CMB_TRY(resolve_profile(c));
+  auto it = c->prof.find(family);
+  if (total_ms) *total_ms = it == c->prof.end() ? 0.0 : it->second.ms;
+  if (launches) *launches = it == c->prof.end() ? 0 : it->second.launches;
+  return CMB_OK;
+}
+
+int cmb_ctx_flush_l2(cmb_ctx* c) {
+  CMB_REQUIRE(c, "null context");
+  CMB_CUDA(cudaSetDevice(c->device));
+  if (!c->d_flush) {
+    c->flush_bytes = size_t(256) << 20;  // 256 MiB > 126 MB L2
+    CMB_CUDA(cudaMalloc(&c->d_flush, c->flush_bytes));
+  }
+  CMB_CUDA(cudaMemsetAsync(c->d_flush, 0, c->flush_bytes, c->stream));
+  return CMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// device_utils.cuh — device helpers shared by the operator-apply and vector kernels.
+#pragma once
+#include "kernels.cuh"
+
+namespace cmb {
+
+// Every operator apply starts with the same prologue (LanczosBase::updateLanczosSteps, lanczos.hpp:429-439):
+// beta = ||w|| ; if beta <= threshold the step is dropped ; else u = w / beta.  The decision is taken on the
+// device so that a chain of steps can be enqueued without a host round trip; `halt` is sticky.
+__device__ __forceinline__ bool step_prologue(const StepScalars& sc, double& inv) {
+  if (*sc.halt) return false;
+  const double beta = sqrt(*sc.nrm2);
+  const bool first = (blockIdx.x == 0 && threadIdx.x == 0);
+  if (first && sc.beta_slot) *sc.beta_slot = beta;
+  if (beta <= sc.threshold) {
+    if (first) *sc.halt = 1;
+    return false;
+  }
+  inv = 1.0 / beta;
+  return true;
+}
+
+// Block-level sum of `nval` (1 or 2) per-thread doubles, per-CTA partial, last-CTA deterministic final sum
+// written to out[0..nval).  Must be called by every thread of every CTA of the grid exactly once.
+template <int NVAL>
+__device__ __forceinline__ void grid_sum_finalize(double a0, double a1, double* partial, unsigned* ticket,
+                                                  double* out) {
+  __shared__ double s_red[2][32];
+  __shared__ int s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  a0 = warp_sum(a0);
+  if (NVAL > 1) a1 = warp_sum(a1);
+  if (lane == 0) {
+    s_red[0][warp] = a0;
+    if (NVAL > 1) s_red[1][warp] = a1;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double b0 = lane < nw ? s_red[0][lane] : 0.0;
+    double b1 = (NVAL > 1 && lane < nw) ? s_red[1][lane] : 0.0;
+    b0 = warp_sum(b0);
+    if (NVAL > 1) b1 = warp_sum(b1);
+    if (lane == 0) {
+      partial[size_t(blockIdx.x) * 2] = b0;
+      if (NVAL > 1) partial[size_t(blockIdx.x) * 2 + 1] = b1;
+      __threadfence();
+      const unsigned prev = atomicAdd(ticket, 1u);
+      s_last = (prev == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (s_last && warp == 0) {
+    __threadfence();
+    double c0 = 0.0, c1 = 0.0;
+    for (int b = lane; b < int(gridDim.x); b += 32) {
+      c0 += __ldcg(&partial[size_t(b) * 2]);
+      if (NVAL > 1) c1 += __ldcg(&partial[size_t(b) * 2 + 1]);
+    }
+    c0 = warp_sum(c0);
+    if (NVAL > 1) c1 = warp_sum(c1);
+    if (lane == 0) {
+      out[0] = c0;
+      if (NVAL > 1) out[1] = c1;
+      *ticket = 0u;
+    }
+  }
+}
+
+}  // namespace cmb

@@ -1,0 +1,49 @@
+// kernels.cuh — internal launcher interfaces shared by the translation units of libcmpt_b200.so.
+#pragma once
+#include "common.cuh"
+
+namespace cmb {
+
+// ---- cgs.cu ------------------------------------------------------------------------------------------
+struct CgsPass {
+  const double* V = nullptr;  // first column of the chunk
+  int64_t ld = 0;             // padded column length in doubles (multiple of 512)
+  int64_t col_stride = 0;     // distance between consecutive chunk columns in doubles (ld, or interval*ld)
+  int ncols = 0;              // columns in the chunk (scalar columns)
+  const double* x = nullptr;  // input vector (nullptr = zero vector)
+  double* y = nullptr;        // output vector (modes 1, 2); may alias x
+  const double* hin = nullptr;  // coefficients to subtract (modes 1, 2)
+  double* hout = nullptr;       // V^H y (modes 0, 1) or ||y||^2 (mode 2)
+  const int* halt = nullptr;    // device flag: non-zero turns the launch into a no-op
+  const char* family = nullptr; // profiling family override
+};
+enum { CGS_DOT = 0, CGS_UPDATE_DOT = 1, CGS_UPDATE_NORM = 2 };
+inline int cgs_max_cols(bool cplx) { return cplx ? 64 : 128; }
+int cgs_pass(cmb_ctx* ctx, bool cplx, int mode, const CgsPass& a);
+
+// ---- vecops.cu ---------------------------------------------------------------------------------------
+// out[0] = sum conj(a_i) b_i (complex: out[0]=re, out[1]=im) over ld doubles; deterministic two-stage
+int vec_dot(cmb_ctx* ctx, bool cplx, const double* a, const double* b, int64_t ld, double* out, const int* halt);
+// y = x * (1/sqrt(nrm2[0]))
+int vec_scale_rsqrt(cmb_ctx* ctx, const double* x, const double* nrm2, double* y, int64_t ld, const int* halt);
+// y += shift * x   (complex shift: sr + i si)
+int vec_axpy_shift(cmb_ctx* ctx, bool cplx, double sr, double si, const double* x, double* y, int64_t ld,
+                   const int* halt);
+// x *= (fr + i fi) / sqrt(nrm2[0])  (final Ritz-vector normalisation + phase)
+int vec_scale_phase(cmb_ctx* ctx, bool cplx, double* x, const double* nrm2, const double* phase_src, int64_t ld);
+// widen a real vector to complex (re, 0)
+int vec_real_to_complex(cmb_ctx* ctx, const double* x, double* z, int64_t n);
+// finds the index of the first element (scalar index) with |x_i| > 0; writes it to out (INT64_MAX if none)
+int vec_first_nonzero(cmb_ctx* ctx, bool cplx, const double* x, int64_t n_scalars, unsigned long long* out);
+
+// Per-step scalars every operator-apply kernel reads (device memory, filled by earlier launches):
+// nrm2 -> beta = sqrt(nrm2); if beta <= threshold the chain halts (lanczos.hpp:433-437).
+struct StepScalars {
+  const double* nrm2;  // ||w||^2 (already reduced over ranks)
+  double threshold;    // halt when sqrt(nrm2) <= threshold (negative: never)
+  int* halt;           // sticky halt flag
+  double* beta_slot;   // receives sqrt(nrm2)
+  double* alpha_slot;  // receives Re<u_new, v> (complex: 2 doubles), local part
+};
+
+}  // namespace cmb

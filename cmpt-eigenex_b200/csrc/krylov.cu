@@ -1,0 +1,668 @@
+// krylov.cu — device-resident Krylov state and the step functions of the C-ABI.
+//
+// cmb_krylov holds what LanczosBase keeps in lanczosvectors_/v_/alpha_/beta_ (lanczos.hpp:233-239) and
+// ArnoldiBase in arnoldivectors_/v_/h_/residue_ (arnoldi.hpp:181-187), in HBM:
+//   basis    column segments of `seg_cols` columns, each column `ld` doubles (ld = local length padded to a
+//            multiple of 512, pads zero; a complex column is ld/2 interleaved pairs).  Deflation vectors
+//            (orthogonalizingVectors_) occupy the first ndefl columns, Krylov vectors follow.
+//   v        operator output (A+shift) u_last
+//   w        the next, not yet normalised, basis vector; scal[0] = ||w||^2
+// One Lanczos step = [CGS2 of v against the basis: three fused passes] + [operator apply fused with
+// w/beta -> new column and the alpha dot].  One Arnoldi step = the same two pieces in the other order.
+// Scalars stay on the device (kernels read beta = sqrt(scal[0]) themselves and stop the chain through a
+// sticky halt flag), so cmb_lanczos_run() can enqueue many steps with no host round trip.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "op.cuh"
+
+using namespace cmb;
+
+namespace {
+constexpr int kMaxSlots = 1 << 16;
+struct Chunk {
+  const double* V;
+  int ncols;
+  int64_t col_stride;
+};
+}  // namespace
+
+struct cmb_krylov {
+  cmb_ctx* ctx = nullptr;
+  int dtype = CMB_F64;
+  bool cplx = false;
+  int es = 1;
+  int64_t n_global = 0, row_begin = 0, n_local = 0, nd_local = 0, ld = 0;
+  int seg_cols = 0;
+  std::vector<double*> segs;
+  int ndefl = 0, nk = 0;
+  double *v = nullptr, *w = nullptr;
+  double *h1 = nullptr, *h2 = nullptr;
+  int hcap = 0;
+  double* scal = nullptr;  // [0] ||w||^2, [1] scratch norm, [2..3] scratch, [4..5] scratch alpha
+  int* halt = nullptr;
+  double *alpha_dev = nullptr, *beta_dev = nullptr;
+  double* h_stage = nullptr;  // pinned staging for scalars
+  size_t h_stage_elems = 0;
+  bool started = false;
+  double residue = 0.0;  // Arnoldi: last residual norm (host copy)
+  double bytes = 0.0;
+  double *tmp1 = nullptr, *tmp2 = nullptr, *tmpz = nullptr;
+  unsigned long long* d_idx = nullptr;
+
+  double* col(int j) const { return segs[j / seg_cols] + int64_t(j % seg_cols) * ld; }
+};
+
+static int ensure_cols(cmb_krylov* K, int total) {
+  while (int(K->segs.size()) * K->seg_cols < total) {
+    double* p = nullptr;
+    const size_t bytes = sizeof(double) * size_t(K->seg_cols) * size_t(K->ld);
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("out of device memory growing the Krylov basis to %d columns (%.2f GB per %d-column segment)", total,
+                double(bytes) / 1e9, K->seg_cols);
+      return CMB_ERR_NOMEM;
+    }
+    CMB_CUDA(cudaMemsetAsync(p, 0, bytes, K->ctx->stream));
+    K->segs.push_back(p);
+  }
+  const int cap = int(K->segs.size()) * K->seg_cols;
+  if (cap > K->hcap) {
+    cudaFree(K->h1);
+    cudaFree(K->h2);
+    K->h1 = K->h2 = nullptr;
+    CMB_CUDA(cudaMalloc(&K->h1, sizeof(double) * 2 * (cap + 8)));
+    CMB_CUDA(cudaMalloc(&K->h2, sizeof(double) * 2 * (cap + 8)));
+    K->hcap = cap;
+  }
+  return CMB_OK;
+}
+
+static int ensure_stage(cmb_krylov* K, size_t elems) {
+  if (elems <= K->h_stage_elems) return CMB_OK;
+  if (K->h_stage) cudaFreeHost(K->h_stage);
+  K->h_stage = nullptr;
+  K->h_stage_elems = 0;
+  size_t want = std::max<size_t>(elems * 2, 4096);
+  CMB_CUDA(cudaMallocHost(&K->h_stage, sizeof(double) * want));
+  K->h_stage_elems = want;
+  return CMB_OK;
+}
+
+// contiguous chunks covering absolute columns [c0, c1)
+static void contiguous_chunks(const cmb_krylov* K, int c0, int c1, std::vector<Chunk>& out) {
+  const int maxc = std::min(K->seg_cols, cgs_max_cols(K->cplx));
+  int c = c0;
+  while (c < c1) {
+    const int in_seg = K->seg_cols - (c % K->seg_cols);
+    const int n = std::min(std::min(in_seg, maxc), c1 - c);
+    out.push_back({K->col(c), n, K->ld});
+    c += n;
+  }
+}
+
+// chunks covering the strided set {first, first+stride, ...} < end (absolute column indices)
+static void strided_chunks(const cmb_krylov* K, int first, int end, int stride, std::vector<Chunk>& out) {
+  if (stride == 1) {
+    contiguous_chunks(K, first, end, out);
+    return;
+  }
+  const int maxc = cgs_max_cols(K->cplx);
+  int c = first;
+  while (c < end) {
+    const int seg = c / K->seg_cols;
+    int n = 0;
+    int cc = c;
+    while (cc < end && cc / K->seg_cols == seg && n < maxc) {
+      ++n;
+      cc += stride;
+    }
+    out.push_back({K->col(c), n, int64_t(stride) * K->ld});
+    c = cc;
+  }
+}
+
+static int total_cols(const std::vector<Chunk>& ch) {
+  int t = 0;
+  for (auto& c : ch) t += c.ncols;
+  return t;
+}
+
+// Gram-Schmidt of x against the chunk columns, result in y (may alias x); coefficients of the first pass
+// in h1, of the second in h2 (chunk order); ||y||^2 in nrm2_out.  Single chunk: DOT, UPDATE_DOT,
+// UPDATE_NORM (the basis is streamed three times).  Several chunks: one extra DOT sweep.
+static int gram_schmidt2(cmb_krylov* K, const std::vector<Chunk>& chunks, const double* x, double* y,
+                         double* nrm2_out) {
+  cmb_ctx* ctx = K->ctx;
+  const int es = K->es;
+  const int nch = int(chunks.size());
+  const int ctot = total_cols(chunks);
+  CgsPass p;
+  p.ld = K->ld;
+  p.halt = K->halt;
+  auto setc = [&](const Chunk& c) {
+    p.V = c.V;
+    p.ncols = c.ncols;
+    p.col_stride = c.col_stride;
+  };
+  // pass 1: h1 = V^H x
+  int off = 0;
+  for (int i = 0; i < nch; ++i) {
+    setc(chunks[i]);
+    p.x = x;
+    p.y = nullptr;
+    p.hin = nullptr;
+    p.hout = K->h1 + off * es;
+    CMB_TRY(cgs_pass(ctx, K->cplx, CGS_DOT, p));
+    off += chunks[i].ncols;
+  }
+  CMB_TRY(allreduce_sum_f64(ctx, K->h1, size_t(ctot) * es));
+  // pass 2: y = x - V h1 ; h2 = V^H y
+  off = 0;
+  for (int i = 0; i < nch; ++i) {
+    setc(chunks[i]);
+    p.x = (i == 0) ? x : y;
+    p.y = y;
+    p.hin = K->h1 + off * es;
+    if (i == nch - 1) {
+      p.hout = K->h2 + off * es;
+      CMB_TRY(cgs_pass(ctx, K->cplx, CGS_UPDATE_DOT, p));
+    } else {
+      p.hout = K->scal + 1;
+      CMB_TRY(cgs_pass(ctx, K->cplx, CGS_UPDATE_NORM, p));
+    }
+    off += chunks[i].ncols;
+  }
+  off = 0;
+  for (int i = 0; i < nch - 1; ++i) {
+    setc(chunks[i]);
+    p.x = y;
+    p.y = nullptr;
+    p.hin = nullptr;
+    p.hout = K->h2 + off * es;
+    CMB_TRY(cgs_pass(ctx, K->cplx, CGS_DOT, p));
+    off += chunks[i].ncols;
+  }
+  CMB_TRY(allreduce_sum_f64(ctx, K->h2, size_t(ctot) * es));
+  // pass 3: y -= V h2 ; ||y||^2
+  off = 0;
+  for (int i = 0; i < nch; ++i) {
+    setc(chunks[i]);
+    p.x = y;
+    p.y = y;
+    p.hin = K->h2 + off * es;
+    p.hout = (i == nch - 1) ? nrm2_out : K->scal + 1;
+    CMB_TRY(cgs_pass(ctx, K->cplx, CGS_UPDATE_NORM, p));
+    off += chunks[i].ncols;
+  }
+  CMB_TRY(allreduce_sum_f64(ctx, nrm2_out, 1));
+  return CMB_OK;
+}
+
+// y = x - sum_chunks V hin ; ||y||^2 -> nrm2_out (coefficients already on the device, chunk order)
+static int subtract_cols(cmb_krylov* K, const std::vector<Chunk>& chunks, const double* hin, const double* x, double* y,
+                         double* nrm2_out, const char* family) {
+  CgsPass p;
+  p.ld = K->ld;
+  p.halt = K->halt;
+  p.family = family;
+  int off = 0;
+  const int nch = int(chunks.size());
+  for (int i = 0; i < nch; ++i) {
+    p.V = chunks[i].V;
+    p.ncols = chunks[i].ncols;
+    p.col_stride = chunks[i].col_stride;
+    p.x = (i == 0) ? x : y;
+    p.y = y;
+    p.hin = hin + off * K->es;
+    p.hout = (i == nch - 1) ? nrm2_out : K->scal + 1;
+    CMB_TRY(cgs_pass(K->ctx, K->cplx, CGS_UPDATE_NORM, p));
+    off += chunks[i].ncols;
+  }
+  CMB_TRY(allreduce_sum_f64(K->ctx, nrm2_out, 1));
+  return CMB_OK;
+}
+
+static void add_step_bytes(cmb_krylov* K, const cmb_op* op, int c) {
+  // B_step(c) = B_op + (3c + 7) n s
+  K->bytes += op->bytes + (3.0 * c + 7.0) * double(K->n_local) * (K->cplx ? 16.0 : 8.0);
+}
+
+static int check_pair(const cmb_krylov* K, const cmb_op* op) {
+  CMB_REQUIRE(K && op, "null argument");
+  CMB_REQUIRE(K->ctx == op->ctx, "operator and Krylov state belong to different contexts");
+  CMB_REQUIRE(K->dtype == op->dtype, "operator and Krylov state have different dtypes");
+  CMB_REQUIRE(K->n_global == op->n_global && K->n_local == op->n_local && K->row_begin == op->row_begin,
+              "operator and Krylov state have different shapes");
+  return CMB_OK;
+}
+
+// Enqueue the orthogonalisation part of Lanczos step k (k = index of the newest Krylov vector).
+static int enqueue_lanczos_orth(cmb_krylov* K, int64_t interval) {
+  const int k = K->nk - 1;
+  std::vector<Chunk> chunks;
+  if (interval == 1) {
+    // full reorthogonalisation: the three-term recurrence is subsumed by CGS pass 1
+    // (alpha_k = h1[k], beta_{k-1} ~ h1[k-1]); deflation vectors are just the leading columns.
+    contiguous_chunks(K, 0, K->ndefl + k + 1, chunks);
+    return gram_schmidt2(K, chunks, K->v, K->w, K->scal);
+  }
+  // explicit recurrence w = v - alpha_k u_k - beta_{k-1} u_{k-1} (lanczos.hpp:402-408)
+  const int first = (k > 0) ? k - 1 : k;
+  contiguous_chunks(K, K->ndefl + first, K->ndefl + k + 1, chunks);
+  CMB_CUDA(cudaMemsetAsync(K->h1, 0, sizeof(double) * 4, K->ctx->stream));
+  int slot = 0;
+  if (k > 0) {
+    CMB_CUDA(cudaMemcpyAsync(K->h1 + slot * K->es, K->beta_dev + (k - 1), sizeof(double), cudaMemcpyDeviceToDevice,
+                             K->ctx->stream));
+    ++slot;
+  }
+  CMB_CUDA(cudaMemcpyAsync(K->h1 + slot * K->es, K->alpha_dev + size_t(k) * 2, sizeof(double), cudaMemcpyDeviceToDevice,
+                           K->ctx->stream));
+  CMB_TRY(subtract_cols(K, chunks, K->h1, K->v, K->w, K->scal, "recurrence"));
+  if (interval > 1) {
+    const int kmod = int((k + 1) % interval);
+    chunks.clear();
+    if (kmod == 0 && K->ndefl > 0) contiguous_chunks(K, 0, K->ndefl, chunks);
+    strided_chunks(K, K->ndefl + kmod, K->ndefl + k + 1, int(interval), chunks);
+    if (!chunks.empty()) CMB_TRY(gram_schmidt2(K, chunks, K->w, K->w, K->scal));
+  }
+  return CMB_OK;
+}
+
+static int orth_cols_count(const cmb_krylov* K, int64_t interval) {
+  const int k = K->nk - 1;
+  if (interval == 1) return K->ndefl + k + 1;
+  if (interval <= 0) return 0;
+  const int kmod = int((k + 1) % interval);
+  int c = (kmod == 0) ? K->ndefl : 0;
+  for (int kk = kmod; kk < k + 1; kk += int(interval)) ++c;
+  return c;
+}
+
+extern "C" {
+
+int cmb_krylov_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t row_begin, int64_t row_end,
+                      int64_t reserve_cols, cmb_krylov** out) {
+  CMB_REQUIRE(ctx && out, "null argument");
+  *out = nullptr;
+  CMB_REQUIRE(dtype == CMB_F64 || dtype == CMB_C64, "dtype must be CMB_F64 or CMB_C64");
+  CMB_REQUIRE(n_global >= 1 && row_begin >= 0 && row_begin < row_end && row_end <= n_global, "bad row range");
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  cmb_krylov* K = new (std::nothrow) cmb_krylov();
+  if (!K) return CMB_ERR_NOMEM;
+  K->ctx = ctx;
+  K->dtype = dtype;
+  K->cplx = dtype == CMB_C64;
+  K->es = K->cplx ? 2 : 1;
+  K->n_global = n_global;
+  K->row_begin = row_begin;
+  K->n_local = row_end - row_begin;
+  K->nd_local = K->n_local * K->es;
+  K->ld = (K->nd_local + 511) / 512 * 512;
+  const int maxc = cgs_max_cols(K->cplx);
+  int64_t want = reserve_cols <= 0 ? 128 : reserve_cols;
+  K->seg_cols = int(std::max<int64_t>(4, std::min<int64_t>(want, maxc)));
+  int rc = [&]() -> int {
+    CMB_CUDA(cudaMalloc(&K->v, sizeof(double) * K->ld));
+    CMB_CUDA(cudaMalloc(&K->w, sizeof(double) * K->ld));
+    CMB_CUDA(cudaMemsetAsync(K->v, 0, sizeof(double) * K->ld, ctx->stream));
+    CMB_CUDA(cudaMemsetAsync(K->w, 0, sizeof(double) * K->ld, ctx->stream));
+    CMB_CUDA(cudaMalloc(&K->scal, sizeof(double) * 16));
+    CMB_CUDA(cudaMemsetAsync(K->scal, 0, sizeof(double) * 16, ctx->stream));
+    CMB_CUDA(cudaMalloc(&K->halt, sizeof(int) * 4));
+    CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int) * 4, ctx->stream));
+    CMB_CUDA(cudaMalloc(&K->alpha_dev, sizeof(double) * 2 * kMaxSlots));
+    CMB_CUDA(cudaMalloc(&K->beta_dev, sizeof(double) * kMaxSlots));
+    CMB_CUDA(cudaMalloc(&K->d_idx, sizeof(unsigned long long) * 2));
+    CMB_TRY(ensure_stage(K, 4096));
+    return CMB_OK;
+  }();
+  if (rc != CMB_OK) {
+    cmb_krylov_destroy(K);
+    return rc;
+  }
+  *out = K;
+  return CMB_OK;
+}
+
+int cmb_krylov_destroy(cmb_krylov* K) {
+  if (!K) return CMB_OK;
+  cudaSetDevice(K->ctx->device);
+  cudaStreamSynchronize(K->ctx->stream);
+  for (auto p : K->segs) cudaFree(p);
+  cudaFree(K->v);
+  cudaFree(K->w);
+  cudaFree(K->h1);
+  cudaFree(K->h2);
+  cudaFree(K->scal);
+  cudaFree(K->halt);
+  cudaFree(K->alpha_dev);
+  cudaFree(K->beta_dev);
+  cudaFree(K->tmp1);
+  cudaFree(K->tmp2);
+  cudaFree(K->tmpz);
+  cudaFree(K->d_idx);
+  if (K->h_stage) cudaFreeHost(K->h_stage);
+  delete K;
+  return CMB_OK;
+}
+
+int cmb_krylov_clear(cmb_krylov* K) {
+  CMB_REQUIRE(K, "null argument");
+  CMB_CUDA(cudaSetDevice(K->ctx->device));
+  K->nk = 0;
+  K->started = false;
+  K->residue = 0.0;
+  K->bytes = 0.0;
+  CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int) * 4, K->ctx->stream));
+  return CMB_OK;
+}
+
+int cmb_krylov_set_deflation(cmb_krylov* K, int64_t nvec, const void* vecs, int64_t ld) {
+  CMB_REQUIRE(K && nvec >= 0 && (nvec == 0 || (vecs && ld >= K->n_local)), "bad deflation vectors");
+  CMB_REQUIRE(K->nk == 0, "deflation vectors can only change while the basis is empty");
+  CMB_REQUIRE(nvec < kMaxSlots, "too many deflation vectors");
+  CMB_CUDA(cudaSetDevice(K->ctx->device));
+  K->ndefl = int(nvec);
+  if (nvec == 0) return CMB_OK;
+  CMB_TRY(ensure_cols(K, int(nvec) + 1));
+  const char* src = static_cast<const char*>(vecs);
+  for (int64_t j = 0; j < nvec; ++j)
+    CMB_CUDA(cudaMemcpyAsync(K->col(int(j)), src + size_t(j) * ld * K->es * sizeof(double),
+                             sizeof(double) * K->nd_local, cudaMemcpyHostToDevice, K->ctx->stream));
+  CMB_CUDA(cudaStreamSynchronize(K->ctx->stream));
+  return CMB_OK;
+}
+
+int cmb_krylov_start(cmb_krylov* K, const void* init, double threshold, int* status) {
+  CMB_REQUIRE(K && init && status, "null argument");
+  cmb_ctx* ctx = K->ctx;
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  K->nk = 0;
+  K->started = false;
+  K->residue = 0.0;
+  CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int) * 4, ctx->stream));
+  CMB_CUDA(cudaMemcpyAsync(K->w, init, sizeof(double) * K->nd_local, cudaMemcpyHostToDevice, ctx->stream));
+  if (K->ndefl > 0) {
+    // lanczos.hpp:312-314: project the deflation vectors out of the start vector
+    std::vector<Chunk> chunks;
+    contiguous_chunks(K, 0, K->ndefl, chunks);
+    CMB_TRY(gram_schmidt2(K, chunks, K->w, K->w, K->scal));
+  } else {
+    CMB_TRY(vec_dot(ctx, K->cplx, K->w, K->w, K->ld, K->scal + 2, K->halt));
+    CMB_CUDA(cudaMemcpyAsync(K->scal, K->scal + 2, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CMB_TRY(allreduce_sum_f64(ctx, K->scal, 1));
+  }
+  CMB_CUDA(cudaMemcpyAsync(K->h_stage, K->scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  const double nrm = sqrt(K->h_stage[0]);
+  if (!(nrm >= threshold)) {  // lanczos.hpp:316-318 (`nrm < threshold_` -> no vector); NaN also fails
+    *status = CMB_STEP_NOSTART;
+    return CMB_OK;
+  }
+  K->started = true;
+  *status = CMB_STEP_OK;
+  return CMB_OK;
+}
+
+int64_t cmb_krylov_ncols(const cmb_krylov* K) { return K ? K->nk : 0; }
+int64_t cmb_krylov_rows(const cmb_krylov* K) { return K ? K->n_local : 0; }
+double cmb_krylov_bytes(const cmb_krylov* K) { return K ? K->bytes : 0.0; }
+
+int cmb_krylov_get_col(cmb_krylov* K, int64_t j, void* out) {
+  CMB_REQUIRE(K && out && j >= 0 && j < K->nk, "column index out of range");
+  CMB_CUDA(cudaSetDevice(K->ctx->device));
+  CMB_CUDA(cudaMemcpyAsync(out, K->col(K->ndefl + int(j)), sizeof(double) * K->nd_local, cudaMemcpyDeviceToHost,
+                           K->ctx->stream));
+  CMB_CUDA(cudaStreamSynchronize(K->ctx->stream));
+  return CMB_OK;
+}
+
+int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, double threshold, int64_t nsteps,
+                    double* alpha, double* beta, int64_t* steps_done, int* status) {
+  CMB_TRY(check_pair(K, op));
+  CMB_REQUIRE(alpha && beta && steps_done && status && nsteps >= 0, "bad argument");
+  cmb_ctx* ctx = K->ctx;
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  *steps_done = 0;
+  *status = CMB_STEP_OK;
+  if (nsteps == 0) return CMB_OK;
+  const int nk0 = K->nk;
+  CMB_REQUIRE(K->ndefl + nk0 + nsteps + 1 < kMaxSlots, "too many Krylov steps");
+  int enq = 0;  // steps enqueued
+  for (int64_t s = 0; s < nsteps; ++s) {
+    StepScalars sc;
+    sc.nrm2 = K->scal;
+    sc.halt = K->halt;
+    if (K->nk + enq == 0) {
+      // first call (lanczos.hpp:378-398): u0 = start/||start|| ; v = (A+shift) u0 ; alpha0
+      CMB_REQUIRE(K->started, "cmb_krylov_start must succeed before the first step");
+      CMB_TRY(ensure_cols(K, K->ndefl + 1));
+      sc.threshold = -1.0;
+      sc.beta_slot = K->scal + 3;
+      sc.alpha_slot = K->alpha_dev;
+      CMB_TRY(op->apply(K->w, K->col(K->ndefl), K->v, shift, 0.0, sc));
+      CMB_TRY(allreduce_sum_f64(ctx, K->alpha_dev, 1));
+      K->bytes += op->bytes + 3.0 * double(K->n_local) * (K->cplx ? 16.0 : 8.0);
+      K->nk = 1;  // the first call cannot break down on the device side
+      continue;
+    }
+    const int k = K->nk + enq - 1;
+    CMB_TRY(ensure_cols(K, K->ndefl + k + 2));
+    const int nk_save = K->nk;
+    K->nk = k + 1;  // enqueue_lanczos_orth works on the state "k+1 vectors"
+    int rc = enqueue_lanczos_orth(K, interval);
+    const int c = orth_cols_count(K, interval);
+    K->nk = nk_save;
+    CMB_TRY(rc);
+    sc.threshold = threshold;
+    sc.beta_slot = K->beta_dev + k;
+    sc.alpha_slot = K->alpha_dev + size_t(k + 1) * 2;
+    CMB_TRY(op->apply(K->w, K->col(K->ndefl + k + 1), K->v, shift, 0.0, sc));
+    CMB_TRY(allreduce_sum_f64(ctx, K->alpha_dev + size_t(k + 1) * 2, 1));
+    add_step_bytes(K, op, c);
+    ++enq;
+  }
+  // one synchronisation for the whole chain
+  const bool did_first = (nk0 == 0);
+  const int a0 = did_first ? 0 : nk0;  // first alpha slot produced
+  const int na = (did_first ? 1 : 0) + enq;
+  const int b0 = nk0 == 0 ? 0 : nk0 - 1;
+  const int nb = enq;
+  CMB_TRY(ensure_stage(K, size_t(2 * na + nb + 8)));
+  double* hs = K->h_stage;
+  if (na) CMB_CUDA(cudaMemcpyAsync(hs, K->alpha_dev + size_t(a0) * 2, sizeof(double) * 2 * na, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nb) CMB_CUDA(cudaMemcpyAsync(hs + 2 * na, K->beta_dev + b0, sizeof(double) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  CMB_CUDA(cudaMemcpyAsync(hs + 2 * na + nb, K->halt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int halted = *reinterpret_cast<int*>(hs + 2 * na + nb);
+  int ok_steps = enq;
+  if (halted) {
+    ok_steps = 0;
+    while (ok_steps < enq && hs[2 * na + ok_steps] > threshold) ++ok_steps;
+    *status = CMB_STEP_BREAKDOWN;
+    CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int), ctx->stream));
+  }
+  int ai = 0;
+  if (did_first) alpha[ai++] = hs[0];
+  for (int s = 0; s < ok_steps; ++s) alpha[ai++] = hs[2 * ((did_first ? 1 : 0) + s)];
+  const int nb_out = halted ? ok_steps + 1 : ok_steps;  // the breaking beta is kept (lanczos.hpp:433-436)
+  for (int s = 0; s < nb_out && s < enq; ++s) beta[s] = hs[2 * na + s];
+  K->nk = (did_first ? 1 : nk0) + ok_steps;
+  *steps_done = (did_first ? 1 : 0) + ok_steps;
+  return CMB_OK;
+}
+
+int cmb_lanczos_step(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, double threshold, double* alpha,
+                     double* beta, int* status) {
+  CMB_REQUIRE(alpha && beta && status, "null argument");
+  int64_t done = 0;
+  double a[2] = {0, 0}, b[2] = {0, 0};
+  CMB_TRY(cmb_lanczos_run(K, op, shift, interval, threshold, 1, a, b, &done, status));
+  *alpha = a[0];
+  *beta = b[0];
+  return CMB_OK;
+}
+
+int cmb_arnoldi_step(cmb_krylov* K, cmb_op* op, const void* shift, double threshold, void* hcol, double* residue,
+                     int* status) {
+  CMB_TRY(check_pair(K, op));
+  CMB_REQUIRE(hcol && residue && status, "null argument");
+  cmb_ctx* ctx = K->ctx;
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  double shr = 0.0, shi = 0.0;
+  if (shift) {
+    shr = static_cast<const double*>(shift)[0];
+    if (K->cplx) shi = static_cast<const double*>(shift)[1];
+  }
+  *status = CMB_STEP_OK;
+  if (K->nk == 0) {
+    CMB_REQUIRE(K->started, "cmb_krylov_start must succeed before the first step");
+  } else {
+    // arnoldiStepIsUtmost (arnoldi.hpp:277-288)
+    if (K->nk >= K->n_global) {
+      *status = CMB_STEP_FULL;
+      *residue = K->residue;
+      return CMB_OK;
+    }
+    if (K->residue <= threshold) {
+      *status = CMB_STEP_BREAKDOWN;
+      *residue = K->residue;
+      return CMB_OK;
+    }
+  }
+  const int k = K->nk;  // index of the vector created now
+  CMB_REQUIRE(K->ndefl + k + 2 < kMaxSlots, "too many Krylov steps");
+  CMB_TRY(ensure_cols(K, K->ndefl + k + 1));
+  StepScalars sc;
+  sc.nrm2 = K->scal;
+  sc.halt = K->halt;
+  sc.threshold = -1.0;  // the host has already tested the residue
+  sc.beta_slot = K->scal + 3;
+  sc.alpha_slot = K->scal + 4;
+  // q_k = w / residue ; v = (A + shift) q_k        (arnoldi.hpp:361-372)
+  CMB_TRY(op->apply(K->w, K->col(K->ndefl + k), K->v, shr, shi, sc));
+  // CGS2 of v against deflation vectors and q_0..q_k ; h(:,k) = h1 + h2 ; residue = ||w||   (:373-385)
+  std::vector<Chunk> chunks;
+  const int c = K->ndefl + k + 1;
+  contiguous_chunks(K, 0, c, chunks);
+  CMB_TRY(gram_schmidt2(K, chunks, K->v, K->w, K->scal));
+  const int es = K->es;
+  CMB_TRY(ensure_stage(K, size_t(2 * c * es + 4)));
+  double* hs = K->h_stage;
+  CMB_CUDA(cudaMemcpyAsync(hs, K->h1, sizeof(double) * c * es, cudaMemcpyDeviceToHost, ctx->stream));
+  CMB_CUDA(cudaMemcpyAsync(hs + c * es, K->h2, sizeof(double) * c * es, cudaMemcpyDeviceToHost, ctx->stream));
+  CMB_CUDA(cudaMemcpyAsync(hs + 2 * c * es, K->scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  double* hout = static_cast<double*>(hcol);
+  for (int i = 0; i < (k + 1) * es; ++i) hout[i] = hs[K->ndefl * es + i] + hs[c * es + K->ndefl * es + i];
+  K->residue = sqrt(hs[2 * c * es]);
+  *residue = K->residue;
+  K->nk = k + 1;
+  add_step_bytes(K, op, c);
+  return CMB_OK;
+}
+
+static int ensure_tmp(cmb_krylov* K, double** p, size_t doubles) {
+  if (*p) return CMB_OK;
+  if (cudaMalloc(p, sizeof(double) * doubles) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("out of device memory for a Ritz-vector work buffer");
+    return CMB_ERR_NOMEM;
+  }
+  CMB_CUDA(cudaMemsetAsync(*p, 0, sizeof(double) * doubles, K->ctx->stream));
+  return CMB_OK;
+}
+
+__global__ void interleave_kernel(const double* __restrict__ re, const double* __restrict__ im, double* __restrict__ z,
+                                  long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    reinterpret_cast<double2*>(z)[i] = make_double2(re[i], im[i]);
+}
+__global__ void add2_kernel(const double* a, const double* b, double* out) { out[0] = a[0] + b[0]; }
+
+int cmb_krylov_ritz_vectors(cmb_krylov* K, cmb_dtype coef_dtype, const void* coef, int64_t ldc, int64_t ncoef,
+                            int64_t nev, void* x_host, int64_t ldx) {
+  CMB_REQUIRE(K && (nev == 0 || (coef && x_host)), "null argument");
+  CMB_REQUIRE(ncoef >= 0 && ncoef <= K->nk && ldc >= ncoef && ldx >= K->n_local && nev >= 0, "bad shape");
+  CMB_REQUIRE(coef_dtype == CMB_F64 || coef_dtype == CMB_C64, "bad coefficient dtype");
+  const bool ccplx = coef_dtype == CMB_C64;
+  CMB_REQUIRE(!(K->cplx && !ccplx), "a complex basis needs complex coefficients");
+  cmb_ctx* ctx = K->ctx;
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  if (nev == 0) return CMB_OK;
+  if (ctx->nranks > 1) {
+    set_error("Ritz-vector assembly is single-rank in this build");
+    return CMB_ERR_UNSUPPORTED;
+  }
+  const int ces = ccplx ? 2 : 1;
+  const bool widen = ccplx && !K->cplx;  // real basis, complex coefficients (ArnoldiEigenSolver<double>)
+  CMB_TRY(ensure_tmp(K, &K->tmp1, K->ld));
+  if (widen) {
+    CMB_TRY(ensure_tmp(K, &K->tmp2, K->ld));
+    CMB_TRY(ensure_tmp(K, &K->tmpz, 2 * K->ld));
+  }
+  std::vector<Chunk> chunks;
+  contiguous_chunks(K, K->ndefl, K->ndefl + int(ncoef), chunks);
+  CMB_TRY(ensure_stage(K, size_t(4 * ncoef + 8)));
+  const double* cf = static_cast<const double*>(coef);
+  const size_t out_es = ccplx ? 2 : 1;
+  for (int64_t e = 0; e < nev; ++e) {
+    double* hs = K->h_stage;
+    const double* ce = cf + size_t(e) * ldc * ces;
+    double* xdev = nullptr;
+    if (ncoef == 0) {
+      CMB_CUDA(cudaMemsetAsync(K->tmp1, 0, sizeof(double) * K->ld, ctx->stream));
+      CMB_CUDA(cudaMemsetAsync(K->scal + 1, 0, sizeof(double), ctx->stream));
+      xdev = K->tmp1;
+    } else if (!widen) {
+      // x = 0 - V (-coef)
+      for (int64_t m = 0; m < ncoef * ces; ++m) hs[m] = -ce[m];
+      CMB_CUDA(cudaMemcpyAsync(K->h1, hs, sizeof(double) * ncoef * ces, cudaMemcpyHostToDevice, ctx->stream));
+      CMB_TRY(subtract_cols(K, chunks, K->h1, nullptr, K->tmp1, K->scal + 1, "ritz_assemble"));
+      xdev = K->tmp1;
+    } else {
+      for (int64_t m = 0; m < ncoef; ++m) {
+        hs[m] = -ce[2 * m];
+        hs[ncoef + m] = -ce[2 * m + 1];
+      }
+      CMB_CUDA(cudaMemcpyAsync(K->h1, hs, sizeof(double) * 2 * ncoef, cudaMemcpyHostToDevice, ctx->stream));
+      CMB_TRY(subtract_cols(K, chunks, K->h1, nullptr, K->tmp1, K->scal + 2, "ritz_assemble"));
+      CMB_TRY(subtract_cols(K, chunks, K->h1 + ncoef, nullptr, K->tmp2, K->scal + 3, "ritz_assemble"));
+      {
+        LaunchScope ls(ctx, "vec_scale");
+        const int grid = int(std::max<long long>(1, std::min<long long>((K->ld + 255) / 256, (long long)ctx->num_sms * 8)));
+        interleave_kernel<<<grid, 256, 0, ctx->stream>>>(K->tmp1, K->tmp2, K->tmpz, K->ld);
+        add2_kernel<<<1, 1, 0, ctx->stream>>>(K->scal + 2, K->scal + 3, K->scal + 1);
+        ctx->launches++;
+      }
+      CMB_CUDA(cudaGetLastError());
+      xdev = K->tmpz;
+    }
+    // host sync needed because the staging buffer is reused per vector
+    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // phase of the first non-zero element (lanczos.hpp:806-813) and normalisation (:816)
+    CMB_TRY(vec_first_nonzero(ctx, ccplx, xdev, K->n_local, K->d_idx));
+    unsigned long long idx = 0;
+    CMB_CUDA(cudaMemcpyAsync(&idx, K->d_idx, sizeof(idx), cudaMemcpyDeviceToHost, ctx->stream));
+    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // copy the phase element aside first: the scaling kernel overwrites it while other CTAs still read it
+    const double* phase_src = nullptr;
+    if (idx != ~0ull) {
+      CMB_CUDA(cudaMemcpyAsync(K->scal + 6, xdev + idx * out_es, sizeof(double) * out_es, cudaMemcpyDeviceToDevice,
+                               ctx->stream));
+      phase_src = K->scal + 6;
+    }
+    CMB_TRY(vec_scale_phase(ctx, ccplx, xdev, K->scal + 1, phase_src, widen ? 2 * K->ld : K->ld));
+    CMB_CUDA(cudaMemcpyAsync(static_cast<char*>(x_host) + size_t(e) * ldx * out_es * sizeof(double), xdev,
+                             sizeof(double) * K->n_local * out_es, cudaMemcpyDeviceToHost, ctx->stream));
+    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return CMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,587 @@
+// ops.cu — operator application kernels: y = (A + shift) x fused with the step's normalisation and the
+// Lanczos alpha dot.  These replace the user `matmul` callback and the three lines around it
+// (lanczos.hpp:439-448, arnoldi.hpp:365-372): u = w/beta ; v = A u ; v += shift u ; alpha = <u|v>.
+//   - CSR input converted on the device to SELL-32 (32-row slices, column-major inside a slice):
+//     thread-per-row, fully coalesced value/index streams, x gathered through L1/L2;
+//   - dense row-major GEMV (cfg 1), warp per row;
+//   - matrix-free spin-1/2 Heisenberg chain (cfg 5), thread per basis state;
+//   - legacy host callback (reference signature), staged through pinned host memory.
+// All are HBM-bound; algorithmic bytes per apply are recorded in cmb_op::bytes.
+#include <string.h>
+
+#include <algorithm>
+
+#include "device_utils.cuh"
+#include "op.cuh"
+
+namespace cmb {
+
+// ======================================================================================================
+// SELL-32
+// ======================================================================================================
+template <bool CPLX>
+__global__ void __launch_bounds__(256)
+spmv_sell_kernel(const long long* __restrict__ slice_ptr, const int* __restrict__ col, const double* __restrict__ val,
+                 long long nrows, long long nslices, const double* __restrict__ w, const double* __restrict__ halo,
+                 double* __restrict__ ucol, double* __restrict__ v, double shr, double shi, StepScalars sc,
+                 double* partial, unsigned* ticket) {
+  double inv;
+  if (!step_prologue(sc, inv)) return;
+  const int lane = threadIdx.x & 31;
+  const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  double d0 = 0.0, d1 = 0.0;
+  for (long long slice = gwarp; slice < nslices; slice += nwarps) {
+    const long long base = slice_ptr[slice];
+    const int width = int((slice_ptr[slice + 1] - base) >> 5);
+    const long long r = slice * 32 + lane;
+    const int* cp = col + base + lane;
+    if (CPLX) {
+      const double2* vp = reinterpret_cast<const double2*>(val) + base + lane;
+      const double2* wz = reinterpret_cast<const double2*>(w);
+      const double2* hz = reinterpret_cast<const double2*>(halo);
+      double ar = 0.0, ai = 0.0;
+#pragma unroll 4
+      for (int k = 0; k < width; ++k) {
+        const int c = __ldg(cp + k * 32);
+        const double2 a = __ldg(vp + k * 32);
+        const double2 xv = (c < nrows) ? wz[c] : hz[c - nrows];
+        ar = fma(a.x, xv.x, ar);
+        ar = fma(-a.y, xv.y, ar);
+        ai = fma(a.x, xv.y, ai);
+        ai = fma(a.y, xv.x, ai);
+      }
+      if (r < nrows) {
+        const double2 wi = wz[r];
+        const double ur = wi.x * inv, ui = wi.y * inv;
+        const double yr = ar * inv + (shr * ur - shi * ui);
+        const double yi = ai * inv + (shr * ui + shi * ur);
+        reinterpret_cast<double2*>(ucol)[r] = make_double2(ur, ui);
+        reinterpret_cast<double2*>(v)[r] = make_double2(yr, yi);
+        d0 += ur * yr + ui * yi;  // conj(u) * y
+        d1 += ur * yi - ui * yr;
+      }
+    } else {
+      const double* vp = val + base + lane;
+      double acc = 0.0;
+#pragma unroll 4
+      for (int k = 0; k < width; ++k) {
+        const int c = __ldg(cp + k * 32);
+        const double a = __ldg(vp + k * 32);
+        const double xv = (c < nrows) ? w[c] : halo[c - nrows];
+        acc = fma(a, xv, acc);
+      }
+      if (r < nrows) {
+        const double ui = w[r] * inv;
+        const double y = acc * inv + shr * ui;
+        ucol[r] = ui;
+        v[r] = y;
+        d0 = fma(ui, y, d0);
+      }
+    }
+  }
+  grid_sum_finalize<CPLX ? 2 : 1>(d0, d1, partial, ticket, sc.alpha_slot);
+}
+
+__global__ void sell_width_kernel(const long long* __restrict__ rowptr, long long nrows, long long nslices,
+                                  int* __restrict__ width) {
+  const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gwarp >= nslices) return;
+  const long long r = gwarp * 32 + lane;
+  int len = (r < nrows) ? int(rowptr[r + 1] - rowptr[r]) : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if (lane == 0) width[gwarp] = len;
+}
+
+template <int ES>
+__global__ void sell_fill_kernel(const long long* __restrict__ rowptr, const int* __restrict__ col,
+                                 const double* __restrict__ val, long long nrows, long long nslices,
+                                 const long long* __restrict__ slice_ptr, int* __restrict__ scol,
+                                 double* __restrict__ sval) {
+  const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gwarp >= nslices) return;
+  const long long r = gwarp * 32 + lane;
+  const long long base = slice_ptr[gwarp];
+  const int width = int((slice_ptr[gwarp + 1] - base) >> 5);
+  long long p0 = 0;
+  int len = 0;
+  if (r < nrows) {
+    p0 = rowptr[r];
+    len = int(rowptr[r + 1] - p0);
+  }
+  const int self = int(r < nrows ? r : 0);
+  for (int k = 0; k < width; ++k) {
+    const long long dst = base + (long long)k * 32 + lane;
+    if (k < len) {
+      scol[dst] = col[p0 + k];
+#pragma unroll
+      for (int e = 0; e < ES; ++e) sval[dst * ES + e] = val[(p0 + k) * ES + e];
+    } else {
+      scol[dst] = self;  // padding: zero value, harmless in-range column
+#pragma unroll
+      for (int e = 0; e < ES; ++e) sval[dst * ES + e] = 0.0;
+    }
+  }
+}
+
+struct SellOp : cmb_op {
+  long long nslices = 0;
+  long long* d_slice_ptr = nullptr;
+  int* d_col = nullptr;
+  double* d_val = nullptr;
+  double* d_halo = nullptr;
+  long long padded_nnz = 0, nnz = 0;
+  ~SellOp() override {
+    cudaFree(d_slice_ptr);
+    cudaFree(d_col);
+    cudaFree(d_val);
+    cudaFree(d_halo);
+  }
+  int apply(const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) override {
+    long long blocks = (nslices + 7) / 8;
+    int grid = int(std::min<long long>(blocks, (long long)ctx->num_sms * 8));
+    if (grid < 1) grid = 1;
+    LaunchScope ls(ctx, "spmv_sell");
+    if (cplx)
+      spmv_sell_kernel<true><<<grid, 256, 0, ctx->stream>>>(d_slice_ptr, d_col, d_val, n_local, nslices, w, d_halo, ucol,
+                                                            v, shr, shi, sc, ctx->d_partial, ctx->d_ticket + 1);
+    else
+      spmv_sell_kernel<false><<<grid, 256, 0, ctx->stream>>>(d_slice_ptr, d_col, d_val, n_local, nslices, w, d_halo,
+                                                             ucol, v, shr, shi, sc, ctx->d_partial, ctx->d_ticket + 1);
+    CMB_CUDA(cudaGetLastError());
+    return CMB_OK;
+  }
+};
+
+static int build_sell(SellOp* op, const int64_t* rowptr, const int32_t* col, const void* val) {
+  cmb_ctx* ctx = op->ctx;
+  const int es = op->cplx ? 2 : 1;
+  const long long n = op->n_local;
+  const long long nnz = rowptr[n];
+  op->nnz = nnz;
+  op->nslices = (n + 31) / 32;
+  long long* d_rowptr = nullptr;
+  int* d_ccol = nullptr;
+  double* d_cval = nullptr;
+  int* d_width = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_rowptr);
+    cudaFree(d_ccol);
+    cudaFree(d_cval);
+    cudaFree(d_width);
+  };
+  int rc = [&]() -> int {
+    CMB_CUDA(cudaMalloc(&d_rowptr, sizeof(long long) * (n + 1)));
+    CMB_CUDA(cudaMalloc(&d_ccol, sizeof(int) * std::max<long long>(nnz, 1)));
+    CMB_CUDA(cudaMalloc(&d_cval, sizeof(double) * es * std::max<long long>(nnz, 1)));
+    CMB_CUDA(cudaMalloc(&d_width, sizeof(int) * std::max<long long>(op->nslices, 1)));
+    CMB_CUDA(cudaMemcpyAsync(d_rowptr, rowptr, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CMB_CUDA(cudaMemcpyAsync(d_ccol, col, sizeof(int) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+    CMB_CUDA(cudaMemcpyAsync(d_cval, val, sizeof(double) * es * nnz, cudaMemcpyHostToDevice, ctx->stream));
+    const int threads = 256;
+    const long long nthreads = op->nslices * 32;
+    const int grid = int((nthreads + threads - 1) / threads);
+    if (op->nslices > 0) {
+      LaunchScope ls(ctx, "sell_build");
+      sell_width_kernel<<<grid, threads, 0, ctx->stream>>>(d_rowptr, n, op->nslices, d_width);
+    }
+    CMB_CUDA(cudaGetLastError());
+    std::vector<int> width(op->nslices);
+    CMB_CUDA(cudaMemcpyAsync(width.data(), d_width, sizeof(int) * op->nslices, cudaMemcpyDeviceToHost, ctx->stream));
+    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<long long> sp(op->nslices + 1);
+    sp[0] = 0;
+    for (long long s = 0; s < op->nslices; ++s) sp[s + 1] = sp[s] + (long long)width[s] * 32;
+    op->padded_nnz = sp[op->nslices];
+    CMB_CUDA(cudaMalloc(&op->d_slice_ptr, sizeof(long long) * (op->nslices + 1)));
+    CMB_CUDA(cudaMalloc(&op->d_col, sizeof(int) * std::max<long long>(op->padded_nnz, 1)));
+    CMB_CUDA(cudaMalloc(&op->d_val, sizeof(double) * es * std::max<long long>(op->padded_nnz, 1)));
+    CMB_CUDA(cudaMemcpyAsync(op->d_slice_ptr, sp.data(), sizeof(long long) * (op->nslices + 1), cudaMemcpyHostToDevice,
+                             ctx->stream));
+    if (op->nslices > 0) {
+      LaunchScope ls(ctx, "sell_build");
+      if (es == 2)
+        sell_fill_kernel<2><<<grid, threads, 0, ctx->stream>>>(d_rowptr, d_ccol, d_cval, n, op->nslices,
+                                                               op->d_slice_ptr, op->d_col, op->d_val);
+      else
+        sell_fill_kernel<1><<<grid, threads, 0, ctx->stream>>>(d_rowptr, d_ccol, d_cval, n, op->nslices,
+                                                               op->d_slice_ptr, op->d_col, op->d_val);
+    }
+    CMB_CUDA(cudaGetLastError());
+    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CMB_OK;
+  }();
+  cleanup();
+  return rc;
+}
+
+// ======================================================================================================
+// dense row-major GEMV (single rank)
+// ======================================================================================================
+template <bool CPLX>
+__global__ void __launch_bounds__(256)
+dense_apply_kernel(const double* __restrict__ A, long long n, const double* __restrict__ w, double* __restrict__ ucol,
+                   double* __restrict__ v, double shr, double shi, StepScalars sc, double* partial, unsigned* ticket) {
+  double inv;
+  if (!step_prologue(sc, inv)) return;
+  const int lane = threadIdx.x & 31;
+  const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  double d0 = 0.0, d1 = 0.0;
+  for (long long r = gwarp; r < n; r += nwarps) {
+    if (CPLX) {
+      const double2* row = reinterpret_cast<const double2*>(A) + r * n;
+      const double2* wz = reinterpret_cast<const double2*>(w);
+      double ar = 0.0, ai = 0.0;
+      for (long long c = lane; c < n; c += 32) {
+        const double2 a = __ldg(row + c);
+        const double2 xv = wz[c];
+        ar = fma(a.x, xv.x, ar);
+        ar = fma(-a.y, xv.y, ar);
+        ai = fma(a.x, xv.y, ai);
+        ai = fma(a.y, xv.x, ai);
+      }
+      ar = warp_sum(ar);
+      ai = warp_sum(ai);
+      if (lane == 0) {
+        const double2 wi = wz[r];
+        const double ur = wi.x * inv, ui = wi.y * inv;
+        const double yr = ar * inv + (shr * ur - shi * ui);
+        const double yi = ai * inv + (shr * ui + shi * ur);
+        reinterpret_cast<double2*>(ucol)[r] = make_double2(ur, ui);
+        reinterpret_cast<double2*>(v)[r] = make_double2(yr, yi);
+        d0 += ur * yr + ui * yi;
+        d1 += ur * yi - ui * yr;
+      }
+    } else {
+      const double* row = A + r * n;
+      double acc = 0.0;
+      for (long long c = lane; c < n; c += 32) acc = fma(__ldg(row + c), w[c], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const double ui = w[r] * inv;
+        const double y = acc * inv + shr * ui;
+        ucol[r] = ui;
+        v[r] = y;
+        d0 = fma(ui, y, d0);
+      }
+    }
+  }
+  grid_sum_finalize<CPLX ? 2 : 1>(d0, d1, partial, ticket, sc.alpha_slot);
+}
+
+struct DenseOp : cmb_op {
+  double* d_a = nullptr;
+  ~DenseOp() override { cudaFree(d_a); }
+  int apply(const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) override {
+    int grid = int(std::min<long long>((n_local + 7) / 8, (long long)ctx->num_sms * 8));
+    if (grid < 1) grid = 1;
+    LaunchScope ls(ctx, "gemv_dense");
+    if (cplx)
+      dense_apply_kernel<true><<<grid, 256, 0, ctx->stream>>>(d_a, n_local, w, ucol, v, shr, shi, sc, ctx->d_partial,
+                                                              ctx->d_ticket + 1);
+    else
+      dense_apply_kernel<false><<<grid, 256, 0, ctx->stream>>>(d_a, n_local, w, ucol, v, shr, shi, sc, ctx->d_partial,
+                                                               ctx->d_ticket + 1);
+    CMB_CUDA(cudaGetLastError());
+    return CMB_OK;
+  }
+};
+
+// ======================================================================================================
+// matrix-free Heisenberg chain (single rank; bit i of the state index = spin i)
+// ======================================================================================================
+template <bool CPLX>
+__global__ void __launch_bounds__(256)
+heis_apply_kernel(int L, int nb, double J, const double* __restrict__ w, double* __restrict__ ucol,
+                  double* __restrict__ v, double shr, double shi, StepScalars sc, double* partial, unsigned* ticket) {
+  double inv;
+  if (!step_prologue(sc, inv)) return;
+  const long long dim = 1ll << L;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double d0 = 0.0, d1 = 0.0;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < dim; s += stride) {
+    int aligned = 0;
+    double ar = 0.0, ai = 0.0;
+    for (int b = 0; b < nb; ++b) {
+      const int i = b, j = (b + 1 == L) ? 0 : b + 1;
+      if (((s >> i) ^ (s >> j)) & 1) {
+        const long long t = s ^ ((1ll << i) | (1ll << j));
+        if (CPLX) {
+          const double2 xv = reinterpret_cast<const double2*>(w)[t];
+          ar += xv.x;
+          ai += xv.y;
+        } else {
+          ar += w[t];
+        }
+      } else {
+        ++aligned;
+      }
+    }
+    const double diag = 0.25 * J * double(2 * aligned - nb);
+    if (CPLX) {
+      const double2 wi = reinterpret_cast<const double2*>(w)[s];
+      const double ur = wi.x * inv, ui = wi.y * inv;
+      const double yr = (diag * wi.x + 0.5 * J * ar) * inv + (shr * ur - shi * ui);
+      const double yi = (diag * wi.y + 0.5 * J * ai) * inv + (shr * ui + shi * ur);
+      reinterpret_cast<double2*>(ucol)[s] = make_double2(ur, ui);
+      reinterpret_cast<double2*>(v)[s] = make_double2(yr, yi);
+      d0 += ur * yr + ui * yi;
+      d1 += ur * yi - ui * yr;
+    } else {
+      const double wi = w[s];
+      const double ui = wi * inv;
+      const double y = (diag * wi + 0.5 * J * ar) * inv + shr * ui;
+      ucol[s] = ui;
+      v[s] = y;
+      d0 = fma(ui, y, d0);
+    }
+  }
+  grid_sum_finalize<CPLX ? 2 : 1>(d0, d1, partial, ticket, sc.alpha_slot);
+}
+
+struct HeisenbergOp : cmb_op {
+  int L = 0, nb = 0;
+  double J = 1.0;
+  int apply(const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) override {
+    int grid = int(std::min<long long>((n_local + 255) / 256, (long long)ctx->num_sms * 8));
+    LaunchScope ls(ctx, "heisenberg_mf");
+    if (cplx)
+      heis_apply_kernel<true><<<grid, 256, 0, ctx->stream>>>(L, nb, J, w, ucol, v, shr, shi, sc, ctx->d_partial,
+                                                             ctx->d_ticket + 1);
+    else
+      heis_apply_kernel<false><<<grid, 256, 0, ctx->stream>>>(L, nb, J, w, ucol, v, shr, shi, sc, ctx->d_partial,
+                                                              ctx->d_ticket + 1);
+    CMB_CUDA(cudaGetLastError());
+    return CMB_OK;
+  }
+};
+
+// ======================================================================================================
+// legacy host callback (lanczos.hpp:116,389,442): device -> pinned host -> user function -> device
+// ======================================================================================================
+__global__ void scale_step_kernel(const double* __restrict__ w, double* __restrict__ ucol, long long nd,
+                                  StepScalars sc) {
+  double inv;
+  if (!step_prologue(sc, inv)) return;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += stride) ucol[i] = w[i] * inv;
+}
+
+struct CallbackOp : cmb_op {
+  cmb_matmul_fn fn = nullptr;
+  void* user = nullptr;
+  double* h_in = nullptr;   // pinned
+  double* h_out = nullptr;  // pinned
+  int* h_halt = nullptr;    // pinned
+  ~CallbackOp() override {
+    cudaFreeHost(h_in);
+    cudaFreeHost(h_out);
+    cudaFreeHost(h_halt);
+  }
+  int apply(const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) override {
+    const int es = cplx ? 2 : 1;
+    const long long nd = n_local * es;
+    {
+      LaunchScope ls(ctx, "callback_scale");
+      int grid = int(std::min<long long>((nd + 255) / 256, (long long)ctx->num_sms * 8));
+      scale_step_kernel<<<grid, 256, 0, ctx->stream>>>(w, ucol, nd, sc);
+    }
+    CMB_CUDA(cudaGetLastError());
+    CMB_CUDA(cudaMemcpyAsync(h_halt, sc.halt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CMB_CUDA(cudaMemcpyAsync(h_in, ucol, sizeof(double) * nd, cudaMemcpyDeviceToHost, ctx->stream));
+    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*h_halt) return CMB_OK;
+    fn(h_in, h_out, user);  // exceptions from C++ callers propagate through the header layer, not through here
+    CMB_CUDA(cudaMemcpyAsync(v, h_out, sizeof(double) * nd, cudaMemcpyHostToDevice, ctx->stream));
+    const long long ldp = (nd + 511) / 512 * 512;  // padded length; pads are zero
+    if (shr != 0.0 || shi != 0.0) CMB_TRY(vec_axpy_shift(ctx, cplx, shr, shi, ucol, v, ldp, sc.halt));
+    CMB_TRY(vec_dot(ctx, cplx, ucol, v, ldp, sc.alpha_slot, sc.halt));
+    return CMB_OK;
+  }
+};
+
+}  // namespace cmb
+
+using namespace cmb;
+
+static int op_common(cmb_op* op, cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t rb, int64_t re) {
+  op->ctx = ctx;
+  op->dtype = dtype;
+  op->cplx = dtype == CMB_C64;
+  op->n_global = n_global;
+  op->row_begin = rb;
+  op->n_local = re - rb;
+  return CMB_OK;
+}
+
+extern "C" {
+
+int cmb_op_csr_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t row_begin, int64_t row_end,
+                      const int64_t* rowptr, const int32_t* col, const void* val, cmb_op** out) {
+  CMB_REQUIRE(ctx && out && rowptr, "null argument");
+  *out = nullptr;
+  CMB_REQUIRE(dtype == CMB_F64 || dtype == CMB_C64, "dtype must be CMB_F64 or CMB_C64");
+  CMB_REQUIRE(n_global >= 0 && row_begin >= 0 && row_begin <= row_end && row_end <= n_global, "bad row range");
+  CMB_REQUIRE(n_global < (int64_t(1) << 31), "column indices are 32-bit: n_global must be < 2^31");
+  const int64_t n = row_end - row_begin;
+  CMB_REQUIRE(rowptr[0] == 0 && rowptr[n] >= 0, "rowptr must start at 0");
+  CMB_REQUIRE(rowptr[n] == 0 || (col && val), "null col/val");
+  if (ctx->nranks > 1) {
+    set_error("distributed CSR operators: use cmb_op_csr_create on a single-rank context in this build");
+    return CMB_ERR_UNSUPPORTED;
+  }
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  SellOp* op = new (std::nothrow) SellOp();
+  if (!op) return CMB_ERR_NOMEM;
+  op_common(op, ctx, dtype, n_global, row_begin, row_end);
+  op->family = "spmv_sell";
+  int rc = build_sell(op, rowptr, col, val);
+  if (rc != CMB_OK) {
+    delete op;
+    return rc;
+  }
+  const double s = op->cplx ? 16.0 : 8.0;
+  // nnz*(s+idx) + (n+1)*ptr + 2*n*s with idx = ptr = 4
+  op->bytes = double(op->nnz) * (s + 4.0) + double(n + 1) * 4.0 + 2.0 * double(n) * s;
+  *out = op;
+  return CMB_OK;
+}
+
+int cmb_op_dense_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t row_begin, int64_t row_end,
+                        const void* a_rows, cmb_op** out) {
+  CMB_REQUIRE(ctx && out, "null argument");
+  *out = nullptr;
+  CMB_REQUIRE(dtype == CMB_F64 || dtype == CMB_C64, "dtype must be CMB_F64 or CMB_C64");
+  CMB_REQUIRE(row_begin == 0 && row_end == n_global && n_global >= 0, "dense operators are single-rank (full rows)");
+  CMB_REQUIRE(n_global == 0 || a_rows, "null matrix");
+  if (ctx->nranks > 1) {
+    set_error("dense operators are not row-partitioned in this build");
+    return CMB_ERR_UNSUPPORTED;
+  }
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  DenseOp* op = new (std::nothrow) DenseOp();
+  if (!op) return CMB_ERR_NOMEM;
+  op_common(op, ctx, dtype, n_global, row_begin, row_end);
+  op->family = "gemv_dense";
+  const double s = op->cplx ? 16.0 : 8.0;
+  const size_t bytes = size_t(double(n_global) * double(n_global) * s);
+  if (cudaMalloc(&op->d_a, std::max<size_t>(bytes, 16)) != cudaSuccess) {
+    cudaGetLastError();
+    delete op;
+    set_error("out of device memory for a %lld x %lld dense operator", (long long)n_global, (long long)n_global);
+    return CMB_ERR_NOMEM;
+  }
+  if (bytes) {
+    cudaError_t e = cudaMemcpy(op->d_a, a_rows, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      delete op;
+      set_error("copying the dense operator failed: %s", cudaGetErrorString(e));
+      return CMB_ERR_CUDA;
+    }
+  }
+  op->bytes = double(n_global) * double(n_global) * s + 2.0 * double(n_global) * s;
+  *out = op;
+  return CMB_OK;
+}
+
+int cmb_op_heisenberg_create(cmb_ctx* ctx, cmb_dtype dtype, int L, double J, int pbc, cmb_op** out) {
+  CMB_REQUIRE(ctx && out, "null argument");
+  *out = nullptr;
+  CMB_REQUIRE(dtype == CMB_F64 || dtype == CMB_C64, "dtype must be CMB_F64 or CMB_C64");
+  CMB_REQUIRE(L >= 2 && L <= 40, "chain length out of range");
+  if (ctx->nranks > 1) {
+    set_error("the matrix-free Heisenberg operator is single-rank in this build");
+    return CMB_ERR_UNSUPPORTED;
+  }
+  HeisenbergOp* op = new (std::nothrow) HeisenbergOp();
+  if (!op) return CMB_ERR_NOMEM;
+  op_common(op, ctx, dtype, int64_t(1) << L, 0, int64_t(1) << L);
+  op->family = "heisenberg_mf";
+  op->L = L;
+  op->J = J;
+  op->nb = (pbc && L > 2) ? L : L - 1;
+  op->bytes = 2.0 * double(op->n_local) * (op->cplx ? 16.0 : 8.0);  // B_mf = 2 n s
+  *out = op;
+  return CMB_OK;
+}
+
+int cmb_op_callback_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n, cmb_matmul_fn fn, void* user, cmb_op** out) {
+  CMB_REQUIRE(ctx && out && fn, "null argument");
+  *out = nullptr;
+  CMB_REQUIRE(dtype == CMB_F64 || dtype == CMB_C64, "dtype must be CMB_F64 or CMB_C64");
+  CMB_REQUIRE(n >= 0, "negative height");
+  if (ctx->nranks > 1) {
+    set_error("host-callback operators are single-rank");
+    return CMB_ERR_UNSUPPORTED;
+  }
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  CallbackOp* op = new (std::nothrow) CallbackOp();
+  if (!op) return CMB_ERR_NOMEM;
+  op_common(op, ctx, dtype, n, 0, n);
+  op->family = "callback";
+  op->fn = fn;
+  op->user = user;
+  const size_t bytes = std::max<size_t>(size_t(n) * (op->cplx ? 16 : 8), 16);
+  if (cudaMallocHost(&op->h_in, bytes) != cudaSuccess || cudaMallocHost(&op->h_out, bytes) != cudaSuccess ||
+      cudaMallocHost(&op->h_halt, sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    delete op;
+    set_error("out of pinned host memory for the callback staging buffers");
+    return CMB_ERR_NOMEM;
+  }
+  op->bytes = 2.0 * double(n) * (op->cplx ? 16.0 : 8.0);
+  *out = op;
+  return CMB_OK;
+}
+
+int cmb_op_destroy(cmb_op* op) {
+  if (!op) return CMB_OK;
+  cudaSetDevice(op->ctx->device);
+  cudaStreamSynchronize(op->ctx->stream);
+  delete op;
+  return CMB_OK;
+}
+
+cmb_ctx* cmb_op_context(const cmb_op* op) { return op ? op->ctx : nullptr; }
+int64_t cmb_op_row_begin(const cmb_op* op) { return op ? op->row_begin : 0; }
+int64_t cmb_op_rows(const cmb_op* op) { return op ? op->n_local : 0; }
+int64_t cmb_op_height(const cmb_op* op) { return op ? op->n_global : 0; }
+int cmb_op_dtype(const cmb_op* op) { return op ? op->dtype : -1; }
+double cmb_op_bytes(const cmb_op* op) { return op ? op->bytes : 0.0; }
+
+int cmb_op_apply_host(cmb_op* op, const void* x, void* y) {
+  CMB_REQUIRE(op && (op->n_local == 0 || (x && y)), "null argument");
+  cmb_ctx* ctx = op->ctx;
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  const int es = op->cplx ? 2 : 1;
+  const int64_t nd = op->n_local * es;
+  if (nd == 0) return CMB_OK;
+  const int64_t ld = (nd + 511) / 512 * 512;
+  double* buf = nullptr;
+  CMB_CUDA(cudaMalloc(&buf, sizeof(double) * (3 * ld + 8)));
+  int rc = [&]() -> int {
+    double *w = buf, *u = buf + ld, *v = buf + 2 * ld, *sc = buf + 3 * ld;
+    CMB_CUDA(cudaMemsetAsync(buf, 0, sizeof(double) * (3 * ld + 8), ctx->stream));
+    CMB_CUDA(cudaMemcpyAsync(w, x, sizeof(double) * nd, cudaMemcpyHostToDevice, ctx->stream));
+    const double one = 1.0;
+    CMB_CUDA(cudaMemcpyAsync(sc, &one, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    StepScalars s;
+    s.nrm2 = sc;
+    s.threshold = -1.0;
+    s.halt = reinterpret_cast<int*>(sc + 1);
+    s.beta_slot = sc + 2;
+    s.alpha_slot = sc + 4;
+    CMB_TRY(op->apply(w, u, v, 0.0, 0.0, s));
+    CMB_CUDA(cudaMemcpyAsync(y, v, sizeof(double) * nd, cudaMemcpyDeviceToHost, ctx->stream));
+    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CMB_OK;
+  }();
+  cudaFree(buf);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+// detail/dense.hpp — value types of the public API.
+//
+// The reference expresses its API in Eigen types (lanczos.hpp:473-482: VectorType, RealVectorType,
+// MatrixType = Eigen::Matrix<Scalar,...>, Index = Eigen::Index).  When Eigen is on the include path the
+// same types are used here, so existing user code keeps compiling.  When it is not (this build image has
+// no Eigen), a minimal column-major Vector/Matrix with the member names the samples use
+// (.data() .size() .rows() .cols() (i,j) [i] .col(j) .norm() .dot()) stands in.
+#ifndef CMPT_EIGEN_EX_DETAIL_DENSE_HPP_
+#define CMPT_EIGEN_EX_DETAIL_DENSE_HPP_
+
+#include <cmath>
+#include <complex>
+#include <cstddef>
+#include <ostream>
+#include <vector>
+
+#if !defined(CMPT_EIGENEX_NO_EIGEN) && defined(__has_include)
+#if __has_include("Eigen/Core")
+#define CMPT_EIGENEX_HAVE_EIGEN 1
+#endif
+#endif
+
+#ifdef CMPT_EIGENEX_HAVE_EIGEN
+#include "Eigen/Core"
+#endif
+
+namespace cmpt {
+namespace EigenEx {
+
+template <class S>
+struct RealOf {
+  using type = S;
+};
+template <class R>
+struct RealOf<std::complex<R>> {
+  using type = R;
+};
+
+namespace detail {
+inline double conj_(double a) { return a; }
+inline float conj_(float a) { return a; }
+template <class R>
+inline std::complex<R> conj_(const std::complex<R>& a) {
+  return std::conj(a);
+}
+inline double real_(double a) { return a; }
+template <class R>
+inline R real_(const std::complex<R>& a) {
+  return a.real();
+}
+}  // namespace detail
+
+#ifdef CMPT_EIGENEX_HAVE_EIGEN
+
+using Index = Eigen::Index;
+template <class S>
+using Vector = Eigen::Matrix<S, Eigen::Dynamic, 1>;
+template <class S>
+using Matrix = Eigen::Matrix<S, Eigen::Dynamic, Eigen::Dynamic>;
+
+#else
+
+using Index = std::ptrdiff_t;
+
+template <class S>
+class Vector {
+ public:
+  using Scalar = S;
+  using RealScalar = typename RealOf<S>::type;
+  Vector() {}
+  explicit Vector(Index n) : d_(static_cast<std::size_t>(n)) {}
+  Vector(Index n, const S& v) : d_(static_cast<std::size_t>(n), v) {}
+  Vector(const S* p, Index n) : d_(p, p + n) {}
+  static Vector Zero(Index n) { return Vector(n, S(0)); }
+  Index size() const { return static_cast<Index>(d_.size()); }
+  Index rows() const { return size(); }
+  Index cols() const { return 1; }
+  void resize(Index n) { d_.resize(static_cast<std::size_t>(n)); }
+  S* data() { return d_.data(); }
+  const S* data() const { return d_.data(); }
+  S& operator[](Index i) { return d_[static_cast<std::size_t>(i)]; }
+  const S& operator[](Index i) const { return d_[static_cast<std::size_t>(i)]; }
+  S& operator()(Index i) { return d_[static_cast<std::size_t>(i)]; }
+  const S& operator()(Index i) const { return d_[static_cast<std::size_t>(i)]; }
+  // <this|other>: conjugates *this, as Eigen's dot()
+  S dot(const Vector& o) const {
+    S s = S(0);
+    for (std::size_t i = 0; i < d_.size(); ++i) s += detail::conj_(d_[i]) * o.d_[i];
+    return s;
+  }
+  RealScalar squaredNorm() const {
+    RealScalar s = 0;
+    for (const S& x : d_) s += std::norm(x);
+    return s;
+  }
+  RealScalar norm() const { return std::sqrt(squaredNorm()); }
+  void normalize() {
+    RealScalar n = norm();
+    if (n > RealScalar(0))
+      for (S& x : d_) x /= n;
+  }
+  Vector normalized() const {
+    Vector r(*this);
+    r.normalize();
+    return r;
+  }
+  Vector& operator*=(const S& a) {
+    for (S& x : d_) x *= a;
+    return *this;
+  }
+  Vector& operator+=(const Vector& o) {
+    for (std::size_t i = 0; i < d_.size(); ++i) d_[i] += o.d_[i];
+    return *this;
+  }
+  Vector& operator-=(const Vector& o) {
+    for (std::size_t i = 0; i < d_.size(); ++i) d_[i] -= o.d_[i];
+    return *this;
+  }
+
+ private:
+  std::vector<S> d_;
+};
+
+template <class S>
+class Matrix {
+ public:
+  using Scalar = S;
+  Matrix() : r_(0), c_(0) {}
+  Matrix(Index r, Index c) : r_(r), c_(c), d_(static_cast<std::size_t>(r * c)) {}
+  static Matrix Zero(Index r, Index c) {
+    Matrix m(r, c);
+    for (S& x : m.d_) x = S(0);
+    return m;
+  }
+  static Matrix Identity(Index r, Index c) {
+    Matrix m = Zero(r, c);
+    for (Index i = 0; i < (r < c ? r : c); ++i) m(i, i) = S(1);
+    return m;
+  }
+  Index rows() const { return r_; }
+  Index cols() const { return c_; }
+  Index size() const { return r_ * c_; }
+  void resize(Index r, Index c) {
+    r_ = r;
+    c_ = c;
+    d_.resize(static_cast<std::size_t>(r * c));
+  }
+  S* data() { return d_.data(); }
+  const S* data() const { return d_.data(); }
+  S& operator()(Index i, Index j) { return d_[static_cast<std::size_t>(j * r_ + i)]; }
+  const S& operator()(Index i, Index j) const { return d_[static_cast<std::size_t>(j * r_ + i)]; }
+  // column j as a vector (copy)
+  Vector<S> col(Index j) const { return Vector<S>(d_.data() + j * r_, r_); }
+  void setCol(Index j, const Vector<S>& v) {
+    for (Index i = 0; i < r_; ++i) (*this)(i, j) = v[i];
+  }
+
+ private:
+  Index r_, c_;
+  std::vector<S> d_;
+};
+
+template <class S>
+std::ostream& operator<<(std::ostream& os, const Vector<S>& v) {
+  for (Index i = 0; i < v.size(); ++i) os << v[i] << (i + 1 < v.size() ? "\n" : "");
+  return os;
+}
+template <class S>
+std::ostream& operator<<(std::ostream& os, const Matrix<S>& m) {
+  for (Index i = 0; i < m.rows(); ++i) {
+    for (Index j = 0; j < m.cols(); ++j) os << m(i, j) << (j + 1 < m.cols() ? " " : "");
+    if (i + 1 < m.rows()) os << "\n";
+  }
+  return os;
+}
+
+#endif  // CMPT_EIGENEX_HAVE_EIGEN
+
+}  // namespace EigenEx
+}  // namespace cmpt
+
+#endif

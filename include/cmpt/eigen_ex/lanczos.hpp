@@ -1,0 +1,672 @@
+// lanczos.hpp — drop-in for versmc/cmpt-eigenex include/cmpt/eigen_ex/lanczos.hpp on B200.
+//
+// Same namespace (cmpt::EigenEx), class names, setters/getters, log strings and stop logic as the
+// reference (file:line cited at each member).  What changed is where the work happens: the Krylov basis,
+// the work vectors and (optionally) the operator live in HBM, and every Lanczos step runs as hand-written
+// sm_100a kernels behind the C-ABI of include/cmpt_b200.h.  The m x m tridiagonal Ritz problem is solved
+// on the host (detail/tridiag_eigen.hpp), as in the reference.
+//
+// Additive API (not in the reference): setMatrixMultiplication(DeviceOperator), updateLanczosSteps(n),
+// ritzResiduals(), deviceBytes().
+//
+// Differences a user can observe:
+//  * full reorthogonalisation (interval 1) is classical Gram-Schmidt applied twice (CGS2) instead of one
+//    modified Gram-Schmidt sweep (lanczos.hpp:411-426): alpha/beta agree to ~1e-14;
+//  * lanczosvectors() / eigenvectors() are copied from the device on demand;
+//  * Scalar must be double or std::complex<double>.
+#ifndef CMPT_EIGEN_EX_LANCZOS_HPP_
+#define CMPT_EIGEN_EX_LANCZOS_HPP_
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <functional>
+#include <map>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "detail/krylov_device.hpp"
+#include "detail/tridiag_eigen.hpp"
+#include "device.hpp"
+#include "random.hpp"
+
+namespace cmpt {
+namespace EigenEx {
+
+/// default value to judge the convergence (lanczos.hpp:62-83): double -> 1e-12, float -> 1e-4
+template <class Scalar>
+class DefaultTolerance {
+ protected:
+  template <class S, class AlwaysBool>
+  struct Dummy {
+    static constexpr S value() { return 1.0e-12; }
+  };
+  template <class AlwaysBool>
+  struct Dummy<float, AlwaysBool> {
+    static constexpr float value() { return 1.0e-4f; }
+  };
+
+ public:
+  static constexpr Scalar value() { return Dummy<Scalar, bool>::value(); }
+};
+
+/// Stand-in for Eigen::SelfAdjointEigenSolver restricted to computeFromTridiagonal (lanczos.hpp:637).
+template <class Scalar>
+class TridiagonalEigenSolver {
+ public:
+  using RealScalar = typename RealOf<Scalar>::type;
+  using RealVectorType = Vector<RealScalar>;
+  using MatrixType = Matrix<Scalar>;  // the reference types the eigenvectors as Matrix<Scalar> (lanczos.hpp:479)
+
+  /// eigen-decomposition of the tridiagonal matrix (diag, subdiag); only subdiag[0..n-2] is read
+  template <class V1, class V2>
+  TridiagonalEigenSolver& computeFromTridiagonal(const V1& diag, const V2& subdiag, bool computeVectors = true) {
+    return computeRaw(diag.data(), subdiag.data(), static_cast<int>(diag.size()), computeVectors);
+  }
+  TridiagonalEigenSolver& computeRaw(const RealScalar* diag, const RealScalar* subdiag, int n, bool computeVectors) {
+    std::vector<RealScalar> w, z;
+    bool ok;
+    if (computeVectors)
+      ok = detail::tridiagonal_eigensystem<RealScalar>(diag, subdiag, n, w, z);
+    else
+      ok = detail::tridiagonal_eigenvalues<RealScalar>(diag, subdiag, n, w);
+    converged_ = ok;
+    eivals_.resize(n);
+    for (int i = 0; i < n; ++i) eivals_[i] = w[i];
+    if (computeVectors) {
+      eivecs_.resize(n, n);
+      for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) eivecs_(i, j) = Scalar(z[static_cast<std::size_t>(j) * n + i]);
+    } else {
+      eivecs_.resize(0, 0);
+    }
+    return *this;
+  }
+  const RealVectorType& eigenvalues() const { return eivals_; }
+  const MatrixType& eigenvectors() const { return eivecs_; }
+  bool converged() const { return converged_; }
+
+ private:
+  RealVectorType eivals_;
+  MatrixType eivecs_;
+  bool converged_ = true;
+};
+
+/// This class generates the basis of the Krylov subspace (lanczos.hpp:104-461):
+/// Lanczos vectors (device resident), alpha (diagonal), beta (sub-diagonal).
+template <class Scalar_>
+class LanczosBase {
+ public:
+  using Index = EigenEx::Index;
+  using Scalar = Scalar_;
+  using RealScalar = typename RealOf<Scalar>::type;
+  using VectorType = Vector<Scalar>;
+  using RealVectorType = Vector<RealScalar>;
+  using MatrixType = Matrix<Scalar>;
+  using ScalarDistribution = typename NormalDistributionGen<Scalar>::Type;
+  using VectorDistribution = typename EigenEx::VectorDistribution<ScalarDistribution>;
+  using MatMulFunction = std::function<void(const Scalar*, Scalar*)>;
+
+  /// make random normalized vector (lanczos.hpp:124-135)
+  template <class URBG>
+  static VectorType makeRandomVector(URBG& g, Index size) {
+    VectorDistribution vdist(ScalarDistribution(), size, true);
+    return vdist(g);
+  }
+
+ protected:
+  Index reserveSize_;
+  std::vector<VectorType> orthogonalizingVectors_;
+  MatMulFunction matrixMultiplication_;
+  DeviceOperator<Scalar> deviceOperator_;  // additive: operator resident in HBM
+  RealScalar eigenvalueShift_;
+  Index matrixHeight_;
+  Index reorthogonalizeInterval_;
+  VectorType initialVector_;
+  RealScalar threshold_;
+
+ public:
+  // accessors for parameters of settings of lanczos computing (lanczos.hpp:160-226)
+  Index reserveSize() const { return reserveSize_; }
+  LanczosBase& setReserveSize(Index resSize) {
+    reserveSize_ = resSize;
+    return *this;
+  }
+  const std::vector<VectorType>& orthogonalizingVectors() const { return orthogonalizingVectors_; }
+  std::vector<VectorType>& refOrthogonalizingVectors() { return orthogonalizingVectors_; }
+  LanczosBase& setOrthogonalizingVectors(const std::vector<VectorType>& orthoVec) {
+    orthogonalizingVectors_ = orthoVec;
+    return *this;
+  }
+  LanczosBase& setOrthogonalizingVectors(std::vector<VectorType>&& orthoVec) {
+    orthogonalizingVectors_.swap(orthoVec);
+    return *this;
+  }
+  const MatMulFunction& matrixMultiplication() const { return matrixMultiplication_; }
+  LanczosBase& setMatrixMultiplication(const MatMulFunction& matmul, Index height) {
+    matrixMultiplication_ = matmul;
+    deviceOperator_ = DeviceOperator<Scalar>();
+    matrixHeight_ = height;
+    return *this;
+  }
+  LanczosBase& setMatrixMultiplication(MatMulFunction&& matmul, Index height) {
+    std::swap(matrixMultiplication_, matmul);
+    deviceOperator_ = DeviceOperator<Scalar>();
+    matrixHeight_ = height;
+    return *this;
+  }
+  /// additive overload: operator resident in HBM (CSR/SELL, dense, matrix-free); no per-step host traffic
+  LanczosBase& setMatrixMultiplication(const DeviceOperator<Scalar>& op) {
+    deviceOperator_ = op;
+    DeviceOperator<Scalar> held = op;
+    matrixMultiplication_ = [held](const Scalar* in, Scalar* out) { held.apply(in, out); };
+    matrixHeight_ = op.height();
+    return *this;
+  }
+  const DeviceOperator<Scalar>& deviceOperator() const { return deviceOperator_; }
+  Index matrixHeight() const { return matrixHeight_; }
+  RealScalar eigenvalueShift() const { return eigenvalueShift_; }
+  LanczosBase& setEigenvalueShift(RealScalar eishift) {
+    eigenvalueShift_ = eishift;
+    return *this;
+  }
+  bool reorthogonalizeInterval() const { return reorthogonalizeInterval_; }  // sic: bool (lanczos.hpp:194)
+  LanczosBase& setReorthogonalizeInterval(Index reorthoInterval) {
+    reorthogonalizeInterval_ = reorthoInterval;
+    return *this;
+  }
+  const VectorType& initialVector() const { return initialVector_; }
+  LanczosBase& setInitialVector(const VectorType& inivec) {
+    initialVector_ = inivec;
+    return *this;
+  }
+  LanczosBase& setInitialVector(VectorType&& inivec) {
+    initialVector_ = std::move(inivec);
+    return *this;
+  }
+  /// initial vector of size matrixHeight with random contents, fixed seed (lanczos.hpp:214-218)
+  LanczosBase& setInitialVector() {
+    std::mt19937 rengine;
+    setInitialVector(makeRandomVector(rengine, matrixHeight_));
+    return *this;
+  }
+  RealScalar threshold() const { return threshold_; }
+  LanczosBase& setThreshold(RealScalar thre) {
+    threshold_ = thre;
+    return *this;
+  }
+
+ protected:
+  // computed data: the vectors live on the device; alpha/beta are mirrored on the host
+  Index iterations_;
+  Index nvectors_;
+  mutable std::vector<VectorType> lanczosvectors_;  // host cache of the device basis, filled on demand
+  std::vector<RealScalar> alpha_;
+  std::vector<RealScalar> beta_;
+  detail::KrylovDevice<Scalar> dev_;
+
+ public:
+  Index iterations() const { return iterations_; }
+  /// number of Lanczos vectors (== lanczosvectors().size(), without copying them to the host)
+  Index lanczosvectorsSize() const { return nvectors_; }
+  /// Lanczos vectors, copied from the device on demand (lanczos.hpp:246)
+  const std::vector<VectorType>& lanczosvectors() const {
+    if (static_cast<Index>(lanczosvectors_.size()) > nvectors_) lanczosvectors_.resize(nvectors_);
+    while (static_cast<Index>(lanczosvectors_.size()) < nvectors_) {
+      VectorType v(matrixHeight_);
+      detail::check(cmb_krylov_get_col(dev_.handle(), static_cast<std::int64_t>(lanczosvectors_.size()), v.data()),
+                    "cmb_krylov_get_col");
+      lanczosvectors_.push_back(std::move(v));
+    }
+    return lanczosvectors_;
+  }
+  const std::vector<RealScalar>& alpha() const { return alpha_; }
+  const std::vector<RealScalar>& beta() const { return beta_; }
+  cmb_krylov* deviceState() const { return dev_.handle(); }
+  /// algorithmic bytes moved by the Krylov steps so far
+  double deviceBytes() const { return dev_.ready() ? cmb_krylov_bytes(dev_.handle()) : 0.0; }
+
+ public:
+  LanczosBase() : iterations_(0), nvectors_(0) { setAllSettingsDefault(); }
+
+  /// default settings; does NOT clear computed data (lanczos.hpp:260-271)
+  LanczosBase& setAllSettingsDefault() {
+    setReserveSize(128);
+    setOrthogonalizingVectors(std::vector<VectorType>());
+    setMatrixMultiplication([](const Scalar*, Scalar*) {}, 0);
+    setEigenvalueShift(0.0);
+    setReorthogonalizeInterval(1);
+    setInitialVector();
+    setThreshold(DefaultTolerance<RealScalar>::value());
+    return *this;
+  }
+
+  /// clears lanczosvectors, alpha, beta; keeps settings (lanczos.hpp:277-283)
+  void clearLanczosSteps() {
+    iterations_ = 0;
+    nvectors_ = 0;
+    lanczosvectors_.clear();
+    alpha_.clear();
+    beta_.clear();
+    if (dev_.ready()) detail::check(cmb_krylov_clear(dev_.handle()), "cmb_krylov_clear");
+  }
+
+  /// clear all data, and set all settings default (lanczos.hpp:289-292)
+  void clear() {
+    clearLanczosSteps();
+    setAllSettingsDefault();
+    dev_.release();
+  }
+
+  /// judge whether the dimension of the Krylov subspace is utmost (lanczos.hpp:331-347)
+  bool lanczosStepIsUtmost() const {
+    if (nvectors_ == matrixHeight_) return true;
+    if (beta_.size() > 0) return beta_.back() <= threshold_;
+    return false;
+  }
+
+  /// one Lanczos step (lanczos.hpp:371-457); false when no step could be done
+  bool updateLanczosSteps() { return updateLanczosSteps(1) == 1; }
+
+  /// additive: up to `count` consecutive calls of updateLanczosSteps() enqueued on the device with a single
+  /// host synchronisation at the end.  Returns how many of them returned true.
+  Index updateLanczosSteps(Index count) {
+    if (matrixHeight_ <= 0) return 0;
+    if (!matrixMultiplication_ && !deviceOperator_) return 0;
+    if (count <= 0) return 0;
+    prepareDevice_();
+    Index done = 0;
+    if (nvectors_ == 0) {
+      if (!setInitialLanczosvector_()) return 0;
+    }
+    std::vector<double> a(static_cast<std::size_t>(count) + 1), b(static_cast<std::size_t>(count) + 1);
+    std::int64_t steps = 0;
+    int status = 0;
+    const bool first = (nvectors_ == 0);
+    int rc = cmb_lanczos_run(dev_.handle(), dev_.op(), eigenvalueShift_, reorthogonalizeInterval_, threshold_, count,
+                             a.data(), b.data(), &steps, &status);
+    dev_.rethrowCallbackError();
+    detail::check(rc, "cmb_lanczos_run");
+    done = static_cast<Index>(steps);
+    const Index nbeta = first ? (done > 0 ? done - 1 : 0) : done;
+    for (Index i = 0; i < done; ++i) alpha_.push_back(a[static_cast<std::size_t>(i)]);
+    for (Index i = 0; i < nbeta; ++i) beta_.push_back(b[static_cast<std::size_t>(i)]);
+    if (status & CMB_STEP_BREAKDOWN) beta_.push_back(b[static_cast<std::size_t>(nbeta)]);  // kept (lanczos.hpp:433-436)
+    nvectors_ += done;
+    iterations_ += nbeta;
+    return done;
+  }
+
+ protected:
+  void prepareDevice_() {
+    Index reserve = reserveSize_;
+    dev_.prepare(deviceOperator_, matrixMultiplication_, matrixHeight_, reserve);
+  }
+
+  /// lanczos.hpp:299-323; returns false when the start vector has (numerically) no component left
+  bool setInitialLanczosvector_() {
+    if (matrixHeight_ < 0) throw LanczosException("matrixHeight_ < 0");
+    if (matrixHeight_ != static_cast<Index>(initialVector_.size())) setInitialVector();
+    dev_.setDeflation(orthogonalizingVectors_, matrixHeight_);
+    int status = 0;
+    detail::check(cmb_krylov_start(dev_.handle(), initialVector_.data(), threshold_, &status), "cmb_krylov_start");
+    return status == CMB_STEP_OK;
+  }
+};
+
+/// eigen solver with Lanczos method (lanczos.hpp:468-927)
+template <class Scalar_>
+class LanczosEigenSolver {
+ public:
+  using Index = EigenEx::Index;
+  using Scalar = Scalar_;
+  using RealScalar = typename RealOf<Scalar>::type;
+  using VectorType = Vector<Scalar>;
+  using RealVectorType = Vector<RealScalar>;
+  using MatrixType = Matrix<Scalar>;
+  using RealMatrixType = Matrix<Scalar>;  // sic (lanczos.hpp:479)
+  using ScalarDistribution = typename NormalDistributionGen<Scalar>::Type;
+  using VectorDistribution = typename EigenEx::VectorDistribution<ScalarDistribution>;
+  using MatMulFunction = std::function<void(const Scalar*, Scalar*)>;
+
+  // header of log generation (lanczos.hpp:486-489)
+  static std::string headERROR() { return std::string("ERROR     "); }
+  static std::string headWARN() { return std::string("WARN      "); }
+  static std::string headINFO() { return std::string("INFO      "); }
+  static std::string headDEBUG() { return std::string("DEBUG     "); }
+
+  // Index value for special case of minIterations, maxIterations
+  static constexpr Index unlimited = -1;
+
+  template <class URBG>
+  static VectorType makeRandomVector(URBG& g, Index size) {
+    return LanczosBase<Scalar>::makeRandomVector(g, size);
+  }
+
+ protected:
+  Index minIterations_;
+  Index maxIterations_;
+  RealScalar tolerance_;
+  std::vector<Index> indicesForConvergence_;
+  Index maxEigenvalues_;
+  bool computeEigenvectorsOn_;
+
+ public:
+  Index minIterations() const { return minIterations_; }
+  LanczosEigenSolver& setMinIterations(Index miniter) {
+    minIterations_ = miniter;
+    return *this;
+  }
+  Index maxIterations() const { return maxIterations_; }
+  LanczosEigenSolver& setMaxIterations(Index maxiter) {
+    maxIterations_ = maxiter;
+    return *this;
+  }
+  RealScalar tolerance() const { return tolerance_; }
+  LanczosEigenSolver& setTolerance(RealScalar toler) {
+    tolerance_ = toler;
+    return *this;
+  }
+  const std::vector<Index>& indicesForConvergence() const { return indicesForConvergence_; }
+  LanczosEigenSolver& setIndicesForConvergence(const std::vector<Index>& iCovs) {
+    indicesForConvergence_ = iCovs;
+    return *this;
+  }
+  Index maxEigenvalues() const { return maxEigenvalues_; }
+  LanczosEigenSolver& setMaxEigenvalues(Index maxeivals) {
+    maxEigenvalues_ = maxeivals;
+    return *this;
+  }
+  Index computeEigenvectorsOn() const { return computeEigenvectorsOn_; }  // sic: Index (lanczos.hpp:551)
+  LanczosEigenSolver& setComputeEigenvectorsOn(bool cEivecOn) {
+    computeEigenvectorsOn_ = cEivecOn;
+    return *this;
+  }
+
+ protected:
+  LanczosBase<Scalar> lanczosBase_;
+
+ public:  // transparent accessors for lanczosBase (lanczos.hpp:562-628)
+  const LanczosBase<Scalar>& lanczosBase() const { return lanczosBase_; }
+  Index reserveSize() const { return lanczosBase_.reserveSize(); }
+  LanczosEigenSolver& setReserveSize(Index resSize) {
+    lanczosBase_.setReserveSize(resSize);
+    return *this;
+  }
+  const std::vector<VectorType>& orthogonalizingVectors() const { return lanczosBase_.orthogonalizingVectors(); }
+  std::vector<VectorType>& refOrthogonalizingVectors() { return lanczosBase_.refOrthogonalizingVectors(); }
+  LanczosEigenSolver& setOrthogonalizingVectors(const std::vector<VectorType>& orthoVec) {
+    lanczosBase_.setOrthogonalizingVectors(orthoVec);
+    return *this;
+  }
+  LanczosEigenSolver& setOrthogonalizingVectors(std::vector<VectorType>&& orthoVec) {
+    lanczosBase_.setOrthogonalizingVectors(std::move(orthoVec));
+    return *this;
+  }
+  const MatMulFunction& matrixMultiplication() const { return lanczosBase_.matrixMultiplication(); }
+  LanczosEigenSolver& setMatrixMultiplication(const MatMulFunction& matmul, Index height) {
+    lanczosBase_.setMatrixMultiplication(matmul, height);
+    return *this;
+  }
+  LanczosEigenSolver& setMatrixMultiplication(MatMulFunction&& matmul, Index height) {
+    lanczosBase_.setMatrixMultiplication(std::move(matmul), height);
+    return *this;
+  }
+  /// additive overload: operator resident in HBM
+  LanczosEigenSolver& setMatrixMultiplication(const DeviceOperator<Scalar>& op) {
+    lanczosBase_.setMatrixMultiplication(op);
+    return *this;
+  }
+  Index matrixHeight() const { return lanczosBase_.matrixHeight(); }
+  RealScalar eigenvalueShift() const { return lanczosBase_.eigenvalueShift(); }
+  LanczosEigenSolver& setEigenvalueShift(RealScalar eishift) {
+    lanczosBase_.setEigenvalueShift(eishift);
+    return *this;
+  }
+  bool reorthogonalizeInterval() const { return lanczosBase_.reorthogonalizeInterval(); }
+  LanczosEigenSolver& setReorthogonalizeInterval(Index reorthoInterval) {
+    lanczosBase_.setReorthogonalizeInterval(reorthoInterval);
+    return *this;
+  }
+  const VectorType& initialVector() const { return lanczosBase_.initialVector(); }
+  LanczosEigenSolver& setInitialVector(const VectorType& inivec) {
+    lanczosBase_.setInitialVector(inivec);
+    return *this;
+  }
+  LanczosEigenSolver& setInitialVector(VectorType&& inivec) {
+    lanczosBase_.setInitialVector(std::move(inivec));
+    return *this;
+  }
+  LanczosEigenSolver& setInitialVector() {
+    lanczosBase_.setInitialVector();
+    return *this;
+  }
+  RealScalar threshold() const { return lanczosBase_.threshold(); }
+  LanczosEigenSolver& setThreshold(RealScalar thre) {
+    lanczosBase_.setThreshold(thre);
+    return *this;
+  }
+  Index iterations() const { return lanczosBase_.iterations(); }
+  const std::vector<VectorType>& lanczosvectors() const { return lanczosBase_.lanczosvectors(); }
+  const std::vector<RealScalar>& alpha() const { return lanczosBase_.alpha(); }
+  const std::vector<RealScalar>& beta() const { return lanczosBase_.beta(); }
+
+ protected:
+  RealVectorType eigenvalues_;
+  MatrixType eigenvectors_;
+  std::vector<std::string> log_;
+  TridiagonalEigenSolver<Scalar> es_tri_;
+  std::map<Index, std::vector<RealScalar>> convergenceLog_;
+
+ public:
+  const RealVectorType& eigenvalues() const { return eigenvalues_; }
+  const MatrixType& eigenvectors() const { return eigenvectors_; }
+  const std::vector<std::string>& log() const { return log_; }
+  const TridiagonalEigenSolver<Scalar>& es_tri() const { return es_tri_; }
+  const std::map<Index, std::vector<RealScalar>>& convergenceLog() const { return convergenceLog_; }
+
+  /// additive: Ritz residual bounds |beta_last * S(last, i)| of the returned eigenpairs
+  RealVectorType ritzResiduals() const {
+    const Index k = static_cast<Index>(alpha().size());
+    RealVectorType r(eigenvalues_.size());
+    const RealScalar bl = (k > 0 && static_cast<Index>(beta().size()) >= k) ? beta()[k - 1] : RealScalar(0);
+    for (Index i = 0; i < static_cast<Index>(eigenvalues_.size()); ++i)
+      r[i] = (k > 0 && es_tri_.eigenvectors().rows() == k) ? std::abs(bl * es_tri_.eigenvectors()(k - 1, i)) : RealScalar(0);
+    return r;
+  }
+
+ public:
+  LanczosEigenSolver() { setAllSettingsDefault(); }
+
+  /// default settings; does NOT clear computed data (lanczos.hpp:657-668)
+  LanczosEigenSolver& setAllSettingsDefault() {
+    setMinIterations(1);
+    setMaxIterations(unlimited);
+    setTolerance(DefaultTolerance<RealScalar>::value());
+    setIndicesForConvergence(std::vector<Index>{0});
+    setMaxEigenvalues(unlimited);
+    setComputeEigenvectorsOn(true);
+    lanczosBase_.setAllSettingsDefault();
+    return *this;
+  }
+
+  /// clear computed data, keep settings (lanczos.hpp:675-682)
+  LanczosEigenSolver& clearComputedData() {
+    lanczosBase_.clearLanczosSteps();
+    eigenvalues_.resize(0);
+    eigenvectors_.resize(0, 0);
+    log_.clear();
+    convergenceLog_.clear();
+    return *this;
+  }
+
+  /// clear computed data and set all settings default (lanczos.hpp:689-693)
+  LanczosEigenSolver& clear() {
+    clearComputedData();
+    setAllSettingsDefault();
+    return *this;
+  }
+
+  /// continue from the current state with possibly changed settings (lanczos.hpp:701-712)
+  Index continueToCompute() {
+    log_.push_back(headINFO() + "EigenSolver<ScalarType>::continueToCompute(...) was called");
+    if (lanczosBase_.lanczosvectorsSize() == 0) return compute();
+    Index ret = mainCalculation_();
+    log_.push_back(headINFO() + "EigenSolver<ScalarType>::compute(...) finish computing");
+    return ret;
+  }
+
+  /// compute matrix diagonalization (lanczos.hpp:717-736)
+  Index compute() {
+    log_.push_back(headINFO() + "EigenSolver<ScalarType>::compute(...) was called");
+    clearComputedData();
+    if (static_cast<Index>(initialVector().size()) != matrixHeight()) {
+      log_.push_back(headINFO() + "in compute(), initial_vector is empty or invalid, then set at random");
+      setInitialVector();
+    }
+    Index ret = mainCalculation_();
+    log_.push_back(headINFO() + "EigenSolver<ScalarType>::compute(...) finish computing");
+    return ret;
+  }
+
+  /// lanczos.hpp:740-823.  Steps that no stop rule can interrupt (iterations < minIterations) are enqueued
+  /// on the device as one batch; their per-trip bookkeeping (convergence log) is replayed afterwards from
+  /// alpha/beta, so results and logs are those of the trip-by-trip loop.
+  Index mainCalculation_() {
+    solveTridiagonal_(0, false);
+    bool set_initialvector_is_fail = false;
+    while (true) {
+      updateConvergenceLog_();
+      {
+        if (set_initialvector_is_fail) {
+          log_.push_back(headINFO() + "initial lanczosvector generation fail");
+          break;
+        }
+        if (lanczosBase_.lanczosStepIsUtmost()) {
+          log_.push_back(headINFO() + "lanczos steps finished with threshold");
+          log_.push_back(headINFO() + "lanczos steps achieved full of Krylov subspace");
+          break;
+        }
+        if (lanczosBase_.iterations() >= minIterations()) {
+          if (lanczosBase_.iterations() == maxIterations()) {
+            log_.push_back(headWARN() + "lanczos steps achieved maxIterations");
+            break;
+          }
+          if (isConverged_()) {
+            log_.push_back(headINFO() + "lanczos steps converged with tolerance");
+            break;
+          }
+        }
+      }
+      // number of calls no test above can interrupt
+      Index batch = 1;
+      if (lanczosBase_.iterations() < minIterations()) {
+        batch = minIterations() - lanczosBase_.iterations() + (lanczosBase_.lanczosvectorsSize() == 0 ? 1 : 0);
+        const Index room = matrixHeight() - lanczosBase_.lanczosvectorsSize();
+        if (batch > room) batch = room;
+        if (batch < 1) batch = 1;
+      }
+      const Index before = static_cast<Index>(lanczosBase_.alpha().size());
+      const Index done = lanczosBase_.updateLanczosSteps(batch);
+      if (lanczosBase_.lanczosvectorsSize() == 0) set_initialvector_is_fail = true;
+      // replay the trips of the intermediate states
+      for (Index j = 1; j < done; ++j) {
+        solveTridiagonal_(before + j, false);
+        updateConvergenceLog_();
+      }
+      solveTridiagonal_(static_cast<Index>(lanczosBase_.alpha().size()), false);
+    }
+
+    // eigenvectors of the tridiagonal matrix are needed once, here (the reference recomputes them every trip)
+    solveTridiagonal_(static_cast<Index>(lanczosBase_.alpha().size()), true);
+
+    // back eigen value to original one (lanczos.hpp:786-795)
+    Index eivalsize = es_tri_.eigenvalues().size();
+    if (maxEigenvalues_ != unlimited) {
+      if (maxEigenvalues_ < eivalsize) eivalsize = maxEigenvalues_;
+    }
+    eigenvalues_.resize(eivalsize);
+    for (Index k = 0; k < eivalsize; ++k) eigenvalues_[k] = es_tri_.eigenvalues()[k] - lanczosBase_.eigenvalueShift();
+
+    // Ritz vectors (lanczos.hpp:798-817): X = V S, normalised, phase-fixed — assembled on the device
+    if (computeEigenvectorsOn_) {
+      eigenvectors_.resize(matrixHeight(), eivalsize);
+      if (eivalsize > 0) {
+        const Index nm = es_tri_.eigenvectors().rows();
+        std::vector<Scalar> coef(static_cast<std::size_t>(nm) * eivalsize);
+        for (Index kk = 0; kk < eivalsize; ++kk)
+          for (Index m = 0; m < nm; ++m) coef[static_cast<std::size_t>(kk) * nm + m] = es_tri_.eigenvectors()(m, kk);
+        detail::check(cmb_krylov_ritz_vectors(lanczosBase_.deviceState(), detail::DTypeOf<Scalar>::value, coef.data(), nm,
+                                              nm, eivalsize, eigenvectors_.data(), matrixHeight()),
+                      "cmb_krylov_ritz_vectors");
+      }
+    } else {
+      eigenvectors_.resize(0, 0);
+    }
+    return 0;
+  }
+
+ protected:
+  void solveTridiagonal_(Index k, bool vectors) {
+    es_tri_.computeRaw(lanczosBase_.alpha().data(), lanczosBase_.beta().data(), static_cast<int>(k), vectors);
+  }
+
+  /// index for eigenvalues in [0,n); negative i counts from the end; -1 when invalid (lanczos.hpp:837-847)
+  static Index getFormalIndex(Index i, Index n) {
+    if (-n <= i && i < 0) {
+      return n - (-i - 1) % n - 1;
+    } else if (0 <= i && i < n) {
+      return i % n;
+    } else {
+      return -1;
+    }
+  }
+
+  /// append convergence log with current es_tri_ (lanczos.hpp:853-864)
+  void updateConvergenceLog_() {
+    const RealVectorType& trieivals = es_tri_.eigenvalues();
+    for (auto& indexForConvergence : indicesForConvergence_) {
+      Index i = getFormalIndex(indexForConvergence, trieivals.size());
+      if (i < 0) continue;
+      convergenceLog_[indexForConvergence].push_back(trieivals[i]);
+    }
+  }
+
+  /// judge convergence with current convergenceLog_ (lanczos.hpp:869-896)
+  bool isConverged_() {
+    if (es_tri_.eigenvalues().size() < 2) return false;
+    RealScalar scale = es_tri_.eigenvalues()[0] - es_tri_.eigenvalues()[es_tri_.eigenvalues().size() - 1];
+    for (auto& idxFroConvergence : indicesForConvergence_) {
+      auto itr = convergenceLog_.find(idxFroConvergence);
+      if (itr == convergenceLog_.end()) return false;
+      auto& edge = itr->second;
+      if (edge.size() < 2) return false;
+      RealScalar cur = edge[edge.size() - 1];
+      RealScalar old = edge[edge.size() - 2];
+      if (std::abs((cur - old) / scale) > tolerance_) return false;
+    }
+    return true;
+  }
+
+ public:
+  /// number of error log lines (lanczos.hpp:903-911)
+  Index hasERROR() const {
+    Index count = 0;
+    for (const auto& str : log_)
+      if (str.find(headERROR()) == 0) ++count;
+    return count;
+  }
+  /// number of warning log lines (lanczos.hpp:914-922)
+  Index hasWARN() const {
+    Index count = 0;
+    for (const auto& str : log_)
+      if (str.find(headWARN()) == 0) ++count;
+    return count;
+  }
+};
+
+}  // namespace EigenEx
+}  // namespace cmpt
+
+#endif

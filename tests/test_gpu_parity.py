@@ -1,0 +1,511 @@
+"""GPU parity tests: the CUDA path (through the C-ABI / solver binding) against the CPU oracle on the same
+seeded inputs.  Floating-point path: tolerances follow BASELINE.json's north star — converged/compared
+eigenvalues within 1e-10 relative in double, eigenvectors up to sign/phase."""
+import numpy as np
+import pytest
+
+import cmpt_eigenex_b200 as pkg
+from cmpt_eigenex_b200 import capi
+from cmpt_eigenex_b200 import synthetic as syn
+from oracle import core
+from oracle import reference_solvers as rs
+
+pytestmark = pytest.mark.gpu
+
+RTOL_EIG = 1e-10  # north star: eigenvalues within 1e-10 relative
+ATOL_AB = 1e-11   # alpha / beta agreement (CGS2 vs the reference's MGS: ~1e-14)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pkg.Context(0)
+    yield c
+    c.close()
+
+
+def _csr_dense(rp, c, v, n):
+    A = np.zeros((n, n), dtype=v.dtype)
+    for r in range(n):
+        A[r, c[rp[r]:rp[r + 1]]] = v[rp[r]:rp[r + 1]]
+    return A
+
+
+# ------------------------------------------------------------------------------------------------
+# operator apply
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["laplacian", "convdiff", "heisenberg", "hermitian_chain", "ragged"])
+def test_csr_apply_matches_oracle(ctx, name):
+    if name == "laplacian":
+        rp, c, v = syn.laplacian2d_csr(37)
+    elif name == "convdiff":
+        rp, c, v = syn.convdiff3d_csr(11)
+    elif name == "heisenberg":
+        rp, c, v = syn.heisenberg_csr(11)
+    elif name == "hermitian_chain":
+        rp, c, v = syn.hermitian_chain_csr(333)
+    else:  # ragged rows incl. empty ones and one long row; n not a multiple of 32
+        rng = np.random.default_rng(5)
+        n = 1000 + 7
+        lens = rng.integers(0, 9, size=n)
+        lens[13] = 300
+        lens[500:520] = 0
+        rp = np.zeros(n + 1, np.int64)
+        np.cumsum(lens, out=rp[1:])
+        c = rng.integers(0, n, size=rp[-1]).astype(np.int32)
+        v = rng.normal(size=rp[-1])
+    n = rp.size - 1
+    x = syn.start_vector(n, seed=3, dtype=v.dtype)
+    op = pkg.DeviceOperator.from_csr(ctx, rp, c, v)
+    y = op.apply(x)
+    yr = core.Operator.csr(rp, c, v).apply(x)
+    np.testing.assert_allclose(y, yr, rtol=0, atol=1e-14 * max(1.0, np.abs(yr).max()) * 8)
+    assert op.bytes == syn.csr_bytes(n, rp[-1], v.dtype.itemsize)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_dense_and_matrix_free_apply(ctx, dtype):
+    rng = np.random.default_rng(1)
+    n = 203
+    A = rng.normal(size=(n, n)).astype(dtype)
+    if dtype == np.complex128:
+        A = A + 1j * rng.normal(size=(n, n))
+    x = syn.start_vector(n, seed=5, dtype=dtype)
+    y = pkg.DeviceOperator.from_dense(ctx, A).apply(x)
+    np.testing.assert_allclose(y, A @ x, atol=1e-13)
+    L = 11
+    xs = syn.start_vector(1 << L, seed=9, dtype=dtype)
+    for pbc in (True, False):
+        yh = pkg.DeviceOperator.heisenberg(ctx, L, 1.0, pbc, dtype=dtype).apply(xs)
+        yo = core.Operator.heisenberg(L, 1.0, pbc, prefix="z" if dtype == np.complex128 else "d").apply(xs)
+        np.testing.assert_allclose(yh, yo, atol=1e-14)
+
+
+# ------------------------------------------------------------------------------------------------
+# Lanczos
+# ------------------------------------------------------------------------------------------------
+def _oracle_lanczos(opr, x0, m, nev, prefix="d", **kw):
+    ref = rs.LanczosEigenSolver(prefix)
+    ref.set_matrix_multiplication(opr)
+    ref.init = x0
+    ref.min_iterations = ref.max_iterations = m
+    ref.max_eigenvalues = nev
+    for k, v in kw.items():
+        setattr(ref, k, v)
+    ref.compute()
+    return ref
+
+
+def _compare_lanczos(es, ref, check_vectors=True):
+    a, b = es.alpha(), es.beta()
+    ra, rb = ref.alpha_beta()
+    assert es.iterations() == ref.iterations
+    assert a.shape == ra.shape and b.shape == rb.shape
+    np.testing.assert_allclose(a, ra, rtol=0, atol=ATOL_AB * max(1.0, np.abs(ra).max()))
+    np.testing.assert_allclose(b, rb, rtol=0, atol=ATOL_AB * max(1.0, np.abs(ra).max()))
+    ev, rev = es.eigenvalues(), ref.eigenvalues
+    assert ev.shape == rev.shape
+    scale = max(np.abs(ra).max(), 1e-300)
+    # relative to the eigenvalue itself when it is not tiny compared with ||A||
+    tol = RTOL_EIG * np.maximum(np.abs(rev), 1e-3 * scale)
+    assert np.all(np.abs(ev - rev) <= tol), (ev, rev)
+    if check_vectors and ev.size:
+        X, R = es.eigenvectors(), ref.eigenvectors
+        assert X.shape == R.shape
+        ov = np.abs(np.sum(np.conj(R) * X, axis=0))
+        assert np.all(np.abs(ov - 1) < 1e-8), ov
+        # phase convention: first non-zero element real positive
+        assert np.all(np.abs(X[0].imag) < 1e-12) and np.all(X[0].real > 0)
+    assert es.log() == ref.log
+
+
+def test_sample_lanczos1_kat(ctx):
+    # src/samples/sample_lanczos1.cpp through the device dense operator
+    H = np.array([[1.0, 0.5, 0.0], [0.5, 2.0, 0.5], [0.0, 0.5, 3.0]])
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(pkg.DeviceOperator.from_dense(ctx, H))
+    es.setTolerance(1e-5).setMaxIterations(100)
+    es.compute()
+    want = np.array([2 - np.sqrt(1.5), 2.0, 2 + np.sqrt(1.5)])
+    np.testing.assert_allclose(es.eigenvalues(), want, atol=1e-14)
+    X = es.eigenvectors()
+    np.testing.assert_allclose(H @ X, X * want, atol=1e-13)
+    assert (X[0] > 0).all()
+    assert "INFO      lanczos steps achieved full of Krylov subspace" in es.log()
+    # default start vector = std::mt19937 default seed: identical to the oracle's restatement
+    ref = rs.LanczosEigenSolver("d")
+    ref.set_matrix_multiplication(core.Operator.dense(H))
+    ref.tolerance = 1e-5
+    ref.max_iterations = 100
+    ref.compute()
+    _compare_lanczos(es, ref)
+
+
+@pytest.mark.parametrize("case", ["dense300", "laplacian48", "heisenberg12", "laplacian_chunked"])
+def test_lanczos_fixed_m_matches_oracle(ctx, case):
+    if case == "dense300":
+        n, m = 300, 60
+        A = syn.dense_symmetric(n, seed=1)
+        op, opr = pkg.DeviceOperator.from_dense(ctx, A), core.Operator.dense(A)
+    elif case == "laplacian48":
+        N, m = 48, 100
+        n = N * N
+        rp, c, v = syn.laplacian2d_csr(N)
+        op, opr = pkg.DeviceOperator.from_csr(ctx, rp, c, v), core.Operator.csr(rp, c, v)
+    elif case == "heisenberg12":
+        L, m = 12, 50
+        n = 1 << L
+        rp, c, v = syn.heisenberg_csr(L)
+        op, opr = pkg.DeviceOperator.from_csr(ctx, rp, c, v), core.Operator.csr(rp, c, v)
+    else:  # basis split over several column segments and > 128 columns (multi-chunk CGS2)
+        N, m = 40, 150
+        n = N * N
+        rp, c, v = syn.laplacian2d_csr(N)
+        op, opr = pkg.DeviceOperator.from_csr(ctx, rp, c, v), core.Operator.csr(rp, c, v)
+    x0 = syn.start_vector(n, seed=7)
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(op).setInitialVector(x0)
+    es.setMinIterations(m).setMaxIterations(m).setMaxEigenvalues(5).setIndicesForConvergence([0, 1, 2, 3, 4])
+    if case == "laplacian_chunked":
+        es.setReserveSize(24)
+    es.compute()
+    ref = _oracle_lanczos(opr, x0, m, 5, indices_for_convergence=[0, 1, 2, 3, 4])
+    _compare_lanczos(es, ref)
+    assert es.hasWARN() == 1
+    for i in range(5):
+        np.testing.assert_allclose(es.convergenceLog(i), ref.convergence_log[i], atol=1e-9)
+    # Ritz residuals: ||A x - theta x|| equals |beta_m S(m,i)| up to rounding
+    X = es.eigenvectors()
+    for i in range(5):
+        r = np.linalg.norm(op.apply(X[:, i]) - es.eigenvalues()[i] * X[:, i])
+        assert abs(r - es.ritzResiduals()[i]) < 1e-9
+    np.testing.assert_allclose(es.ritzResiduals(), ref.ritz_residuals(), atol=1e-9)
+    # orthonormal basis
+    V = np.stack([es.basisVector(k) for k in range(0, es.nvectors(), max(1, es.nvectors() // 12))], axis=1)
+    np.testing.assert_allclose(V.T @ V, np.eye(V.shape[1]), atol=1e-13)
+
+
+def test_lanczos_complex_sample2(ctx):
+    # src/samples/sample_lanczos2.cpp:19-59, exact settings, complex Scalar
+    n = 200
+    rp, c, v = syn.hermitian_chain_csr(n)
+    x0 = core.seeded_vector(1, n, "z")  # makeRandomVector(std::mt19937(1), n)
+    es = pkg.LanczosEigenSolver(np.complex128)
+    es.setMatrixMultiplication(pkg.DeviceOperator.from_csr(ctx, rp, c, v))
+    es.setEigenvalueShift(0.0).setTolerance(1e-7).setThreshold(1e-14)
+    es.setMinIterations(es.unlimited).setMaxIterations(1000).setComputeEigenvectorsOn(True)
+    es.setIndicesForConvergence([0]).setInitialVector(x0).setMaxEigenvalues(10)
+    es.setOrthogonalizingVectors([]).setReorthogonalizeInterval(1).setReserveSize(128)
+    es.compute()
+    ref = rs.LanczosEigenSolver("z")
+    ref.set_matrix_multiplication(core.Operator.csr(rp, c, v))
+    ref.tolerance, ref.threshold, ref.min_iterations, ref.max_iterations = 1e-7, 1e-14, -1, 1000
+    ref.max_eigenvalues, ref.init = 10, x0
+    ref.compute()
+    assert abs(es.iterations() - ref.iterations) <= 1  # stop rule may flip by one trip
+    if es.iterations() == ref.iterations:
+        _compare_lanczos(es, ref)
+    assert abs(es.eigenvalues()[0] - 2 * np.cos(200 * np.pi / 201)) < 1e-4
+    # full Krylov space: exact spectrum 2cos(k pi/201)
+    es2 = pkg.LanczosEigenSolver(np.complex128)
+    es2.setMatrixMultiplication(pkg.DeviceOperator.from_csr(ctx, rp, c, v))
+    es2.setThreshold(1e-14).setTolerance(0.0).setInitialVector(x0).setComputeEigenvectorsOn(False)
+    es2.compute()
+    assert es2.nvectors() == n
+    np.testing.assert_allclose(es2.eigenvalues(), np.sort(2 * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))), atol=2e-13)
+
+
+def test_lanczos_convergence_stop_heisenberg(ctx):
+    # cfg 4 semantics at small L: ground state with the reference's stop rule (tolerance 1e-12, index 0)
+    L = 12
+    rp, c, v = syn.heisenberg_csr(L)
+    x0 = syn.start_vector(1 << L, seed=7)
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(pkg.DeviceOperator.from_csr(ctx, rp, c, v)).setInitialVector(x0)
+    es.setMaxIterations(200).setMaxEigenvalues(1)
+    es.compute()
+    ref = rs.LanczosEigenSolver("d")
+    ref.set_matrix_multiplication(core.Operator.csr(rp, c, v))
+    ref.init, ref.max_iterations, ref.max_eigenvalues = x0, 200, 1
+    ref.compute()
+    assert abs(es.iterations() - ref.iterations) <= 1
+    assert abs(es.eigenvalues()[0] - syn.HEISENBERG_RING_E0[L]) < 2e-10
+    assert abs(es.eigenvalues()[0] - ref.eigenvalues[0]) < RTOL_EIG * abs(ref.eigenvalues[0])
+    assert "INFO      lanczos steps converged with tolerance" in es.log()
+    # matrix-free operator gives the same run
+    es2 = pkg.LanczosEigenSolver()
+    es2.setMatrixMultiplication(pkg.DeviceOperator.heisenberg(ctx, L)).setInitialVector(x0)
+    es2.setMaxIterations(200).setMaxEigenvalues(1)
+    es2.compute()
+    assert es2.iterations() == es.iterations()
+    np.testing.assert_allclose(es2.alpha(), es.alpha(), atol=1e-12)
+
+
+@pytest.mark.parametrize("interval", [0, 1, 2, 3, 7])
+def test_lanczos_reorthogonalize_interval(ctx, interval):
+    N, m = 24, 40
+    n = N * N
+    rp, c, v = syn.laplacian2d_csr(N)
+    x0 = syn.start_vector(n, seed=7)
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(pkg.DeviceOperator.from_csr(ctx, rp, c, v)).setInitialVector(x0)
+    es.setMinIterations(m).setMaxIterations(m).setMaxEigenvalues(3).setReorthogonalizeInterval(interval)
+    es.compute()
+    ref = _oracle_lanczos(core.Operator.csr(rp, c, v), x0, m, 3, interval=interval)
+    a, b = es.alpha(), es.beta()
+    ra, rb = ref.alpha_beta()
+    # without full reorthogonalisation rounding errors grow with the step count: compare the early steps
+    # tightly and the Ritz values loosely
+    k = 12 if interval != 1 else m
+    np.testing.assert_allclose(a[:k], ra[:k], atol=1e-9)
+    np.testing.assert_allclose(b[:k], rb[:k], atol=1e-9)
+    assert abs(es.eigenvalues()[0] - ref.eigenvalues[0]) < (1e-10 if interval == 1 else 1e-6)
+
+
+def test_lanczos_deflation_shift_and_continue(ctx):
+    N = 20
+    n = N * N
+    rp, c, v = syn.laplacian2d_csr(N)
+    op = pkg.DeviceOperator.from_csr(ctx, rp, c, v)
+    opr = core.Operator.csr(rp, c, v)
+    x0 = syn.start_vector(n, seed=7)
+    lam = syn.laplacian2d_eigenvalues(N, 4)
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(op).setInitialVector(x0).setMinIterations(80).setMaxIterations(80).setMaxEigenvalues(1)
+    es.compute()
+    g = es.eigenvectors()[:, 0].copy()
+    assert abs(es.eigenvalues()[0] - lam[0]) < 1e-12
+    # deflate the ground state + shift: lowest Ritz value becomes the first excited level
+    es2 = pkg.LanczosEigenSolver()
+    es2.setMatrixMultiplication(op).setInitialVector(x0).setOrthogonalizingVectors([g]).setEigenvalueShift(1.5)
+    es2.setMinIterations(80).setMaxIterations(80).setMaxEigenvalues(1)
+    es2.compute()
+    ref2 = _oracle_lanczos(opr, x0, 80, 1, ortho=[g], shift=1.5)
+    assert abs(es2.eigenvalues()[0] - lam[1]) < 1e-10
+    assert abs(es2.eigenvalues()[0] - ref2.eigenvalues[0]) < 1e-10
+    assert abs(g @ es2.eigenvectors()[:, 0]) < 1e-12
+    np.testing.assert_allclose(es2.alpha(), ref2.alpha_beta()[0], atol=1e-10)
+    # continueToCompute extends the same Krylov space (lanczos.hpp:701-712)
+    es3 = pkg.LanczosEigenSolver()
+    es3.setMatrixMultiplication(op).setInitialVector(x0).setMinIterations(30).setMaxIterations(30).setMaxEigenvalues(2)
+    es3.compute()
+    es3.setMinIterations(80).setMaxIterations(80)
+    es3.continueToCompute()
+    ref3 = _oracle_lanczos(opr, x0, 30, 2)
+    ref3.min_iterations = ref3.max_iterations = 80
+    ref3.continue_to_compute()
+    assert es3.iterations() == 80 == ref3.iterations
+    np.testing.assert_allclose(es3.alpha(), es.alpha(), atol=1e-12)
+    np.testing.assert_allclose(es3.eigenvalues(), ref3.eigenvalues, atol=1e-10)
+    assert es3.log() == ref3.log
+
+
+def test_lanczos_edge_cases(ctx):
+    H = np.diag([1.0, 2.0, 3.0, 4.0])
+    op = pkg.DeviceOperator.from_dense(ctx, H)
+    # zero start vector -> quiet failure (lanczos.hpp:316-318,748-752)
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(op).setInitialVector(np.zeros(4))
+    es.compute()
+    assert es.nvectors() == 0 and es.eigenvalues().size == 0
+    assert "INFO      initial lanczosvector generation fail" in es.log()
+    # start vector inside an invariant subspace -> breakdown after 2 vectors, beta kept (lanczos.hpp:433-437)
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(op).setInitialVector(np.array([1.0, 1.0, 0.0, 0.0]))
+    es.compute()
+    ref = rs.LanczosEigenSolver("d")
+    ref.set_matrix_multiplication(core.Operator.dense(H))
+    ref.init = np.array([1.0, 1.0, 0.0, 0.0])
+    ref.compute()
+    assert es.nvectors() == 2 == ref.base.nvectors
+    assert es.beta().size == es.alpha().size == 2
+    np.testing.assert_allclose(es.eigenvalues(), [1.0, 2.0], atol=1e-14)
+    assert es.log() == ref.log
+    # maxEigenvalues unlimited: every Ritz vector is assembled (n x (m+1))
+    N = 12
+    rp, c, v = syn.laplacian2d_csr(N)
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(pkg.DeviceOperator.from_csr(ctx, rp, c, v)).setInitialVector(syn.start_vector(N * N))
+    es.setMinIterations(9).setMaxIterations(9)
+    es.compute()
+    X = es.eigenvectors()
+    assert X.shape == (N * N, 10)
+    np.testing.assert_allclose(X.T @ X, np.eye(10), atol=1e-12)
+    # compute without eigenvectors
+    es.setComputeEigenvectorsOn(False)
+    es.compute()
+    assert es.eigenvectors().size == 0 and es.eigenvalues().size == 10
+    # wrong-size start vector is replaced by the default random one, with the INFO line
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(op).setInitialVector(np.ones(3))
+    es.compute()
+    assert "INFO      in compute(), initial_vector is empty or invalid, then set at random" in es.log()
+    np.testing.assert_allclose(es.eigenvalues(), [1, 2, 3, 4], atol=1e-13)
+
+
+def test_legacy_callback_operator(ctx):
+    # the reference's own plug-in: a host function (const Scalar*, Scalar*) (lanczos.hpp:116)
+    N = 16
+    n = N * N
+    rp, c, v = syn.laplacian2d_csr(N)
+    A = _csr_dense(rp, c, v, n)
+    x0 = syn.start_vector(n, seed=7)
+    calls = []
+
+    def matmul(x):
+        calls.append(1)
+        return A @ x
+
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(matmul, n).setInitialVector(x0).setMinIterations(30).setMaxIterations(30)
+    es.setMaxEigenvalues(2).setEigenvalueShift(0.25)
+    es.compute()
+    ref = _oracle_lanczos(core.Operator.csr(rp, c, v), x0, 30, 2, shift=0.25)
+    assert len(calls) == 31  # m+1 operator applies
+    _compare_lanczos(es, ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# Arnoldi
+# ------------------------------------------------------------------------------------------------
+def _sorted_close(a, b, tol):
+    a, b = np.asarray(a), np.asarray(b)
+    d = np.abs(a[:, None] - b[None, :])
+    return d.min(axis=1).max() < tol and d.min(axis=0).max() < tol
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_arnoldi_convdiff_matches_oracle(ctx, dtype):
+    M, m = 10, 50
+    n = M ** 3
+    rp, c, v = syn.convdiff3d_csr(M)
+    v = v.astype(dtype)
+    x0 = syn.start_vector(n, seed=7, dtype=dtype)
+    es = pkg.ArnoldiEigenSolver(dtype)
+    es.setMatrixMultiplication(pkg.DeviceOperator.from_csr(ctx, rp, c, v)).setInitialVector(x0)
+    es.setMinIterations(m).setMaxIterations(m).setMaxEigenvalues(5).setIndicesForConvergence([0, 1, 2])
+    es.compute()
+    ref = rs.ArnoldiEigenSolver("z" if dtype == np.complex128 else "d")
+    ref.set_matrix_multiplication(core.Operator.csr(rp, c, v))
+    ref.init = x0
+    ref.min_iterations = ref.max_iterations = m
+    ref.max_eigenvalues = 5
+    ref.indices_for_convergence = [0, 1, 2]
+    ref.compute()
+    assert es.iterations() == m == ref.iterations
+    H, Hr = es.hessenbergMatrix(), ref.hessenberg
+    np.testing.assert_allclose(H, Hr, atol=1e-10)
+    assert abs(es.residue() - ref.base.residue) < 1e-10
+    ev, rev = es.eigenvalues(), ref.eigenvalues
+    assert _sorted_close(ev, rev, RTOL_EIG * np.abs(rev).max())
+    A = _csr_dense(rp, c, v, n)
+    P, D = es.eigenvectors(), es.eigenvalues()
+    res = np.linalg.norm(A @ P - P * D, axis=0)
+    assert np.all(np.abs(res - es.ritzResiduals()) < 1e-9)
+    np.testing.assert_allclose(np.linalg.norm(P, axis=0), 1.0, atol=1e-12)
+    assert np.all(np.abs(P[0].imag) < 1e-12) and np.all(P[0].real > 0)
+    # leading Ritz vectors agree with the oracle up to phase (both are phase-fixed the same way)
+    ov = np.abs(np.sum(np.conj(ref.eigenvectors[:, :2]) * P[:, :2], axis=0))
+    assert np.all(np.abs(ov - 1) < 1e-7)
+    assert es.log() == ref.log
+    assert _sorted_close(es.convergenceLog(0)[-5:], np.array(ref.convergence_log[0][-5:]), 1e-8)
+
+
+def test_arnoldi_sample_random_complex(ctx):
+    # src/samples/sample_arnoldi.cpp: 50x50 complex, m = 40, two leading eigenpairs, AP - PD small
+    rng = np.random.default_rng(0)
+    n, m = 50, 40
+    A = rng.uniform(-1, 1, (n, n)) + 1j * rng.uniform(-1, 1, (n, n))
+    es = pkg.ArnoldiEigenSolver(np.complex128)
+    es.setMatrixMultiplication(pkg.DeviceOperator.from_dense(ctx, A))
+    es.setMaxIterations(m).setMinIterations(m).setTolerance(1e-14).setMaxEigenvalues(2)
+    es.compute()
+    ref = rs.ArnoldiEigenSolver("z")
+    ref.set_matrix_multiplication(core.Operator.dense(A))
+    ref.min_iterations = ref.max_iterations = m
+    ref.tolerance, ref.max_eigenvalues = 1e-14, 2
+    ref.compute()
+    assert _sorted_close(es.eigenvalues(), ref.eigenvalues, 1e-10 * np.abs(ref.eigenvalues).max())
+    P, D = es.eigenvectors(), es.eigenvalues()
+    res = np.linalg.norm(A @ P - P * D, axis=0)
+    assert np.all(res < es.ritzResiduals() + 1e-10)
+    # full Krylov dimension on a 4x4 (src/experiments/arnoldi/arnoldi_test.cpp:50-92)
+    A4 = A[:4, :4].copy()
+    es4 = pkg.ArnoldiEigenSolver(np.complex128)
+    es4.setMatrixMultiplication(pkg.DeviceOperator.from_dense(ctx, A4)).setThreshold(1e-14)
+    es4.setMaxIterations(es4.unlimited).setMinIterations(es4.unlimited).setMaxEigenvalues(5).setTolerance(1e-10)
+    es4.setInitialVector()
+    es4.compute()
+    P, D = es4.eigenvectors(), es4.eigenvalues()
+    assert D.size == 4 and np.abs(A4 @ P - P * D).max() < 1e-12
+    assert _sorted_close(D, np.linalg.eigvals(A4), 1e-12)
+    assert "INFO      arnoldi steps achieved full of Krylov subspace" in es4.log()
+
+
+def test_arnoldi_shift_deflation_restart(ctx):
+    M = 8
+    n = M ** 3
+    rp, c, v = syn.convdiff3d_csr(M)
+    op = pkg.DeviceOperator.from_csr(ctx, rp, c, v)
+    x0 = syn.start_vector(n, seed=7)
+    exact = syn.convdiff3d_eigenvalues(M, count=3)
+    es = pkg.ArnoldiEigenSolver(np.float64)
+    es.setMatrixMultiplication(op).setInitialVector(x0).setMinIterations(30).setMaxIterations(30).setMaxEigenvalues(2)
+    es.setEigenvalueShift(2.0)
+    es.compute()
+    ref = rs.ArnoldiEigenSolver("d")
+    ref.set_matrix_multiplication(core.Operator.csr(rp, c, v))
+    ref.init, ref.shift = x0, 2.0
+    ref.min_iterations = ref.max_iterations = 30
+    ref.max_eigenvalues = 2
+    ref.compute()
+    assert _sorted_close(es.eigenvalues(), ref.eigenvalues, 1e-10 * 12)
+    # explicit restart (cfg 3): each cycle restarts from the leading Ritz vector; the leading Ritz value improves
+    es2 = pkg.ArnoldiEigenSolver(np.float64)
+    es2.setMatrixMultiplication(op).setInitialVector(x0).setMinIterations(20).setMaxIterations(20).setMaxEigenvalues(1)
+    es2.compute()
+    e1 = abs(es2.eigenvalues()[0] - exact[0])
+    es2.computeWithRestarts(6)
+    e6 = abs(es2.eigenvalues()[0] - exact[0])
+    assert e6 < e1 and e6 < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE sizes: size-independent properties (the oracle would take minutes here)
+# ------------------------------------------------------------------------------------------------
+def test_cfg2_full_size_properties(ctx):
+    # cfg 2: 2D Laplacian 4096^2 (16.8M rows), Lanczos m=100 with full reorthogonalisation
+    N, m = 4096, 100
+    n = N * N
+    rp, c, v = syn.laplacian2d_csr(N)
+    assert rp[-1] == 83869696
+    op = pkg.DeviceOperator.from_csr(ctx, rp, c, v)
+    del rp, c, v
+    x0 = syn.start_vector(n, seed=7)
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(op).setInitialVector(x0)
+    es.setMinIterations(m).setMaxIterations(m).setMaxEigenvalues(5).setIndicesForConvergence([0, 1, 2, 3, 4])
+    es.compute()
+    assert es.iterations() == m and es.nvectors() == m + 1
+    ev = es.eigenvalues()
+    assert np.all(np.diff(ev) > 0) and ev[0] > 0 and ev[-1] < 8
+    X = es.eigenvectors(copy=False)
+    rr = es.ritzResiduals()
+    for i in range(5):
+        xi = np.ascontiguousarray(X[:, i])
+        r = np.linalg.norm(op.apply(xi) - ev[i] * xi)
+        assert abs(np.linalg.norm(xi) - 1) < 1e-12
+        assert abs(r - rr[i]) < 1e-8, (i, r, rr[i])  # ||A x - theta x|| = |beta_m S(m,i)|
+    G = X.T @ X
+    np.testing.assert_allclose(G, np.eye(5), atol=1e-11)
+    # basis orthonormality on a sample of columns (V^T V - I <= 1e-13)
+    cols = [0, 1, 37, 64, 99, 100]
+    V = np.stack([es.basisVector(k) for k in cols], axis=1)
+    np.testing.assert_allclose(V.T @ V, np.eye(len(cols)), atol=1e-13)
+    # tridiagonal relation: A u_k = beta_{k-1} u_{k-1} + alpha_k u_k + beta_k u_{k+1}
+    a, b = es.alpha(), es.beta()
+    u36, u38 = es.basisVector(36), es.basisVector(38)
+    resid = op.apply(V[:, 2]) - (b[36] * u36 + a[37] * V[:, 2] + b[37] * u38)
+    assert np.linalg.norm(resid) < 1e-12
+    # algorithmic byte count of SURVEY.md §8(d): 101 * B_spmv + sum_{c=1..100} (3c+7) n s  (+ first-step vectors)
+    want = 100 * op.bytes + (3 * 5050 + 700) * n * 8.0
+    assert abs(es.deviceBytes() - want) / want < 0.01

@@ -1,0 +1,105 @@
+"""CPU tests of the product's host-side pieces: the m x m Ritz solvers (detail/tridiag_eigen.hpp,
+detail/hessenberg_eigen.hpp) against LAPACK, and the C-ABI export list.  No GPU needed."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+import cmpt_eigenex_b200 as pkg
+from cmpt_eigenex_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 57, 101])
+def test_tridiagonal_eigen_matches_lapack(n):
+    rng = np.random.default_rng(n)
+    a = rng.normal(size=n)
+    b = rng.normal(size=max(n - 1, 0))
+    w, z = pkg.host_tridiagonal_eigen(a, b)
+    T = np.diag(a) + np.diag(b, 1) + np.diag(b, -1)
+    wl = np.linalg.eigvalsh(T)
+    np.testing.assert_allclose(w, wl, atol=1e-13 * max(1, np.abs(wl).max()))
+    np.testing.assert_allclose(z.T @ z, np.eye(n), atol=1e-13)
+    np.testing.assert_allclose(T @ z, z * w, atol=1e-12)
+    w2 = pkg.host_tridiagonal_eigen(a, b, vectors=False)
+    np.testing.assert_allclose(w2, wl, atol=1e-13 * max(1, np.abs(wl).max()))
+
+
+def test_tridiagonal_eigen_lanczos_like_and_extra_beta():
+    # Lanczos T of a Laplacian: graded, nearly-degenerate Ritz values; beta may carry one extra entry
+    n = 80
+    a = 4 + 0.01 * np.cos(np.arange(n))
+    b = np.full(n, 2.0) * (1 + 1e-8 * np.arange(n))  # n entries: the last one must be ignored
+    w, z = pkg.host_tridiagonal_eigen(a, b)
+    wl = sla.eigh_tridiagonal(a, b[: n - 1], eigvals_only=True)
+    np.testing.assert_allclose(w, wl, atol=1e-13)
+    # zero off-diagonal (breakdown) splits the matrix
+    b2 = b.copy()
+    b2[30] = 0.0
+    w3 = pkg.host_tridiagonal_eigen(a, b2, vectors=False)
+    np.testing.assert_allclose(w3, sla.eigh_tridiagonal(a, b2[: n - 1], eigvals_only=True), atol=1e-13)
+
+
+@pytest.mark.parametrize("n,cplx", [(1, True), (2, True), (5, False), (20, True), (50, False), (64, True)])
+def test_hessenberg_eigen_matches_lapack(n, cplx):
+    rng = np.random.default_rng(100 + n)
+    h = rng.normal(size=(n, n))
+    if cplx:
+        h = h + 1j * rng.normal(size=(n, n))
+    h = np.triu(h, -1)
+    w, v = pkg.host_hessenberg_eigen(h)
+    wl = np.linalg.eigvals(h)
+    # compare as multisets
+    d = np.abs(w[:, None] - wl[None, :])
+    assert d.min(axis=1).max() < 1e-10 and d.min(axis=0).max() < 1e-10
+    np.testing.assert_allclose(np.linalg.norm(v, axis=0), 1.0, atol=1e-12)
+    res = np.linalg.norm(h @ v - v * w, axis=0)
+    assert res.max() < 1e-9 * max(1.0, np.abs(h).max() * n)
+    w2 = pkg.host_hessenberg_eigen(h, vectors=False)
+    d2 = np.abs(w2[:, None] - wl[None, :])
+    assert d2.min(axis=1).max() < 1e-10 and d2.min(axis=0).max() < 1e-10
+
+
+def test_hessenberg_eigen_real_nonsymmetric_conjugate_pairs():
+    # real Hessenberg with complex-conjugate eigenvalues embedded in complex arithmetic
+    h = np.array([[0.0, -1.0, 0.3], [1.0, 0.0, 0.2], [0.0, 0.5, 2.0]])
+    w, v = pkg.host_hessenberg_eigen(h)
+    wl = np.linalg.eigvals(h)
+    assert np.abs(np.sort_complex(w) - np.sort_complex(wl)).max() < 1e-12
+    assert np.abs(h @ v - v * w).max() < 1e-12
+
+
+def _declared_in_headers():
+    names = set()
+    for hdr in ("cmpt_b200.h", "cmpt_b200_solver.h"):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names.update(re.findall(r"\b(cmbs?_[a-z0-9_]+)\s*\(", src))
+    names.discard("cmb_matmul_fn")
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(capi.LIB_PATH), "libcmpt_b200.so must be built by __graft_entry__.build()"
+    L = ctypes.CDLL(capi.LIB_PATH)
+    declared = _declared_in_headers()
+    assert len(declared) > 60
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    # the ctypes binding covers the same list
+    assert set(capi.declared_symbols()) == declared
+
+
+def test_no_silent_cpu_fallback_without_gpu():
+    n = ctypes.c_int(-1)
+    capi.check(capi.lib().cmb_device_count(ctypes.byref(n)))
+    if n.value > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(capi.CmbError) as e:
+        pkg.Context(0)
+    assert e.value.code == capi.CMB_ERR_NO_DEVICE
+    assert b"no CPU fallback" in capi.lib().cmb_last_error()
