@@ -507,6 +507,34 @@ int cmb_lanczos_step(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, 
   return CMB_OK;
 }
 
+static int ensure_tmp(cmb_krylov* K, double** p, size_t doubles);
+
+int cmb_lanczos_residual_norm(cmb_krylov* K, double* out) {
+  CMB_REQUIRE(K && out, "null argument");
+  CMB_REQUIRE(K->nk >= 1, "no Lanczos vector yet");
+  cmb_ctx* ctx = K->ctx;
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  CMB_TRY(ensure_tmp(K, &K->tmp1, K->ld));
+  const int k = K->nk - 1;
+  const int first = (k > 0) ? k - 1 : k;
+  std::vector<Chunk> chunks;
+  contiguous_chunks(K, K->ndefl + first, K->ndefl + k + 1, chunks);
+  CMB_CUDA(cudaMemsetAsync(K->h2, 0, sizeof(double) * 4, ctx->stream));
+  int slot = 0;
+  if (k > 0) {
+    CMB_CUDA(cudaMemcpyAsync(K->h2 + slot * K->es, K->beta_dev + (k - 1), sizeof(double), cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+    ++slot;
+  }
+  CMB_CUDA(cudaMemcpyAsync(K->h2 + slot * K->es, K->alpha_dev + size_t(k) * 2, sizeof(double), cudaMemcpyDeviceToDevice,
+                           ctx->stream));
+  CMB_TRY(subtract_cols(K, chunks, K->h2, K->v, K->tmp1, K->scal + 1, "recurrence"));
+  CMB_CUDA(cudaMemcpyAsync(K->h_stage, K->scal + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = sqrt(K->h_stage[0]);
+  return CMB_OK;
+}
+
 int cmb_arnoldi_step(cmb_krylov* K, cmb_op* op, const void* shift, double threshold, void* hcol, double* residue,
                      int* status) {
   CMB_TRY(check_pair(K, op));
@@ -566,6 +594,8 @@ int cmb_arnoldi_step(cmb_krylov* K, cmb_op* op, const void* shift, double thresh
   return CMB_OK;
 }
 
+}  // extern "C"
+
 static int ensure_tmp(cmb_krylov* K, double** p, size_t doubles) {
   if (*p) return CMB_OK;
   if (cudaMalloc(p, sizeof(double) * doubles) != cudaSuccess) {
@@ -584,6 +614,8 @@ __global__ void interleave_kernel(const double* __restrict__ re, const double* _
     reinterpret_cast<double2*>(z)[i] = make_double2(re[i], im[i]);
 }
 __global__ void add2_kernel(const double* a, const double* b, double* out) { out[0] = a[0] + b[0]; }
+
+extern "C" {
 
 int cmb_krylov_ritz_vectors(cmb_krylov* K, cmb_dtype coef_dtype, const void* coef, int64_t ldc, int64_t ncoef,
                             int64_t nev, void* x_host, int64_t ldx) {

@@ -466,11 +466,19 @@ class LanczosEigenSolver {
   const TridiagonalEigenSolver<Scalar>& es_tri() const { return es_tri_; }
   const std::map<Index, std::vector<RealScalar>>& convergenceLog() const { return convergenceLog_; }
 
-  /// additive: Ritz residual bounds |beta_last * S(last, i)| of the returned eigenpairs
+  /// additive: Ritz residual bounds ||A x_i - theta_i x_i|| = |beta_next * S(last, i)| of the returned eigenpairs,
+  /// beta_next = ||A u_k - alpha_k u_k - beta_{k-1} u_{k-1}|| (one fused device pass; the kept beta after a breakdown)
   RealVectorType ritzResiduals() const {
     const Index k = static_cast<Index>(alpha().size());
     RealVectorType r(eigenvalues_.size());
-    const RealScalar bl = (k > 0 && static_cast<Index>(beta().size()) >= k) ? beta()[k - 1] : RealScalar(0);
+    RealScalar bl = RealScalar(0);
+    if (k > 0 && static_cast<Index>(beta().size()) >= k) {
+      bl = beta()[k - 1];
+    } else if (k > 0 && lanczosBase_.deviceState()) {
+      double b = 0.0;
+      detail::check(cmb_lanczos_residual_norm(lanczosBase_.deviceState(), &b), "cmb_lanczos_residual_norm");
+      bl = b;
+    }
     for (Index i = 0; i < static_cast<Index>(eigenvalues_.size()); ++i)
       r[i] = (k > 0 && es_tri_.eigenvectors().rows() == k) ? std::abs(bl * es_tri_.eigenvectors()(k - 1, i)) : RealScalar(0);
     return r;

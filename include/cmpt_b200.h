@@ -132,6 +132,10 @@ int cmb_lanczos_step(cmb_krylov* k, cmb_op* op, double shift, int64_t interval, 
 int cmb_lanczos_run(cmb_krylov* k, cmb_op* op, double shift, int64_t interval, double threshold,
                     int64_t nsteps, double* alpha, double* beta, int64_t* steps_done, int* status);
 
+/* ||A u_k - alpha_k u_k - beta_{k-1} u_{k-1}|| for the newest Lanczos vector u_k: the beta the next step would
+ * produce, i.e. the factor of the Ritz residual bounds |beta_next * S(last,i)|.  Does not change the state. */
+int cmb_lanczos_residual_norm(cmb_krylov* k, double* out);
+
 /* updateArnoldiSteps() (arnoldi.hpp:312-392).  hcol receives h(0..ncols-1, ncols-1) of the new column
  * (dtype elements); *residue the new residual norm.  shift points at one dtype element. */
 int cmb_arnoldi_step(cmb_krylov* k, cmb_op* op, const void* shift, double threshold, void* hcol,

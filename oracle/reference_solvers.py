@@ -184,12 +184,20 @@ class LanczosEigenSolver:
         return 0
 
     def ritz_residuals(self):
-        """|beta_last * S(last, i)| — not in the reference; derivable from its exposed state."""
+        """|beta_next * S(last, i)| — not in the reference; derivable from its exposed state:
+        beta_next = ||A u_k - alpha_k u_k - beta_{k-1} u_{k-1}|| (the kept beta after a breakdown)."""
         a, be = self.base.alpha_beta()
         k = len(a)
         if k == 0:
             return np.zeros(0)
-        bl = be[k - 1] if len(be) >= k else 0.0
+        if len(be) >= k:
+            bl = be[k - 1]
+        else:
+            u = self.base.vector(k - 1)
+            r = self.op.apply(u) + self.shift * u - a[k - 1] * u
+            if k > 1:
+                r = r - be[k - 2] * self.base.vector(k - 2)
+            bl = np.linalg.norm(r)
         return np.abs(bl * self._S[k - 1, : len(self.eigenvalues)])
 
     def has_warn(self):
