@@ -6,6 +6,7 @@ arnoldi.hpp:537-671) so the parity tests read like the reference's samples.  All
 in libcmpt_b200.so on the GPU; this file only marshals arguments.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -25,6 +26,9 @@ class Context:
             check(lib().cmb_ctx_create_dist(int(device), int(rank), int(nranks), idbuf, C.byref(h)))
         self.h = h
         self.rank, self.nranks, self.device = rank, nranks, device
+        # operators and solvers that use this context: they must be destroyed before it
+        self._ops = weakref.WeakSet()
+        self._solvers = weakref.WeakSet()
 
     @staticmethod
     def nccl_unique_id():
@@ -59,6 +63,10 @@ class Context:
 
     def close(self):
         if self.h:
+            for s in list(self._solvers):
+                s.close()
+            for o in list(self._ops):
+                o.close()
             lib().cmb_ctx_destroy(self.h)
             self.h = None
 
@@ -74,6 +82,7 @@ class DeviceOperator:
 
     def __init__(self, ctx, handle, keep=None):
         self.ctx, self.h, self._keep = ctx, handle, keep
+        ctx._ops.add(self)
 
     @staticmethod
     def from_csr(ctx, rowptr, col, val, n_global=None, row_begin=0):
@@ -178,6 +187,7 @@ class _Solver:
         if isinstance(op, DeviceOperator):
             check(lib().cmbs_set_operator(self.h, op.ctx.h, op.h))
             self._op = op
+            op.ctx._solvers.add(self)
         else:
             cb, _ = _make_callback(op, int(height), self.dtype)
             check(lib().cmbs_set_callback(self.h, int(height), cb, None))
