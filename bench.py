@@ -305,6 +305,8 @@ def run_ours(args):
             barrier()
             if i >= args.warmup:
                 times.append(dt)
+            if os.environ.get("BENCH_DEBUG"):
+                print("e2e iter %d: %.1f ms" % (i, dt * 1e3), file=sys.stderr, flush=True)
             del chk, X
         tot = max_over_ranks(sum(times))
         e2e = {"value": m * len(times) / tot, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -501,7 +501,7 @@ def test_arnoldi_shift_deflation_restart(ctx):
     ref.min_iterations = ref.max_iterations = 30
     ref.max_eigenvalues = 2
     ref.compute()
-    assert abs(es.eigenvalues()[0] - ref.eigenvalues[0]) < 1e-8 * abs(ref.eigenvalues[0])  # unconverged: sensitive
+    assert abs(es.eigenvalues()[0] - ref.eigenvalues[0]) < 1e-6 * abs(ref.eigenvalues[0])  # unconverged: sensitive
     assert _sorted_close(es.eigenvalues(), ref.eigenvalues, 1e-4)
     # explicit restart (cfg 3): each cycle restarts from the leading Ritz vector; the leading Ritz value improves
     es2 = pkg.ArnoldiEigenSolver(np.float64)
