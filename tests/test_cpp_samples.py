@@ -1,0 +1,71 @@
+"""The C++ drop-in headers driven from C++ (samples/*.cpp, built by __graft_entry__.build()): same call
+sequences as the reference's samples, results checked against the known answers."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "samples", "bin")
+
+
+def _run(name, *args):
+    exe = os.path.join(BIN, name)
+    assert os.path.exists(exe), "samples are built by __graft_entry__.build()"
+    p = subprocess.run([exe, *args], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    return p.stdout
+
+
+def test_samples_are_built():
+    for n in ("sample_lanczos1", "sample_lanczos2", "sample_arnoldi", "sample_device_csr"):
+        assert os.path.exists(os.path.join(BIN, n))
+
+
+@pytest.mark.gpu
+def test_sample_lanczos1_legacy_callback():
+    out = _run("sample_lanczos1")
+    ev = [float(x) for x in re.search(r"eigenvalues:(.*)", out).group(1).split()]
+    np.testing.assert_allclose(ev, [2 - np.sqrt(1.5), 2.0, 2 + np.sqrt(1.5)], atol=1e-13)
+    rows = [list(map(float, l.split())) for l in out.split("eigenvectors:\n")[1].splitlines()[:3]]
+    X = np.array(rows)
+    want = np.array([[0.90824829, 0.40824829, 0.09175171], [-0.40824829, 0.81649658, 0.40824829],
+                     [0.09175171, -0.40824829, 0.90824829]])
+    np.testing.assert_allclose(X, want, atol=1e-8)
+    assert "log: INFO      lanczos steps achieved full of Krylov subspace" in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["device", "callback"])
+def test_sample_lanczos2_all_setters(mode):
+    out = _run("sample_lanczos2", *([] if mode == "device" else ["callback"]))
+    assert "matrix height : 200" in out
+    it = int(re.search(r"iterations : (\d+)", out).group(1))
+    rank = int(re.search(r"subspace rank : (\d+)", out).group(1))
+    assert rank == it + 1 and 100 < it < 200
+    ev = [float(x) for x in re.search(r"eigenvalues:(.*)", out).group(1).split()]
+    assert len(ev) == 10 and abs(ev[0] - 2 * np.cos(200 * np.pi / 201)) < 1e-4
+    assert "log: INFO      lanczos steps converged with tolerance" in out
+
+
+@pytest.mark.gpu
+def test_sample_arnoldi():
+    out = _run("sample_arnoldi")
+    m = re.search(r"m=40 max\|AP-PD\| = (\S+)\s+ritz residuals (\S+) (\S+)", out)
+    assert float(m.group(1)) <= max(float(m.group(2)), float(m.group(3))) + 1e-10
+    assert "log: WARN      arnoldi steps achieved maxIterations" in out
+    m = re.search(r"full-krylov n=4: (\d+) eigenvalues, max\|AP-PD\| = (\S+)", out)
+    assert int(m.group(1)) == 4 and float(m.group(2)) < 1e-12
+    assert "log: INFO      arnoldi steps achieved full of Krylov subspace" in out
+
+
+@pytest.mark.gpu
+def test_sample_device_csr_and_continue():
+    out = _run("sample_device_csr", "128", "80")
+    assert "iterations=80" in out and "after continueToCompute: iterations=160" in out
+    low = float(re.search(r"after continueToCompute: iterations=160 lowest (\S+)", out).group(1))
+    exact = float(re.search(r"exact lowest eigenvalue (\S+)\)", out).group(1))
+    assert abs(low - exact) < 1e-5 and low >= exact - 1e-12
+    assert "log: INFO      EigenSolver<ScalarType>::continueToCompute(...) was called" in out
