@@ -64,6 +64,8 @@ def _declare(L):
         "cmb_ctx_profile_get": (i32, [vp, cp, P(dbl), P(C.c_uint64)]),
         "cmb_ctx_flush_l2": (i32, [vp]),
         "cmb_op_csr_create": (i32, [vp, i32, i64, i64, i64, vp, vp, vp, P(vp)]),
+        "cmb_partition_begin": (i64, [i64, i32, i32]),
+        "cmb_plan_halo": (i32, [i64, i32, i32, i64, vp, vp, P(i64), vp, vp, i64]),
         "cmb_op_dense_create": (i32, [vp, i32, i64, i64, i64, vp, P(vp)]),
         "cmb_op_heisenberg_create": (i32, [vp, i32, i32, dbl, i32, P(vp)]),
         "cmb_op_callback_create": (i32, [vp, i32, i64, MATMUL_FN, vp, P(vp)]),

@@ -58,7 +58,7 @@ struct NcclApi {
   const char* (*GetErrorString)(int) = nullptr;
 };
 int nccl_load(NcclApi** api);  // CMB_OK or CMB_ERR_NCCL
-enum { kNcclFloat64 = 8, kNcclInt8 = 0, kNcclSum = 0 };
+enum { kNcclFloat64 = 8, kNcclInt8 = 0, kNcclInt32 = 2, kNcclInt64 = 4, kNcclUint64 = 5, kNcclSum = 0, kNcclMax = 2, kNcclMin = 3 };
 
 struct ProfEntry {
   double ms = 0.0;
@@ -112,6 +112,7 @@ struct LaunchScope {
 int resolve_profile(cmb_ctx* ctx);
 
 int allreduce_sum_f64(cmb_ctx* ctx, double* dev_ptr, size_t count);  // no-op when nranks == 1
+int allreduce_min_u64(cmb_ctx* ctx, unsigned long long* dev_ptr, size_t count);
 
 // driver entry point for tensor-map encoding (no link-time libcuda dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

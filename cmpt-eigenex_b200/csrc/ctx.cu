@@ -117,6 +117,16 @@ int allreduce_sum_f64(cmb_ctx* ctx, double* p, size_t count) {
   return CMB_OK;
 }
 
+int allreduce_min_u64(cmb_ctx* ctx, unsigned long long* p, size_t count) {
+  if (ctx->nranks == 1) return CMB_OK;
+  int r = ctx->nccl->AllReduce(p, p, count, kNcclUint64, kNcclMin, ctx->nccl_comm, ctx->stream);
+  if (r != 0) {
+    set_error("ncclAllReduce(min) failed: %s", ctx->nccl->GetErrorString ? ctx->nccl->GetErrorString(r) : "?");
+    return CMB_ERR_NCCL;
+  }
+  return CMB_OK;
+}
+
 static int ctx_init_common(cmb_ctx* c, int device) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {

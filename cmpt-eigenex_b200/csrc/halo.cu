@@ -1,0 +1,240 @@
+// halo.cu — row-partitioned operators: halo planning (host), NVLink halo exchange (NCCL send/recv groups).
+//
+// The reference has no distributed code; the partition is the one §8(e) defines: rank q owns
+// the contiguous global rows [q*n/P, (q+1)*n/P).  For a CSR shard the plan is
+//   halo_cols   sorted distinct remote columns this rank reads (grouped by owner because owners are ranges)
+//   col_local   column indices remapped to [0, n_local) for owned columns and n_local + position in halo_cols
+//               for remote ones, so the SpMV kernel gathers from one of two base pointers
+// and, after the owners learn what each peer needs, per apply:
+//   pack (gather owned w entries into one contiguous send buffer)  ->  ncclGroup{Send,Recv per peer}  ->  SpMV.
+// The values exchanged are the un-normalised w; 1/beta is a global scalar applied inside the SpMV.
+#include <algorithm>
+#include <thread>
+
+#include "halo.cuh"
+
+namespace cmb {
+
+int64_t partition_begin(int64_t n, int P, int q) { return (int64_t(q) * n) / P; }
+
+static int owner_of(int64_t g, int64_t n, int P) {
+  // smallest q with partition_begin(q+1) > g
+  int q = int((g * P) / n);
+  if (q >= P) q = P - 1;
+  while (q > 0 && partition_begin(n, P, q) > g) --q;
+  while (q < P - 1 && partition_begin(n, P, q + 1) <= g) ++q;
+  return q;
+}
+
+int plan_halo(int64_t n, int P, int rank, int64_t nnz, const int32_t* col, int32_t* col_local,
+              std::vector<int32_t>& halo_cols, std::vector<int64_t>& per_owner) {
+  const int64_t r0 = partition_begin(n, P, rank), r1 = partition_begin(n, P, rank + 1);
+  const int64_t nloc = r1 - r0;
+  // 1. distinct remote columns: per-thread collection, then sort + unique
+  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const unsigned nt = nnz > (1 << 20) ? hw : 1;
+  std::vector<std::vector<int32_t>> parts(nt);
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() {
+        const int64_t a = nnz * t / nt, b = nnz * (t + 1) / nt;
+        auto& v = parts[t];
+        int32_t last = -1;
+        for (int64_t i = a; i < b; ++i) {
+          const int32_t c = col[i];
+          if ((c < r0 || c >= r1) && c != last) {
+            v.push_back(c);
+            last = c;
+          }
+        }
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+      });
+    for (auto& t : th) t.join();
+  }
+  halo_cols.clear();
+  for (auto& v : parts) halo_cols.insert(halo_cols.end(), v.begin(), v.end());
+  std::sort(halo_cols.begin(), halo_cols.end());
+  halo_cols.erase(std::unique(halo_cols.begin(), halo_cols.end()), halo_cols.end());
+  for (int32_t c : halo_cols)
+    if (c < 0 || c >= n) {
+      set_error("column index %d out of range [0,%lld)", int(c), (long long)n);
+      return CMB_ERR_INVALID;
+    }
+  per_owner.assign(P, 0);
+  for (int32_t c : halo_cols) per_owner[owner_of(c, n, P)]++;
+  // 2. remap
+  if (col_local) {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() {
+        const int64_t a = nnz * t / nt, b = nnz * (t + 1) / nt;
+        for (int64_t i = a; i < b; ++i) {
+          const int32_t c = col[i];
+          if (c >= r0 && c < r1) {
+            col_local[i] = int32_t(c - r0);
+          } else {
+            const auto it = std::lower_bound(halo_cols.begin(), halo_cols.end(), c);
+            col_local[i] = int32_t(nloc + (it - halo_cols.begin()));
+          }
+        }
+      });
+    for (auto& t : th) t.join();
+  }
+  return CMB_OK;
+}
+
+// ---- NCCL helpers --------------------------------------------------------------------------------------
+static int nccl_check(cmb_ctx* ctx, int r, const char* what) {
+  if (r != 0) {
+    set_error("%s failed: %s", what, ctx->nccl->GetErrorString ? ctx->nccl->GetErrorString(r) : "?");
+    return CMB_ERR_NCCL;
+  }
+  return CMB_OK;
+}
+
+template <int ES>
+__global__ void pack_kernel(const double* __restrict__ w, const int* __restrict__ idx, long long count,
+                            double* __restrict__ out, const int* __restrict__ halt) {
+  if (*halt) return;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const long long s = idx[i];
+#pragma unroll
+    for (int e = 0; e < ES; ++e) out[i * ES + e] = w[s * ES + e];
+  }
+}
+
+HaloExchange::~HaloExchange() {
+  cudaFree(d_send_idx);
+  cudaFree(d_sendbuf);
+  cudaFree(d_halo);
+}
+
+int HaloExchange::setup(cmb_ctx* ctx, int64_t n, int es_, const std::vector<int32_t>& halo_cols,
+                        const std::vector<int64_t>& per_owner) {
+  P = ctx->nranks;
+  rank = ctx->rank;
+  es = es_;
+  const int64_t r0 = partition_begin(n, P, rank);
+  recv_off.assign(P + 1, 0);
+  for (int q = 0; q < P; ++q) recv_off[q + 1] = recv_off[q] + per_owner[q];
+  nrecv = recv_off[P];
+  // 1. everybody learns the P x P matrix of counts: allreduce of a matrix in which each rank fills its row
+  double* d_cnt = nullptr;
+  CMB_CUDA(cudaMalloc(&d_cnt, sizeof(double) * P * P));
+  std::vector<double> cnt(size_t(P) * P, 0.0);
+  for (int q = 0; q < P; ++q) cnt[size_t(rank) * P + q] = double(per_owner[q]);
+  CMB_CUDA(cudaMemcpyAsync(d_cnt, cnt.data(), sizeof(double) * P * P, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = allreduce_sum_f64(ctx, d_cnt, size_t(P) * P);
+  if (rc == CMB_OK) {
+    cudaError_t e = cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(double) * P * P, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      set_error("halo setup: %s", cudaGetErrorString(e));
+      rc = CMB_ERR_CUDA;
+    }
+  }
+  cudaFree(d_cnt);
+  CMB_TRY(rc);
+  send_off.assign(P + 1, 0);
+  for (int q = 0; q < P; ++q) send_off[q + 1] = send_off[q] + int64_t(cnt[size_t(q) * P + rank]);  // what q needs from me
+  nsend = send_off[P];
+  // 2. exchange the index lists (global column numbers), then localise the ones I have to serve
+  int32_t* d_need = nullptr;
+  CMB_CUDA(cudaMalloc(&d_need, sizeof(int32_t) * std::max<int64_t>(nrecv, 1)));
+  CMB_CUDA(cudaMalloc(&d_send_idx, sizeof(int32_t) * std::max<int64_t>(nsend, 1)));
+  CMB_CUDA(cudaMemcpyAsync(d_need, halo_cols.data(), sizeof(int32_t) * nrecv, cudaMemcpyHostToDevice, ctx->stream));
+  rc = nccl_check(ctx, ctx->nccl->GroupStart(), "ncclGroupStart");
+  for (int q = 0; q < P && rc == CMB_OK; ++q) {
+    if (q == rank) continue;
+    if (recv_off[q + 1] > recv_off[q])
+      rc = nccl_check(ctx, ctx->nccl->Send(d_need + recv_off[q], size_t(recv_off[q + 1] - recv_off[q]), kNcclInt32, q,
+                                           ctx->nccl_comm, ctx->stream), "ncclSend");
+    if (rc == CMB_OK && send_off[q + 1] > send_off[q])
+      rc = nccl_check(ctx, ctx->nccl->Recv(d_send_idx + send_off[q], size_t(send_off[q + 1] - send_off[q]), kNcclInt32, q,
+                                           ctx->nccl_comm, ctx->stream), "ncclRecv");
+  }
+  if (rc == CMB_OK) rc = nccl_check(ctx, ctx->nccl->GroupEnd(), "ncclGroupEnd");
+  else ctx->nccl->GroupEnd();
+  std::vector<int32_t> sidx(std::max<int64_t>(nsend, 1));
+  if (rc == CMB_OK) {
+    cudaError_t e = cudaMemcpyAsync(sidx.data(), d_send_idx, sizeof(int32_t) * nsend, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      set_error("halo setup: %s", cudaGetErrorString(e));
+      rc = CMB_ERR_CUDA;
+    }
+  }
+  cudaFree(d_need);
+  CMB_TRY(rc);
+  const int64_t nloc = partition_begin(n, P, rank + 1) - r0;
+  for (int64_t i = 0; i < nsend; ++i) {
+    const int64_t l = int64_t(sidx[i]) - r0;
+    if (l < 0 || l >= nloc) {
+      set_error("halo setup: peer asked for row %d which rank %d does not own", int(sidx[i]), rank);
+      return CMB_ERR_INVALID;
+    }
+    sidx[i] = int32_t(l);
+  }
+  CMB_CUDA(cudaMemcpyAsync(d_send_idx, sidx.data(), sizeof(int32_t) * nsend, cudaMemcpyHostToDevice, ctx->stream));
+  CMB_CUDA(cudaMalloc(&d_sendbuf, sizeof(double) * es * std::max<int64_t>(nsend, 1)));
+  CMB_CUDA(cudaMalloc(&d_halo, sizeof(double) * es * std::max<int64_t>(nrecv, 1)));
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CMB_OK;
+}
+
+int HaloExchange::exchange(cmb_ctx* ctx, const double* w, const int* halt) {
+  if (nsend > 0) {
+    LaunchScope ls(ctx, "halo_pack");
+    const int grid = int(std::max<int64_t>(1, std::min<int64_t>((nsend + 255) / 256, int64_t(ctx->num_sms) * 8)));
+    if (es == 2)
+      pack_kernel<2><<<grid, 256, 0, ctx->stream>>>(w, d_send_idx, nsend, d_sendbuf, halt);
+    else
+      pack_kernel<1><<<grid, 256, 0, ctx->stream>>>(w, d_send_idx, nsend, d_sendbuf, halt);
+    CMB_CUDA(cudaGetLastError());
+  }
+  int rc = nccl_check(ctx, ctx->nccl->GroupStart(), "ncclGroupStart");
+  for (int q = 0; q < P && rc == CMB_OK; ++q) {
+    if (q == rank) continue;
+    if (send_off[q + 1] > send_off[q])
+      rc = nccl_check(ctx, ctx->nccl->Send(d_sendbuf + send_off[q] * es, size_t(send_off[q + 1] - send_off[q]) * es,
+                                           kNcclFloat64, q, ctx->nccl_comm, ctx->stream), "ncclSend");
+    if (rc == CMB_OK && recv_off[q + 1] > recv_off[q])
+      rc = nccl_check(ctx, ctx->nccl->Recv(d_halo + recv_off[q] * es, size_t(recv_off[q + 1] - recv_off[q]) * es,
+                                           kNcclFloat64, q, ctx->nccl_comm, ctx->stream), "ncclRecv");
+  }
+  if (rc == CMB_OK) rc = nccl_check(ctx, ctx->nccl->GroupEnd(), "ncclGroupEnd");
+  else ctx->nccl->GroupEnd();
+  return rc;
+}
+
+}  // namespace cmb
+
+using namespace cmb;
+
+extern "C" {
+
+int64_t cmb_partition_begin(int64_t n_global, int nranks, int rank) {
+  if (nranks <= 0 || rank < 0 || rank > nranks || n_global < 0) return -1;
+  return partition_begin(n_global, nranks, rank);
+}
+
+int cmb_plan_halo(int64_t n_global, int nranks, int rank, int64_t nnz, const int32_t* col, int32_t* col_local,
+                  int64_t* halo_count, int64_t* per_owner_counts, int32_t* halo_cols_out, int64_t halo_capacity) {
+  CMB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks && n_global >= 0 && nnz >= 0, "bad partition");
+  CMB_REQUIRE(nnz == 0 || col, "null column array");
+  std::vector<int32_t> halo;
+  std::vector<int64_t> per;
+  CMB_TRY(plan_halo(n_global, nranks, rank, nnz, col, col_local, halo, per));
+  if (halo_count) *halo_count = int64_t(halo.size());
+  if (per_owner_counts) std::copy(per.begin(), per.end(), per_owner_counts);
+  if (halo_cols_out) {
+    CMB_REQUIRE(halo_capacity >= int64_t(halo.size()), "halo_cols capacity too small");
+    std::copy(halo.begin(), halo.end(), halo_cols_out);
+  }
+  return CMB_OK;
+}
+
+}  // extern "C"

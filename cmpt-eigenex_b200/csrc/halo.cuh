@@ -1,0 +1,27 @@
+// halo.cuh — row partition + halo exchange interfaces (halo.cu).
+#pragma once
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace cmb {
+
+int64_t partition_begin(int64_t n, int P, int q);
+// host-only: distinct remote columns (sorted), per-owner counts, and the remapped column array
+int plan_halo(int64_t n, int P, int rank, int64_t nnz, const int32_t* col, int32_t* col_local,
+              std::vector<int32_t>& halo_cols, std::vector<int64_t>& per_owner);
+
+struct HaloExchange {
+  int P = 1, rank = 0, es = 1;
+  int64_t nsend = 0, nrecv = 0;
+  std::vector<int64_t> send_off, recv_off;
+  int32_t* d_send_idx = nullptr;
+  double* d_sendbuf = nullptr;
+  double* d_halo = nullptr;
+  ~HaloExchange();
+  int setup(cmb_ctx* ctx, int64_t n_global, int es, const std::vector<int32_t>& halo_cols,
+            const std::vector<int64_t>& per_owner);
+  int exchange(cmb_ctx* ctx, const double* w, const int* halt);
+};
+
+}  // namespace cmb

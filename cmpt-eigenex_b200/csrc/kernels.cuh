@@ -34,7 +34,9 @@ int vec_scale_phase(cmb_ctx* ctx, bool cplx, double* x, const double* nrm2, cons
 // widen a real vector to complex (re, 0)
 int vec_real_to_complex(cmb_ctx* ctx, const double* x, double* z, int64_t n);
 // finds the index of the first element (scalar index) with |x_i| > 0; writes it to out (INT64_MAX if none)
-int vec_first_nonzero(cmb_ctx* ctx, bool cplx, const double* x, int64_t n_scalars, unsigned long long* out);
+int vec_first_nonzero(cmb_ctx* ctx, bool cplx, const double* x, int64_t n_scalars, int64_t offset, unsigned long long* out);
+int vec_pick_element(cmb_ctx* ctx, const double* x, const unsigned long long* idx, int64_t offset, int64_t n, int es,
+                     double* out);
 
 // Per-step scalars every operator-apply kernel reads (device memory, filled by earlier launches):
 // nrm2 -> beta = sqrt(nrm2); if beta <= threshold the chain halts (lanczos.hpp:433-437).

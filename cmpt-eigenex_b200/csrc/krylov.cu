@@ -445,7 +445,7 @@ int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, d
       sc.beta_slot = K->scal + 3;
       sc.alpha_slot = K->alpha_dev;
       CMB_TRY(op->apply(K->w, K->col(K->ndefl), K->v, shift, 0.0, sc));
-      CMB_TRY(allreduce_sum_f64(ctx, K->alpha_dev, 1));
+      if (interval != 1) CMB_TRY(allreduce_sum_f64(ctx, K->alpha_dev, 1));
       K->bytes += op->bytes + 3.0 * double(K->n_local) * (K->cplx ? 16.0 : 8.0);
       K->nk = 1;  // the first call cannot break down on the device side
       continue;
@@ -462,7 +462,8 @@ int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, d
     sc.beta_slot = K->beta_dev + k;
     sc.alpha_slot = K->alpha_dev + size_t(k + 1) * 2;
     CMB_TRY(op->apply(K->w, K->col(K->ndefl + k + 1), K->v, shift, 0.0, sc));
-    CMB_TRY(allreduce_sum_f64(ctx, K->alpha_dev + size_t(k + 1) * 2, 1));
+    // with full reorthogonalisation alpha is only read by the host: one allreduce for the whole chain (below)
+    if (interval != 1) CMB_TRY(allreduce_sum_f64(ctx, K->alpha_dev + size_t(k + 1) * 2, 1));
     add_step_bytes(K, op, c);
     ++enq;
   }
@@ -474,6 +475,7 @@ int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, d
   const int nb = enq;
   CMB_TRY(ensure_stage(K, size_t(2 * na + nb + 8)));
   double* hs = K->h_stage;
+  if (interval == 1 && na) CMB_TRY(allreduce_sum_f64(ctx, K->alpha_dev + size_t(a0) * 2, size_t(2) * na));
   if (na) CMB_CUDA(cudaMemcpyAsync(hs, K->alpha_dev + size_t(a0) * 2, sizeof(double) * 2 * na, cudaMemcpyDeviceToHost, ctx->stream));
   if (nb) CMB_CUDA(cudaMemcpyAsync(hs + 2 * na, K->beta_dev + b0, sizeof(double) * nb, cudaMemcpyDeviceToHost, ctx->stream));
   CMB_CUDA(cudaMemcpyAsync(hs + 2 * na + nb, K->halt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -627,10 +629,6 @@ int cmb_krylov_ritz_vectors(cmb_krylov* K, cmb_dtype coef_dtype, const void* coe
   cmb_ctx* ctx = K->ctx;
   CMB_CUDA(cudaSetDevice(ctx->device));
   if (nev == 0) return CMB_OK;
-  if (ctx->nranks > 1) {
-    set_error("Ritz-vector assembly is single-rank in this build");
-    return CMB_ERR_UNSUPPORTED;
-  }
   const int ces = ccplx ? 2 : 1;
   const bool widen = ccplx && !K->cplx;  // real basis, complex coefficients (ArnoldiEigenSolver<double>)
   CMB_TRY(ensure_tmp(K, &K->tmp1, K->ld));
@@ -678,17 +676,13 @@ int cmb_krylov_ritz_vectors(cmb_krylov* K, cmb_dtype coef_dtype, const void* coe
     // host sync needed because the staging buffer is reused per vector
     CMB_CUDA(cudaStreamSynchronize(ctx->stream));
     // phase of the first non-zero element (lanczos.hpp:806-813) and normalisation (:816)
-    CMB_TRY(vec_first_nonzero(ctx, ccplx, xdev, K->n_local, K->d_idx));
-    unsigned long long idx = 0;
-    CMB_CUDA(cudaMemcpyAsync(&idx, K->d_idx, sizeof(idx), cudaMemcpyDeviceToHost, ctx->stream));
-    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
-    // copy the phase element aside first: the scaling kernel overwrites it while other CTAs still read it
-    const double* phase_src = nullptr;
-    if (idx != ~0ull) {
-      CMB_CUDA(cudaMemcpyAsync(K->scal + 6, xdev + idx * out_es, sizeof(double) * out_es, cudaMemcpyDeviceToDevice,
-                               ctx->stream));
-      phase_src = K->scal + 6;
-    }
+    // global index of the first non-zero element (min over ranks); its owner contributes the value, which is
+    // copied aside because the scaling kernel overwrites it while other CTAs still read it
+    CMB_TRY(vec_first_nonzero(ctx, ccplx, xdev, K->n_local, K->row_begin, K->d_idx));
+    CMB_TRY(allreduce_min_u64(ctx, K->d_idx, 1));
+    CMB_TRY(vec_pick_element(ctx, xdev, K->d_idx, K->row_begin, K->n_local, int(out_es), K->scal + 6));
+    CMB_TRY(allreduce_sum_f64(ctx, K->scal + 6, out_es));
+    const double* phase_src = K->scal + 6;  // (0,0) when the vector is identically zero: no phase change
     CMB_TRY(vec_scale_phase(ctx, ccplx, xdev, K->scal + 1, phase_src, widen ? 2 * K->ld : K->ld));
     CMB_CUDA(cudaMemcpyAsync(static_cast<char*>(x_host) + size_t(e) * ldx * out_es * sizeof(double), xdev,
                              sizeof(double) * K->n_local * out_es, cudaMemcpyDeviceToHost, ctx->stream));

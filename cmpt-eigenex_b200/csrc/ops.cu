@@ -12,6 +12,7 @@
 #include <algorithm>
 
 #include "device_utils.cuh"
+#include "halo.cuh"
 #include "op.cuh"
 
 namespace cmb {
@@ -132,22 +133,28 @@ struct SellOp : cmb_op {
   long long* d_slice_ptr = nullptr;
   int* d_col = nullptr;
   double* d_val = nullptr;
-  double* d_halo = nullptr;
+  HaloExchange* halo = nullptr;  // row-partitioned shards only
   long long padded_nnz = 0, nnz = 0;
   ~SellOp() override {
     cudaFree(d_slice_ptr);
     cudaFree(d_col);
     cudaFree(d_val);
-    cudaFree(d_halo);
+    delete halo;
   }
   int apply(const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) override {
+    const double* d_halo = nullptr;
+    if (halo) {
+      // NVLink halo exchange of the un-normalised w (1/beta is applied inside the SpMV)
+      CMB_TRY(halo->exchange(ctx, w, sc.halt));
+      d_halo = halo->d_halo;
+    }
     long long blocks = (nslices + 7) / 8;
     int grid = int(std::min<long long>(blocks, (long long)ctx->num_sms * 8));
     if (grid < 1) grid = 1;
     LaunchScope ls(ctx, "spmv_sell");
     if (cplx)
-      spmv_sell_kernel<true><<<grid, 256, 0, ctx->stream>>>(d_slice_ptr, d_col, d_val, n_local, nslices, w, d_halo, ucol,
-                                                            v, shr, shi, sc, ctx->d_partial, ctx->d_ticket + 1);
+      spmv_sell_kernel<true><<<grid, 256, 0, ctx->stream>>>(d_slice_ptr, d_col, d_val, n_local, nslices, w, d_halo,
+                                                            ucol, v, shr, shi, sc, ctx->d_partial, ctx->d_ticket + 1);
     else
       spmv_sell_kernel<false><<<grid, 256, 0, ctx->stream>>>(d_slice_ptr, d_col, d_val, n_local, nslices, w, d_halo,
                                                              ucol, v, shr, shi, sc, ctx->d_partial, ctx->d_ticket + 1);
@@ -430,23 +437,42 @@ int cmb_op_csr_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t r
   const int64_t n = row_end - row_begin;
   CMB_REQUIRE(rowptr[0] == 0 && rowptr[n] >= 0, "rowptr must start at 0");
   CMB_REQUIRE(rowptr[n] == 0 || (col && val), "null col/val");
-  if (ctx->nranks > 1) {
-    set_error("distributed CSR operators: use cmb_op_csr_create on a single-rank context in this build");
-    return CMB_ERR_UNSUPPORTED;
-  }
   CMB_CUDA(cudaSetDevice(ctx->device));
   SellOp* op = new (std::nothrow) SellOp();
   if (!op) return CMB_ERR_NOMEM;
   op_common(op, ctx, dtype, n_global, row_begin, row_end);
   op->family = "spmv_sell";
-  int rc = build_sell(op, rowptr, col, val);
+  int rc = CMB_OK;
+  if (ctx->nranks > 1) {
+    // row-partitioned shard: the uniform partition of SURVEY.md §8(e) is required
+    if (row_begin != partition_begin(n_global, ctx->nranks, ctx->rank) ||
+        row_end != partition_begin(n_global, ctx->nranks, ctx->rank + 1)) {
+      set_error("rank %d must own rows [%lld,%lld) of the uniform partition", ctx->rank,
+                (long long)partition_begin(n_global, ctx->nranks, ctx->rank),
+                (long long)partition_begin(n_global, ctx->nranks, ctx->rank + 1));
+      delete op;
+      return CMB_ERR_INVALID;
+    }
+    std::vector<int32_t> col_local(size_t(std::max<int64_t>(rowptr[n], 1)));
+    std::vector<int32_t> halo_cols;
+    std::vector<int64_t> per_owner;
+    rc = plan_halo(n_global, ctx->nranks, ctx->rank, rowptr[n], col, col_local.data(), halo_cols, per_owner);
+    if (rc == CMB_OK) {
+      op->halo = new (std::nothrow) HaloExchange();
+      rc = op->halo ? op->halo->setup(ctx, n_global, op->cplx ? 2 : 1, halo_cols, per_owner) : CMB_ERR_NOMEM;
+    }
+    if (rc == CMB_OK) rc = build_sell(op, rowptr, col_local.data(), val);
+  } else {
+    rc = build_sell(op, rowptr, col, val);
+  }
   if (rc != CMB_OK) {
     delete op;
     return rc;
   }
   const double s = op->cplx ? 16.0 : 8.0;
-  // nnz*(s+idx) + (n+1)*ptr + 2*n*s with idx = ptr = 4
-  op->bytes = double(op->nnz) * (s + 4.0) + double(n + 1) * 4.0 + 2.0 * double(n) * s;
+  // nnz*(s+idx) + (n+1)*ptr + 2*n*s with idx = ptr = 4 (+ the halo values read once)
+  op->bytes = double(op->nnz) * (s + 4.0) + double(n + 1) * 4.0 + 2.0 * double(n) * s +
+              (op->halo ? double(op->halo->nrecv) * s : 0.0);
   *out = op;
   return CMB_OK;
 }

@@ -168,31 +168,51 @@ int vec_real_to_complex(cmb_ctx* ctx, const double* x, double* z, int64_t n) {
 
 template <bool CPLX>
 __global__ void __launch_bounds__(256)
-first_nonzero_kernel(const double* __restrict__ x, long long n, unsigned long long* __restrict__ out) {
+first_nonzero_kernel(const double* __restrict__ x, long long n, long long offset, unsigned long long* __restrict__ out) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    if ((unsigned long long)i >= *reinterpret_cast<volatile unsigned long long*>(out)) return;  // an earlier index won
+    if ((unsigned long long)(i + offset) >= *reinterpret_cast<volatile unsigned long long*>(out)) return;  // an earlier index won
     bool nz;
     if (CPLX)
       nz = (x[2 * i] != 0.0) || (x[2 * i + 1] != 0.0);
     else
       nz = x[i] != 0.0;
     if (nz) {
-      atomicMin(out, (unsigned long long)i);
+      atomicMin(out, (unsigned long long)(i + offset));
       return;
     }
   }
 }
 
-int vec_first_nonzero(cmb_ctx* ctx, bool cplx, const double* x, int64_t n, unsigned long long* out) {
+// out[0] = global index (local index + offset) of the first element with |x_i| > 0, ULLONG_MAX if none
+int vec_first_nonzero(cmb_ctx* ctx, bool cplx, const double* x, int64_t n, int64_t offset, unsigned long long* out) {
   CMB_CUDA(cudaMemsetAsync(out, 0xff, sizeof(unsigned long long), ctx->stream));
   if (n == 0) return CMB_OK;
   const int grid = stream_grid(ctx, n, 256);
   LaunchScope ls(ctx, "vec_first_nonzero");
   if (cplx)
-    first_nonzero_kernel<true><<<grid, 256, 0, ctx->stream>>>(x, n, out);
+    first_nonzero_kernel<true><<<grid, 256, 0, ctx->stream>>>(x, n, offset, out);
   else
-    first_nonzero_kernel<false><<<grid, 256, 0, ctx->stream>>>(x, n, out);
+    first_nonzero_kernel<false><<<grid, 256, 0, ctx->stream>>>(x, n, offset, out);
+  CMB_CUDA(cudaGetLastError());
+  return CMB_OK;
+}
+
+// out[0..es) = x[idx - offset] if the global index idx[0] falls into this rank's rows, else 0
+__global__ void pick_element_kernel(const double* __restrict__ x, const unsigned long long* __restrict__ idx,
+                                    long long offset, long long n, int es, double* __restrict__ out) {
+  const unsigned long long g = idx[0];
+  for (int e = 0; e < es; ++e) {
+    double v = 0.0;
+    if (g != ~0ull && (long long)g >= offset && (long long)g < offset + n) v = x[((long long)g - offset) * es + e];
+    out[e] = v;
+  }
+}
+
+int vec_pick_element(cmb_ctx* ctx, const double* x, const unsigned long long* idx, int64_t offset, int64_t n, int es,
+                     double* out) {
+  LaunchScope ls(ctx, "vec_first_nonzero");
+  pick_element_kernel<<<1, 1, 0, ctx->stream>>>(x, idx, offset, n, es, out);
   CMB_CUDA(cudaGetLastError());
   return CMB_OK;
 }

@@ -83,6 +83,13 @@ int cmb_ctx_flush_l2(cmb_ctx* ctx);
  * on the device to SELL-32 and, in a distributed context, its halo lists are built. */
 int cmb_op_csr_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t row_begin, int64_t row_end,
                       const int64_t* rowptr, const int32_t* col, const void* val, cmb_op** out);
+/* the uniform row partition every distributed object uses: rank q owns [begin(q), begin(q+1)) */
+int64_t cmb_partition_begin(int64_t n_global, int nranks, int rank);
+/* host-only (no GPU): halo plan of a CSR shard under that partition.  col_local (nnz entries, may be NULL)
+ * receives the remapped column indices: owned columns -> [0,n_local), remote ones -> n_local + position in the
+ * sorted list of distinct remote columns; halo_cols (capacity entries, may be NULL) receives that list. */
+int cmb_plan_halo(int64_t n_global, int nranks, int rank, int64_t nnz, const int32_t* col, int32_t* col_local,
+                  int64_t* halo_count, int64_t* per_owner_counts, int32_t* halo_cols, int64_t halo_capacity);
 /* dense row-major rows [row_begin,row_end) x n_global (cfg 1) */
 int cmb_op_dense_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t row_begin, int64_t row_end,
                         const void* a_rows, cmb_op** out);

@@ -1,0 +1,166 @@
+"""Worker of the multi-rank tests: launched by torch.distributed.run, one process per GPU (or, with
+--cpu, one process per rank on the CPU for the host-side logic only)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import cmpt_eigenex_b200 as pkg  # noqa: E402
+from cmpt_eigenex_b200 import capi, dist  # noqa: E402
+from cmpt_eigenex_b200 import synthetic as syn  # noqa: E402
+
+
+def gather_rows(local, n, td):
+    import torch
+
+    world = td.get_world_size()
+    parts = [None] * world
+    td.all_gather_object(parts, np.asarray(local))
+    return np.concatenate(parts)
+
+
+def cpu_main():
+    """host-side logic at world_size 2 over gloo: partition, halo plans, id broadcast."""
+    import ctypes as C
+
+    import torch
+
+    td = dist.init()
+    rank, world = td.get_rank(), td.get_world_size()
+    L = capi.lib()
+    N = 12
+    n = N * N
+    r0, r1 = dist.row_range(n)
+    assert (r0, r1) == (L.cmb_partition_begin(n, world, rank), L.cmb_partition_begin(n, world, rank + 1))
+    rp, c, v = syn.laplacian2d_csr(N, r0, r1)
+    col_local = np.empty_like(c)
+    cnt = C.c_int64()
+    per = np.zeros(world, np.int64)
+    halo = np.empty(c.size, np.int32)
+    capi.check(L.cmb_plan_halo(n, world, rank, c.size, capi.ptr(c), capi.ptr(col_local), C.byref(cnt), capi.ptr(per),
+                               capi.ptr(halo), halo.size))
+    halo = halo[: cnt.value]
+    # what I need is exactly the set of remote columns, owned by the other rank
+    remote = np.unique(c[(c < r0) | (c >= r1)])
+    assert np.array_equal(halo, remote) and per[rank] == 0 and per.sum() == halo.size
+    assert halo.size == N  # one grid line of the neighbour block
+    own = (c >= r0) & (c < r1)
+    assert np.array_equal(col_local[own], c[own] - r0)
+    assert np.array_equal(halo[col_local[~own] - (r1 - r0)], c[~own])
+    # the lists are consistent across ranks: every index I ask for is owned by the peer
+    lists = [None] * world
+    td.all_gather_object(lists, (r0, r1, halo.tolist()))
+    for q, (q0, q1, need) in enumerate(lists):
+        for g in need:
+            owner = [k for k, (a, b, _) in enumerate(lists) if a <= g < b]
+            assert owner and owner[0] != q
+    # 128-byte token broadcast (the path the NCCL id takes)
+    tok = np.arange(128, dtype=np.uint8) if rank == 0 else np.zeros(128, np.uint8)
+    t = torch.from_numpy(tok)
+    td.broadcast(t, src=0)
+    assert np.array_equal(t.numpy(), np.arange(128, dtype=np.uint8))
+    assert dist.all_max(float(rank)) == world - 1 and dist.all_sum(1.0) == world
+    td.barrier()
+    if rank == 0:
+        print("DIST_CPU_OK")
+
+
+def gpu_main():
+    from oracle import core
+    from oracle import reference_solvers as rs
+
+    td = dist.init()
+    rank, world = td.get_rank(), td.get_world_size()
+    ctx = dist.make_context()
+    core.set_num_threads(2)
+    results = {}
+    for name in ("laplacian", "heisenberg", "convdiff_arnoldi"):
+        if name == "laplacian":
+            N, m = 40, 60
+            n = N * N
+            full = syn.laplacian2d_csr(N)
+            r0, r1 = dist.row_range(n)
+            shard = syn.laplacian2d_csr(N, r0, r1)
+        elif name == "heisenberg":
+            Ls, m = 12, 40
+            n = 1 << Ls
+            full = syn.heisenberg_csr(Ls)
+            r0, r1 = dist.row_range(n)
+            shard = syn.heisenberg_csr(Ls, r0=r0, r1=r1)
+        else:
+            M, m = 9, 30
+            n = M ** 3
+            full = syn.convdiff3d_csr(M)
+            r0, r1 = dist.row_range(n)
+            shard = syn.convdiff3d_csr(M, r0=r0, r1=r1)
+        x0 = syn.start_vector(n, seed=7)
+        op = pkg.DeviceOperator.from_csr(ctx, *shard, n_global=n, row_begin=r0)
+        # operator apply: local slab of A x
+        y = op.apply(x0[r0:r1])
+        yr = core.Operator.csr(*full).apply(x0)
+        assert np.abs(y - yr[r0:r1]).max() < 1e-13, name
+        if name != "convdiff_arnoldi":
+            es = pkg.LanczosEigenSolver()
+            es.setMatrixMultiplication(op).setInitialVector(x0[r0:r1])
+            es.setMinIterations(m).setMaxIterations(m).setMaxEigenvalues(3).setIndicesForConvergence([0, 1, 2])
+            es.compute()
+            ref = rs.LanczosEigenSolver("d")
+            ref.set_matrix_multiplication(core.Operator.csr(*full))
+            ref.init = x0
+            ref.min_iterations = ref.max_iterations = m
+            ref.max_eigenvalues = 3
+            ref.indices_for_convergence = [0, 1, 2]
+            ref.compute()
+            ra, rb = ref.alpha_beta()
+            assert es.iterations() == m
+            assert np.abs(es.alpha() - ra).max() < 1e-11 and np.abs(es.beta() - rb).max() < 1e-11, name
+            assert np.abs(es.eigenvalues() - ref.eigenvalues).max() < 1e-10 * np.abs(ra).max(), name
+            X = es.eigenvectors()
+            assert X.shape == (r1 - r0, 3)
+            Xfull = gather_rows(X, n, td)
+            ov = np.abs(np.sum(ref.eigenvectors * Xfull, axis=0))
+            assert np.abs(ov - 1).max() < 1e-8, (name, ov)
+            assert np.all(Xfull[0] > 0)
+            assert es.log() == ref.log
+            rr = es.ritzResiduals()
+            assert np.abs(rr - ref.ritz_residuals()).max() < 1e-9
+            results[name] = es.eigenvalues()
+            es.close()
+        else:
+            es = pkg.ArnoldiEigenSolver(np.float64)
+            es.setMatrixMultiplication(op).setInitialVector(x0[r0:r1])
+            es.setMinIterations(m).setMaxIterations(m).setMaxEigenvalues(2)
+            es.compute()
+            ref = rs.ArnoldiEigenSolver("d")
+            ref.set_matrix_multiplication(core.Operator.csr(*full))
+            ref.init = x0
+            ref.min_iterations = ref.max_iterations = m
+            ref.max_eigenvalues = 2
+            ref.compute()
+            assert abs(es.eigenvalues()[0] - ref.eigenvalues[0]) < 1e-8 * abs(ref.eigenvalues[0]), name
+            H = es.hessenbergMatrix()
+            assert np.abs(H[:, :6] - ref.hessenberg[:, :6]).max() < 1e-11
+            P = gather_rows(es.eigenvectors(), n, td)
+            assert np.abs(np.linalg.norm(P, axis=0) - 1).max() < 1e-12
+            A = np.zeros((n, n))
+            rp, c, v = full
+            for r in range(n):
+                A[r, c[rp[r]:rp[r + 1]]] = v[rp[r]:rp[r + 1]]
+            res = np.linalg.norm(A @ P - P * es.eigenvalues(), axis=0)
+            assert np.all(np.abs(res - es.ritzResiduals()) < 1e-9)
+            es.close()
+        op.close()
+    td.barrier()
+    ctx.close()
+    if rank == 0:
+        print("DIST_GPU_OK", {k: v.tolist() for k, v in results.items()})
+
+
+if __name__ == "__main__":
+    if "--cpu" in sys.argv:
+        cpu_main()
+    else:
+        gpu_main()

@@ -1,0 +1,65 @@
+"""Multi-rank paths.  CPU: world_size-2 over gloo (partition, halo plans, id broadcast).  GPU: 2 ranks on 2
+B200s against the oracle (skipped on a 1-GPU box)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from cmpt_eigenex_b200 import capi
+from cmpt_eigenex_b200 import synthetic as syn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torchrun(nproc, *args, timeout=600):
+    env = dict(os.environ)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", "29631", os.path.join(ROOT, "tests", "dist_worker.py"), *args]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+
+
+def test_partition_and_halo_plan_single_process():
+    L = capi.lib()
+    n, P = 1000, 8
+    b = [L.cmb_partition_begin(n, P, q) for q in range(P + 1)]
+    assert b[0] == 0 and b[-1] == n and all(b[i] < b[i + 1] for i in range(P))
+    # Heisenberg shard: remote columns are found, sorted, grouped by owner, and the remap is consistent
+    Ls, P, rank = 10, 4, 2
+    n = 1 << Ls
+    r0, r1 = L.cmb_partition_begin(n, P, rank), L.cmb_partition_begin(n, P, rank + 1)
+    rp, c, v = syn.heisenberg_csr(Ls, r0=r0, r1=r1)
+    col_local = np.empty_like(c)
+    cnt, per = C.c_int64(), np.zeros(P, np.int64)
+    halo = np.empty(c.size, np.int32)
+    capi.check(L.cmb_plan_halo(n, P, rank, c.size, capi.ptr(c), capi.ptr(col_local), C.byref(cnt), capi.ptr(per),
+                               capi.ptr(halo), halo.size))
+    halo = halo[: cnt.value]
+    remote = np.unique(c[(c < r0) | (c >= r1)])
+    assert np.array_equal(halo, remote)
+    owners = np.searchsorted(np.array([L.cmb_partition_begin(n, P, q) for q in range(1, P + 1)]), halo, side="right")
+    assert np.array_equal(np.bincount(owners, minlength=P), per) and per[rank] == 0
+    own = (c >= r0) & (c < r1)
+    assert np.array_equal(col_local[own], c[own] - r0)
+    assert np.array_equal(halo[col_local[~own] - (r1 - r0)], c[~own])
+    # out-of-range column is rejected
+    bad = c.copy()
+    bad[0] = n + 5
+    assert L.cmb_plan_halo(n, P, rank, bad.size, capi.ptr(bad), None, None, None, None, 0) != 0
+
+
+def test_world_size_2_gloo_cpu():
+    p = _torchrun(2, "--cpu")
+    assert p.returncode == 0 and "DIST_CPU_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+
+
+@pytest.mark.gpu
+def test_two_ranks_on_two_gpus_match_oracle():
+    n = C.c_int(0)
+    capi.check(capi.lib().cmb_device_count(C.byref(n)))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    p = _torchrun(2)
+    assert p.returncode == 0 and "DIST_GPU_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-6000:]
