@@ -72,7 +72,7 @@ struct Common : cmbs_solver {
   void set_ortho(int64_t nvec, const void* vecs, int64_t ld) override {
     std::vector<typename Solver::VectorType> o;
     const Scalar* p = static_cast<const Scalar*>(vecs);
-    const Index n = es.matrixHeight();
+    const Index n = es.localHeight();
     for (int64_t j = 0; j < nvec; ++j) {
       typename Solver::VectorType x(n);
       memcpy(x.data(), p + size_t(j) * ld, sizeof(Scalar) * size_t(n));
@@ -106,6 +106,7 @@ struct Common : cmbs_solver {
     else if (k == "hasWARN") *v = es.hasWARN();
     else if (k == "hasERROR") *v = es.hasERROR();
     else if (k == "matrixHeight") *v = es.matrixHeight();
+    else if (k == "localHeight") *v = es.localHeight();
     else return false;
     return true;
   }
@@ -170,7 +171,7 @@ struct LanczosS : Common<LanczosEigenSolver<Scalar>> {
   }
   void basis_vector(int64_t k, void* out) override {
     const auto& v = es.lanczosvectors();
-    memcpy(out, v.at(size_t(k)).data(), sizeof(Scalar) * size_t(es.matrixHeight()));
+    memcpy(out, v.at(size_t(k)).data(), sizeof(Scalar) * size_t(es.localHeight()));
   }
   void conv_log(int64_t index, void* out, int64_t* n) override {
     auto it = es.convergenceLog().find(Index(index));
@@ -243,7 +244,7 @@ struct ArnoldiS : Common<ArnoldiEigenSolver<Scalar>> {
   }
   void basis_vector(int64_t k, void* out) override {
     const auto& v = es.arnoldivectors();
-    memcpy(out, v.at(size_t(k)).data(), sizeof(Scalar) * size_t(es.matrixHeight()));
+    memcpy(out, v.at(size_t(k)).data(), sizeof(Scalar) * size_t(es.localHeight()));
   }
   void conv_log(int64_t index, void* out, int64_t* n) override {
     auto it = es.convergenceLog().find(Index(index));

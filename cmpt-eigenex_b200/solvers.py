@@ -303,7 +303,7 @@ class _Solver:
         return out
 
     def basisVector(self, k):
-        out = np.empty(self.matrixHeight(), dtype=self.dtype)
+        out = np.empty(self._geti("localHeight"), dtype=self.dtype)
         check(lib().cmbs_get_basis_vector(self.h, k, ptr(out)))
         return out
 

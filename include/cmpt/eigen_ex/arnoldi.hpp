@@ -142,6 +142,9 @@ class ArnoldiBase {
   }
   const DeviceOperator<Scalar>& deviceOperator() const { return deviceOperator_; }
   Index matrixHeight() const { return matrixHeight_; }
+  /// additive: rows held by this process (see LanczosBase::localHeight)
+  Index localHeight() const { return deviceOperator_ ? deviceOperator_.rows() : matrixHeight_; }
+  Index localRowBegin() const { return deviceOperator_ ? deviceOperator_.rowBegin() : 0; }
   Scalar eigenvalueShift() const { return eigenvalueShift_; }
   ArnoldiBase& setEigenvalueShift(Scalar eishift) {
     eigenvalueShift_ = eishift;
@@ -158,7 +161,14 @@ class ArnoldiBase {
   }
   ArnoldiBase& setInitialVector() {  // arnoldi.hpp:162-166
     std::mt19937 rengine;
-    setInitialVector(makeRandomVector(rengine, matrixHeight_));
+    VectorType full = makeRandomVector(rengine, matrixHeight_);
+    if (localHeight() == matrixHeight_) {
+      setInitialVector(std::move(full));
+    } else {
+      VectorType slab(localHeight());
+      for (Index i = 0; i < localHeight(); ++i) slab[i] = full[localRowBegin() + i];
+      setInitialVector(std::move(slab));
+    }
     return *this;
   }
   RealScalar threshold() const { return threshold_; }
@@ -181,7 +191,7 @@ class ArnoldiBase {
   const std::vector<VectorType>& arnoldivectors() const {
     if (static_cast<Index>(arnoldivectors_.size()) > nvectors_) arnoldivectors_.resize(nvectors_);
     while (static_cast<Index>(arnoldivectors_.size()) < nvectors_) {
-      VectorType v(matrixHeight_);
+      VectorType v(localHeight());
       detail::check(cmb_krylov_get_col(dev_.handle(), static_cast<std::int64_t>(arnoldivectors_.size()), v.data()),
                     "cmb_krylov_get_col");
       arnoldivectors_.push_back(std::move(v));
@@ -237,8 +247,8 @@ class ArnoldiBase {
     if (nvectors_ == 0) {
       // setInitialArnoldivector (arnoldi.hpp:245-269)
       if (matrixHeight_ < 0) throw ArnoldiException("matrixHeight_ < 0");
-      if (matrixHeight_ != static_cast<Index>(initialVector_.size())) setInitialVector();
-      dev_.setDeflation(orthogonalizingVectors_, matrixHeight_);
+      if (localHeight() != static_cast<Index>(initialVector_.size())) setInitialVector();
+      dev_.setDeflation(orthogonalizingVectors_, localHeight());
       int st = 0;
       detail::check(cmb_krylov_start(dev_.handle(), initialVector_.data(), threshold_, &st), "cmb_krylov_start");
       if (st != CMB_STEP_OK) return false;
@@ -267,9 +277,9 @@ class ArnoldiBase {
 
   /// dense copy of the basis, n x (number of Hessenberg columns) (arnoldi.hpp:398-409)
   MatrixType makeArnoldiMatrix() const {
-    Index nr = matrixHeight_;
+    Index nr = localHeight();
     Index nc = static_cast<Index>(h_.size());
-    if (nc > nr) nc = nr;
+    if (nc > matrixHeight_) nc = matrixHeight_;
     MatrixType V(nr, nc);
     const auto& vecs = arnoldivectors();
     for (Index c = 0; c < nc; ++c)
@@ -397,6 +407,7 @@ class ArnoldiEigenSolver {
     return *this;
   }
   Index matrixHeight() const { return arnoldiBase_.matrixHeight(); }
+  Index localHeight() const { return arnoldiBase_.localHeight(); }
   Scalar eigenvalueShift() const { return arnoldiBase_.eigenvalueShift(); }
   ArnoldiEigenSolver& setEigenvalueShift(Scalar eishift) {
     arnoldiBase_.setEigenvalueShift(eishift);
@@ -490,7 +501,7 @@ class ArnoldiEigenSolver {
   Index compute() {  // arnoldi.hpp:741-760
     log_.push_back(headINFO() + "ArnoldiEigenSolver<ScalarType>::compute(...) was called");
     clearComputedData();
-    if (static_cast<Index>(initialVector().size()) != matrixHeight()) {
+    if (static_cast<Index>(initialVector().size()) != localHeight()) {
       log_.push_back(headINFO() + "in compute(), initial_vector is empty or invalid, then set at random");
       setInitialVector();
     }
@@ -507,8 +518,8 @@ class ArnoldiEigenSolver {
     for (Index c = 0; c < cycles; ++c) {
       if (c > 0) {
         if (eigenvectors_.cols() == 0) break;
-        VectorType next(matrixHeight());
-        for (Index i = 0; i < matrixHeight(); ++i) next[i] = fromComplex_(eigenvectors_(i, 0));
+        VectorType next(localHeight());
+        for (Index i = 0; i < localHeight(); ++i) next[i] = fromComplex_(eigenvectors_(i, 0));
         setInitialVector(std::move(next));
       }
       ret = compute();
@@ -559,14 +570,14 @@ class ArnoldiEigenSolver {
 
     // Ritz vectors X = Q Y, normalised, phase-fixed (arnoldi.hpp:841-865) — assembled on the device
     if (computeEigenvectorsOn_) {
-      eigenvectors_ = ComplexMatrixType::Zero(matrixHeight(), eivalsize);
+      eigenvectors_ = ComplexMatrixType::Zero(localHeight(), eivalsize);
       if (eivalsize > 0 && eigenvectors_h_.rows() > 0) {
         const Index nm = eigenvectors_h_.rows();
         std::vector<ComplexScalar> coef(static_cast<std::size_t>(nm) * eivalsize);
         for (Index c = 0; c < eivalsize; ++c)
           for (Index j = 0; j < nm; ++j) coef[static_cast<std::size_t>(c) * nm + j] = eigenvectors_h_(j, c);
         detail::check(cmb_krylov_ritz_vectors(arnoldiBase_.deviceState(), CMB_C64, coef.data(), nm, nm, eivalsize,
-                                              eigenvectors_.data(), matrixHeight()),
+                                              eigenvectors_.data(), localHeight()),
                       "cmb_krylov_ritz_vectors");
       }
     } else {

@@ -166,6 +166,10 @@ class LanczosBase {
   }
   const DeviceOperator<Scalar>& deviceOperator() const { return deviceOperator_; }
   Index matrixHeight() const { return matrixHeight_; }
+  /// additive: length of the vectors this process holds — matrixHeight() on one GPU, the number of rows of this
+  /// rank's shard in a row-partitioned run (start/deflation/basis/Ritz vectors are then local slabs)
+  Index localHeight() const { return deviceOperator_ ? deviceOperator_.rows() : matrixHeight_; }
+  Index localRowBegin() const { return deviceOperator_ ? deviceOperator_.rowBegin() : 0; }
   RealScalar eigenvalueShift() const { return eigenvalueShift_; }
   LanczosBase& setEigenvalueShift(RealScalar eishift) {
     eigenvalueShift_ = eishift;
@@ -188,7 +192,14 @@ class LanczosBase {
   /// initial vector of size matrixHeight with random contents, fixed seed (lanczos.hpp:214-218)
   LanczosBase& setInitialVector() {
     std::mt19937 rengine;
-    setInitialVector(makeRandomVector(rengine, matrixHeight_));
+    VectorType full = makeRandomVector(rengine, matrixHeight_);
+    if (localHeight() == matrixHeight_) {
+      setInitialVector(std::move(full));
+    } else {  // row-partitioned: this rank's slab of the same global vector
+      VectorType slab(localHeight());
+      for (Index i = 0; i < localHeight(); ++i) slab[i] = full[localRowBegin() + i];
+      setInitialVector(std::move(slab));
+    }
     return *this;
   }
   RealScalar threshold() const { return threshold_; }
@@ -214,7 +225,7 @@ class LanczosBase {
   const std::vector<VectorType>& lanczosvectors() const {
     if (static_cast<Index>(lanczosvectors_.size()) > nvectors_) lanczosvectors_.resize(nvectors_);
     while (static_cast<Index>(lanczosvectors_.size()) < nvectors_) {
-      VectorType v(matrixHeight_);
+      VectorType v(localHeight());
       detail::check(cmb_krylov_get_col(dev_.handle(), static_cast<std::int64_t>(lanczosvectors_.size()), v.data()),
                     "cmb_krylov_get_col");
       lanczosvectors_.push_back(std::move(v));
@@ -307,8 +318,8 @@ class LanczosBase {
   /// lanczos.hpp:299-323; returns false when the start vector has (numerically) no component left
   bool setInitialLanczosvector_() {
     if (matrixHeight_ < 0) throw LanczosException("matrixHeight_ < 0");
-    if (matrixHeight_ != static_cast<Index>(initialVector_.size())) setInitialVector();
-    dev_.setDeflation(orthogonalizingVectors_, matrixHeight_);
+    if (localHeight() != static_cast<Index>(initialVector_.size())) setInitialVector();
+    dev_.setDeflation(orthogonalizingVectors_, localHeight());
     int status = 0;
     detail::check(cmb_krylov_start(dev_.handle(), initialVector_.data(), threshold_, &status), "cmb_krylov_start");
     return status == CMB_STEP_OK;
@@ -419,6 +430,7 @@ class LanczosEigenSolver {
     return *this;
   }
   Index matrixHeight() const { return lanczosBase_.matrixHeight(); }
+  Index localHeight() const { return lanczosBase_.localHeight(); }
   RealScalar eigenvalueShift() const { return lanczosBase_.eigenvalueShift(); }
   LanczosEigenSolver& setEigenvalueShift(RealScalar eishift) {
     lanczosBase_.setEigenvalueShift(eishift);
@@ -529,7 +541,7 @@ class LanczosEigenSolver {
   Index compute() {
     log_.push_back(headINFO() + "EigenSolver<ScalarType>::compute(...) was called");
     clearComputedData();
-    if (static_cast<Index>(initialVector().size()) != matrixHeight()) {
+    if (static_cast<Index>(initialVector().size()) != localHeight()) {
       log_.push_back(headINFO() + "in compute(), initial_vector is empty or invalid, then set at random");
       setInitialVector();
     }
@@ -599,14 +611,14 @@ class LanczosEigenSolver {
 
     // Ritz vectors (lanczos.hpp:798-817): X = V S, normalised, phase-fixed — assembled on the device
     if (computeEigenvectorsOn_) {
-      eigenvectors_.resize(matrixHeight(), eivalsize);
+      eigenvectors_.resize(localHeight(), eivalsize);
       if (eivalsize > 0) {
         const Index nm = es_tri_.eigenvectors().rows();
         std::vector<Scalar> coef(static_cast<std::size_t>(nm) * eivalsize);
         for (Index kk = 0; kk < eivalsize; ++kk)
           for (Index m = 0; m < nm; ++m) coef[static_cast<std::size_t>(kk) * nm + m] = es_tri_.eigenvectors()(m, kk);
         detail::check(cmb_krylov_ritz_vectors(lanczosBase_.deviceState(), detail::DTypeOf<Scalar>::value, coef.data(), nm,
-                                              nm, eivalsize, eigenvectors_.data(), matrixHeight()),
+                                              nm, eivalsize, eigenvectors_.data(), localHeight()),
                       "cmb_krylov_ritz_vectors");
       }
     } else {
