@@ -638,11 +638,11 @@ int cmb_krylov_ritz_vectors(cmb_krylov* K, cmb_dtype coef_dtype, const void* coe
   }
   std::vector<Chunk> chunks;
   contiguous_chunks(K, K->ndefl, K->ndefl + int(ncoef), chunks);
-  CMB_TRY(ensure_stage(K, size_t(4 * ncoef + 8)));
+  CMB_TRY(ensure_stage(K, size_t(nev) * size_t(4 * ncoef + 8)));  // one staging slice per vector: no host sync in the loop
   const double* cf = static_cast<const double*>(coef);
   const size_t out_es = ccplx ? 2 : 1;
   for (int64_t e = 0; e < nev; ++e) {
-    double* hs = K->h_stage;
+    double* hs = K->h_stage + size_t(e) * size_t(4 * ncoef + 8);
     const double* ce = cf + size_t(e) * ldc * ces;
     double* xdev = nullptr;
     if (ncoef == 0) {
@@ -673,8 +673,6 @@ int cmb_krylov_ritz_vectors(cmb_krylov* K, cmb_dtype coef_dtype, const void* coe
       CMB_CUDA(cudaGetLastError());
       xdev = K->tmpz;
     }
-    // host sync needed because the staging buffer is reused per vector
-    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
     // phase of the first non-zero element (lanczos.hpp:806-813) and normalisation (:816)
     // global index of the first non-zero element (min over ranks); its owner contributes the value, which is
     // copied aside because the scaling kernel overwrites it while other CTAs still read it
@@ -686,8 +684,8 @@ int cmb_krylov_ritz_vectors(cmb_krylov* K, cmb_dtype coef_dtype, const void* coe
     CMB_TRY(vec_scale_phase(ctx, ccplx, xdev, K->scal + 1, phase_src, widen ? 2 * K->ld : K->ld));
     CMB_CUDA(cudaMemcpyAsync(static_cast<char*>(x_host) + size_t(e) * ldx * out_es * sizeof(double), xdev,
                              sizeof(double) * K->n_local * out_es, cudaMemcpyDeviceToHost, ctx->stream));
-    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
   return CMB_OK;
 }
 

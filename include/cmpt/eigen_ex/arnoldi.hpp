@@ -570,8 +570,10 @@ class ArnoldiEigenSolver {
 
     // Ritz vectors X = Q Y, normalised, phase-fixed (arnoldi.hpp:841-865) — assembled on the device
     if (computeEigenvectorsOn_) {
-      eigenvectors_ = ComplexMatrixType::Zero(localHeight(), eivalsize);
-      if (eivalsize > 0 && eigenvectors_h_.rows() > 0) {
+      if (!(eivalsize > 0 && eigenvectors_h_.rows() > 0)) {
+        eigenvectors_ = ComplexMatrixType::Zero(localHeight(), eivalsize);
+      } else {
+        detail::resize_result(eigenvectors_, localHeight(), eivalsize);
         const Index nm = eigenvectors_h_.rows();
         std::vector<ComplexScalar> coef(static_cast<std::size_t>(nm) * eivalsize);
         for (Index c = 0; c < eivalsize; ++c)

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <complex>
 #include <cstddef>
+#include <cstring>
 #include <ostream>
 #include <vector>
 
@@ -22,6 +23,8 @@
 
 #ifdef CMPT_EIGENEX_HAVE_EIGEN
 #include "Eigen/Core"
+#else
+#include "cmpt_b200_solver.h"  // cmb_host_alloc / cmb_host_free for pinned result buffers
 #endif
 
 namespace cmpt {
@@ -61,6 +64,101 @@ using Matrix = Eigen::Matrix<S, Eigen::Dynamic, Eigen::Dynamic>;
 #else
 
 using Index = std::ptrdiff_t;
+
+namespace detail {
+// Contiguous storage with Eigen's resize semantics: growing does NOT initialise the new elements (a
+// std::vector would zero-fill 670 MB for five Ritz vectors of cfg 2) and shrinking keeps the allocation.
+// Large result buffers can be allocated as pinned host memory (cmb_host_alloc) so device->host copies of
+// Ritz vectors run at full PCIe rate.
+template <class S>
+class Storage {
+ public:
+  Storage() {}
+  explicit Storage(std::size_t n) { resize(n); }
+  Storage(std::size_t n, const S& v) {
+    resize(n);
+    for (std::size_t i = 0; i < n; ++i) p_[i] = v;
+  }
+  Storage(const S* b, const S* e) {
+    resize(static_cast<std::size_t>(e - b));
+    if (n_) std::memcpy(static_cast<void*>(p_), b, n_ * sizeof(S));
+  }
+  Storage(const Storage& o) {
+    resize(o.n_);
+    if (n_) std::memcpy(static_cast<void*>(p_), o.p_, n_ * sizeof(S));
+  }
+  Storage(Storage&& o) noexcept : p_(o.p_), n_(o.n_), cap_(o.cap_), pinned_(o.pinned_) {
+    o.p_ = nullptr;
+    o.n_ = o.cap_ = 0;
+  }
+  Storage& operator=(const Storage& o) {
+    if (this != &o) {
+      resize(o.n_);
+      if (n_) std::memcpy(static_cast<void*>(p_), o.p_, n_ * sizeof(S));
+    }
+    return *this;
+  }
+  Storage& operator=(Storage&& o) noexcept {
+    if (this != &o) {
+      release();
+      p_ = o.p_;
+      n_ = o.n_;
+      cap_ = o.cap_;
+      pinned_ = o.pinned_;
+      o.p_ = nullptr;
+      o.n_ = o.cap_ = 0;
+    }
+    return *this;
+  }
+  ~Storage() { release(); }
+  std::size_t size() const { return n_; }
+  S* data() { return p_; }
+  const S* data() const { return p_; }
+  S& operator[](std::size_t i) { return p_[i]; }
+  const S& operator[](std::size_t i) const { return p_[i]; }
+  S* begin() { return p_; }
+  S* end() { return p_ + n_; }
+  const S* begin() const { return p_; }
+  const S* end() const { return p_ + n_; }
+  // new elements are left uninitialised; `pinned` requests page-locked memory for a (re)allocation
+  void resize(std::size_t n, bool pinned = false) {
+    if (n > cap_ || (pinned && !pinned_ && n > 0)) {
+      S* q = nullptr;
+      bool got_pinned = false;
+      if (pinned) {
+        void* v = nullptr;
+        if (cmb_host_alloc(n * sizeof(S), &v) == CMB_OK) {
+          q = static_cast<S*>(v);
+          got_pinned = true;
+        }
+      }
+      if (!q) q = static_cast<S*>(::operator new(n * sizeof(S)));
+      if (n_) std::memcpy(static_cast<void*>(q), p_, (n_ < n ? n_ : n) * sizeof(S));
+      release();
+      p_ = q;
+      cap_ = n;
+      pinned_ = got_pinned;
+    }
+    n_ = n;
+  }
+
+ private:
+  void release() {
+    if (p_) {
+      if (pinned_)
+        cmb_host_free(p_);
+      else
+        ::operator delete(p_);
+    }
+    p_ = nullptr;
+    n_ = cap_ = 0;
+    pinned_ = false;
+  }
+  S* p_ = nullptr;
+  std::size_t n_ = 0, cap_ = 0;
+  bool pinned_ = false;
+};
+}  // namespace detail
 
 template <class S>
 class Vector {
@@ -118,7 +216,7 @@ class Vector {
   }
 
  private:
-  std::vector<S> d_;
+  detail::Storage<S> d_;
 };
 
 template <class S>
@@ -145,6 +243,12 @@ class Matrix {
     c_ = c;
     d_.resize(static_cast<std::size_t>(r * c));
   }
+  /// resize into page-locked host memory (falls back to pageable): device->host copies run at PCIe rate
+  void resizePinned(Index r, Index c) {
+    r_ = r;
+    c_ = c;
+    d_.resize(static_cast<std::size_t>(r * c), true);
+  }
   S* data() { return d_.data(); }
   const S* data() const { return d_.data(); }
   S& operator()(Index i, Index j) { return d_[static_cast<std::size_t>(j * r_ + i)]; }
@@ -157,7 +261,7 @@ class Matrix {
 
  private:
   Index r_, c_;
-  std::vector<S> d_;
+  detail::Storage<S> d_;
 };
 
 template <class S>
@@ -175,6 +279,21 @@ std::ostream& operator<<(std::ostream& os, const Matrix<S>& m) {
 }
 
 #endif  // CMPT_EIGENEX_HAVE_EIGEN
+
+namespace detail {
+// (Re)size a matrix that will receive device results (Ritz vectors): contents are left uninitialised.
+template <class S>
+inline void resize_result(Matrix<S>& m, Index r, Index c) {
+#ifdef CMPT_EIGENEX_HAVE_EIGEN
+  m.resize(r, c);
+#else
+  if (static_cast<std::size_t>(r) * static_cast<std::size_t>(c) * sizeof(S) >= (std::size_t(1) << 20))
+    m.resizePinned(r, c);
+  else
+    m.resize(r, c);
+#endif
+}
+}  // namespace detail
 
 }  // namespace EigenEx
 }  // namespace cmpt

@@ -52,7 +52,10 @@ bool tridiagonal_qr(int n, Real* d, Real* e, Real* z) {
     Real zb = e[start];  // the bulge
     for (int k = start; k < end; ++k) {
       // rotation [c -s; s c] with s x + c zb = 0
-      const Real r = std::hypot(x, zb);
+      // sqrt(x^2+z^2) directly (std::hypot is ~10x slower); fall back to hypot only when the squares
+      // over/underflow
+      Real r = std::sqrt(x * x + zb * zb);
+      if (!(r > tiny) || !(r < std::numeric_limits<Real>::max())) r = std::hypot(x, zb);
       Real c = Real(1), s = Real(0);
       if (r != Real(0)) {
         c = x / r;

@@ -24,6 +24,7 @@
 #include <map>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "detail/krylov_device.hpp"
@@ -590,11 +591,8 @@ class LanczosEigenSolver {
       const Index before = static_cast<Index>(lanczosBase_.alpha().size());
       const Index done = lanczosBase_.updateLanczosSteps(batch);
       if (lanczosBase_.lanczosvectorsSize() == 0) set_initialvector_is_fail = true;
-      // replay the trips of the intermediate states
-      for (Index j = 1; j < done; ++j) {
-        solveTridiagonal_(before + j, false);
-        updateConvergenceLog_();
-      }
+      // replay the trips of the intermediate states (their tridiagonal problems are independent of each other)
+      replayTrips_(before, done);
       solveTridiagonal_(static_cast<Index>(lanczosBase_.alpha().size()), false);
     }
 
@@ -611,7 +609,7 @@ class LanczosEigenSolver {
 
     // Ritz vectors (lanczos.hpp:798-817): X = V S, normalised, phase-fixed — assembled on the device
     if (computeEigenvectorsOn_) {
-      eigenvectors_.resize(localHeight(), eivalsize);
+      detail::resize_result(eigenvectors_, localHeight(), eivalsize);
       if (eivalsize > 0) {
         const Index nm = es_tri_.eigenvectors().rows();
         std::vector<Scalar> coef(static_cast<std::size_t>(nm) * eivalsize);
@@ -630,6 +628,43 @@ class LanczosEigenSolver {
  protected:
   void solveTridiagonal_(Index k, bool vectors) {
     es_tri_.computeRaw(lanczosBase_.alpha().data(), lanczosBase_.beta().data(), static_cast<int>(k), vectors);
+  }
+
+  /// Convergence-log entries of the states with before+1 .. before+done-1 Lanczos vectors, i.e. the trips a
+  /// batched updateLanczosSteps(done) skipped.  The Ritz values of each T_j are computed on a few host threads,
+  /// then appended in trip order, exactly as updateConvergenceLog_ would have done.
+  void replayTrips_(Index before, Index done) {
+    const Index ntrips = done - 1;
+    if (ntrips <= 0) return;
+    std::vector<std::vector<RealScalar>> ritz(static_cast<std::size_t>(ntrips));
+    const RealScalar* a = lanczosBase_.alpha().data();
+    const RealScalar* b = lanczosBase_.beta().data();
+    auto work = [&](Index t0, Index t1) {
+      for (Index t = t0; t < t1; ++t)
+        detail::tridiagonal_eigenvalues<RealScalar>(a, b, static_cast<int>(before + 1 + t), ritz[static_cast<std::size_t>(t)]);
+    };
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads > 8) nthreads = 8;
+    if (nthreads < 1 || ntrips < 8) nthreads = 1;
+    if (nthreads == 1) {
+      work(0, ntrips);
+    } else {
+      // interleave so that every thread gets small and large problems
+      std::vector<std::thread> pool;
+      for (unsigned w = 0; w < nthreads; ++w)
+        pool.emplace_back([&, w]() {
+          for (Index t = static_cast<Index>(w); t < ntrips; t += static_cast<Index>(nthreads)) work(t, t + 1);
+        });
+      for (auto& th : pool) th.join();
+    }
+    for (Index t = 0; t < ntrips; ++t) {
+      const std::vector<RealScalar>& ev = ritz[static_cast<std::size_t>(t)];
+      for (auto& indexForConvergence : indicesForConvergence_) {
+        Index i = getFormalIndex(indexForConvergence, static_cast<Index>(ev.size()));
+        if (i < 0) continue;
+        convergenceLog_[indexForConvergence].push_back(ev[static_cast<std::size_t>(i)]);
+      }
+    }
   }
 
   /// index for eigenvalues in [0,n); negative i counts from the end; -1 when invalid (lanczos.hpp:837-847)
