@@ -7,11 +7,15 @@
 //   UPDATE_DOT   y  = x - V hin ;  h = V^H y      (both from the same shared-memory tile)
 //   UPDATE_NORM  y  = x - V hin ;  nrm2 = ||y||^2
 // HBM-bound (0.25 flop/B): no tensor cores.  One persistent CTA per SM; one producer thread feeds a
-// ring of shared-memory stages with TMA (2D tiled loads of a [T rows x NC cols] box of V, 1D bulk
-// copy of the x tile); 8 consumer warps each own a column group (CG columns held in registers for
+// ring of shared-memory stages with TMA (2D tiled loads of a [T rows x nc cols] box of V, 1D bulk
+// copy of the x tile); 8 consumer warps each own a column group (cg columns held in registers for
 // both the update and the dot) and a row group; per-column sums live in registers across all tiles of
 // the CTA and are reduced once at the end: warp shuffle -> shared memory -> per-CTA partial -> the last
 // CTA to finish sums the partials in CTA order (deterministic, no floating-point atomics).
+//
+// The number of columns per warp `cg` is a run-time value (<= the compile-time register budget CG), so the
+// TMA box holds exactly WC*cg >= c columns: shared-memory traffic (the limiter of the UPDATE passes,
+// profiles/r1_prof_cgs_raw.txt) is spent on real columns only.
 //
 // All vectors are double arrays of padded length ld (multiple of 512, pads are zero), a complex vector
 // being ld/2 interleaved (re,im) pairs; a lane always holds one double2 per column, i.e. one complex
@@ -24,36 +28,35 @@ namespace cmb {
 constexpr int kConsumerWarps = 8;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 
-template <int CG, int WC>
+template <int WC>
 struct CgsCfg {
   static constexpr int WR = kConsumerWarps / WC;
-  static constexpr int T = 64 * WR;                   // rows (doubles) per tile
-  static constexpr int NC = CG * WC;                  // columns per tile
-  static constexpr int BOXR = T < 256 ? T : 256;      // TMA box rows
+  static constexpr int T = 64 * WR;               // rows (doubles) per tile
+  static constexpr int BOXR = T < 256 ? T : 256;  // TMA box rows
   static constexpr int NBOX = T / BOXR;
-  static constexpr int V_BYTES = NC * T * 8;
   static constexpr int X_BYTES = T * 8;
-  static constexpr int STAGE_BYTES = V_BYTES + X_BYTES;
   static constexpr int PW_BYTES = (WC > 1) ? 2 * WC * T * 8 : 0;
-  static constexpr int RED_BYTES = WR * NC * 2 * 8;
 };
 
 template <int CG, int WC, bool CPLX, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x, double* __restrict__ y,
            const double* __restrict__ hin, double* __restrict__ hout, double* __restrict__ partial,
-           unsigned* __restrict__ ticket, const int* __restrict__ halt, int ncols, int ntiles, int stages) {
-  using Cfg = CgsCfg<CG, WC>;
-  constexpr int T = Cfg::T, NC = Cfg::NC, WR = Cfg::WR;
+           unsigned* __restrict__ ticket, const int* __restrict__ halt, int ncols, int cg, int ntiles, int stages) {
+  using Cfg = CgsCfg<WC>;
+  constexpr int T = Cfg::T, WR = Cfg::WR;
   constexpr int ES = CPLX ? 2 : 1;  // doubles per coefficient
+  constexpr int NCMAX = CG * WC;
   if (*halt) return;
+  const int nc = cg * WC;                  // columns in the TMA box (>= ncols)
+  const int stage_doubles = nc * T + T;    // V tile + x tile
 
   extern __shared__ __align__(1024) unsigned char smem[];
   double* stage_base = reinterpret_cast<double*>(smem);
-  unsigned char* tail = smem + size_t(stages) * Cfg::STAGE_BYTES;
+  unsigned char* tail = smem + size_t(stages) * stage_doubles * 8;
   double* pw = reinterpret_cast<double*>(tail);
   double* red = reinterpret_cast<double*>(tail + Cfg::PW_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(tail + Cfg::PW_BYTES + Cfg::RED_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail + Cfg::PW_BYTES + WR * NCMAX * 2 * 8);
   uint64_t* empty = full + stages;
   __shared__ int s_last;
 
@@ -71,18 +74,18 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
     // ===== producer: one thread issues every TMA of this CTA =====
     if (lane == 0) {
       prefetch_tmap(&tmV);
-      const uint32_t bytes = Cfg::V_BYTES + (x ? Cfg::X_BYTES : 0);
+      const uint32_t bytes = uint32_t(nc) * T * 8 + (x ? Cfg::X_BYTES : 0);
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = it % stages;
         const uint32_t ph = (it / stages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], bytes);
-        double* vs = stage_base + size_t(s) * (Cfg::STAGE_BYTES / 8);
+        double* vs = stage_base + size_t(s) * stage_doubles;
 #pragma unroll
         for (int b = 0; b < Cfg::NBOX; ++b)
-          tma_load_2d(vs + size_t(b) * NC * Cfg::BOXR, &tmV, tile * T + b * Cfg::BOXR, 0, &full[s]);
-        if (x) bulk_load_1d(vs + NC * T, x + size_t(tile) * T, Cfg::X_BYTES, &full[s]);
+          tma_load_2d(vs + size_t(b) * nc * Cfg::BOXR, &tmV, tile * T + b * Cfg::BOXR, 0, &full[s]);
+        if (x) bulk_load_1d(vs + nc * T, x + size_t(tile) * T, Cfg::X_BYTES, &full[s]);
       }
     }
     return;
@@ -91,16 +94,17 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
   // ===== consumers =====
   const int gc = warp % WC;  // column group
   const int gr = warp / WC;  // row group (64 doubles each)
-  const int row = gr * 64 + 2 * lane;                                  // first of this lane's two doubles in the tile
-  const int vofs = (row / Cfg::BOXR) * NC * Cfg::BOXR + (row % Cfg::BOXR);  // offset inside the V tile for column 0
+  const int row = gr * 64 + 2 * lane;  // first of this lane's two doubles in the tile
+  const int vofs = (row / Cfg::BOXR) * nc * Cfg::BOXR + (row % Cfg::BOXR) + gc * cg * Cfg::BOXR;
 
   double hr[CG], hi[CPLX ? CG : 1];
   if (MODE >= 1) {
 #pragma unroll
     for (int j = 0; j < CG; ++j) {
-      const int col = gc * CG + j;
-      hr[j] = col < ncols ? hin[col * ES] : 0.0;
-      if (CPLX) hi[j] = col < ncols ? hin[col * ES + 1] : 0.0;
+      const int col = gc * cg + j;
+      const bool ok = (j < cg) && (col < ncols);
+      hr[j] = ok ? hin[col * ES] : 0.0;
+      if (CPLX) hi[j] = ok ? hin[col * ES + 1] : 0.0;
     }
   }
   double ar[CG], ai[CPLX ? CG : 1];
@@ -116,27 +120,31 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
     const int s = it % stages;
     const uint32_t ph = (it / stages) & 1;
     mbar_wait(&full[s], ph);
-    const double* vs = stage_base + size_t(s) * (Cfg::STAGE_BYTES / 8);
+    const double* vs = stage_base + size_t(s) * stage_doubles;
     double2 xv = make_double2(0.0, 0.0);
-    if (x) xv = *reinterpret_cast<const double2*>(vs + NC * T + row);
+    if (x) xv = *reinterpret_cast<const double2*>(vs + nc * T + row);
     double2 v[CG];
 #pragma unroll
-    for (int j = 0; j < CG; ++j)
-      v[j] = *reinterpret_cast<const double2*>(vs + vofs + (gc * CG + j) * Cfg::BOXR);
+    for (int j = 0; j < CG; ++j) {
+      v[j] = make_double2(0.0, 0.0);
+      if (j < cg) v[j] = *reinterpret_cast<const double2*>(vs + vofs + j * Cfg::BOXR);
+    }
 
     double2 yv = xv;
     if (MODE >= 1) {
       double2 p = make_double2(0.0, 0.0);
 #pragma unroll
       for (int j = 0; j < CG; ++j) {
-        if (CPLX) {
-          p.x = fma(v[j].x, hr[j], p.x);
-          p.x = fma(-v[j].y, hi[j], p.x);
-          p.y = fma(v[j].x, hi[j], p.y);
-          p.y = fma(v[j].y, hr[j], p.y);
-        } else {
-          p.x = fma(v[j].x, hr[j], p.x);
-          p.y = fma(v[j].y, hr[j], p.y);
+        if (j < cg) {
+          if (CPLX) {
+            p.x = fma(v[j].x, hr[j], p.x);
+            p.x = fma(-v[j].y, hi[j], p.x);
+            p.y = fma(v[j].x, hi[j], p.y);
+            p.y = fma(v[j].y, hr[j], p.y);
+          } else {
+            p.x = fma(v[j].x, hr[j], p.x);
+            p.y = fma(v[j].y, hr[j], p.y);
+          }
         }
       }
       if (WC > 1) {
@@ -158,14 +166,16 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
     if (MODE <= 1) {
 #pragma unroll
       for (int j = 0; j < CG; ++j) {
-        if (CPLX) {  // conj(v) * y
-          ar[j] = fma(v[j].x, yv.x, ar[j]);
-          ar[j] = fma(v[j].y, yv.y, ar[j]);
-          ai[j] = fma(v[j].x, yv.y, ai[j]);
-          ai[j] = fma(-v[j].y, yv.x, ai[j]);
-        } else {
-          ar[j] = fma(v[j].x, yv.x, ar[j]);
-          ar[j] = fma(v[j].y, yv.y, ar[j]);
+        if (j < cg) {
+          if (CPLX) {  // conj(v) * y
+            ar[j] = fma(v[j].x, yv.x, ar[j]);
+            ar[j] = fma(v[j].y, yv.y, ar[j]);
+            ai[j] = fma(v[j].x, yv.y, ai[j]);
+            ai[j] = fma(-v[j].y, yv.x, ai[j]);
+          } else {
+            ar[j] = fma(v[j].x, yv.x, ar[j]);
+            ar[j] = fma(v[j].y, yv.y, ar[j]);
+          }
         }
       }
     } else if (gc == 0) {
@@ -177,16 +187,18 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
   }
 
   // ===== CTA-level reduction =====
-  constexpr int NRED = (MODE <= 1) ? NC * ES : 1;  // values per CTA
+  const int nred = (MODE <= 1) ? nc * ES : 1;  // values per CTA
   if (MODE <= 1) {
 #pragma unroll
     for (int j = 0; j < CG; ++j) {
-      const double sr = warp_sum(ar[j]);
-      double si = 0.0;
-      if (CPLX) si = warp_sum(ai[j]);
-      if (lane == 0) {
-        red[gr * NC * ES + (gc * CG + j) * ES] = sr;
-        if (CPLX) red[gr * NC * ES + (gc * CG + j) * ES + 1] = si;
+      if (j < cg) {
+        const double sr = warp_sum(ar[j]);
+        double si = 0.0;
+        if (CPLX) si = warp_sum(ai[j]);
+        if (lane == 0) {
+          red[gr * NCMAX * ES + (gc * cg + j) * ES] = sr;
+          if (CPLX) red[gr * NCMAX * ES + (gc * cg + j) * ES + 1] = si;
+        }
       }
     }
   } else {
@@ -195,10 +207,10 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
   }
   asm volatile("bar.sync 9, %0;" ::"r"(kConsumerWarps * 32) : "memory");
   const int nout = (MODE <= 1) ? ncols * ES : 1;
-  for (int t = threadIdx.x; t < NRED; t += kConsumerWarps * 32) {
+  for (int t = threadIdx.x; t < nred; t += kConsumerWarps * 32) {
     double sacc = 0.0;
 #pragma unroll
-    for (int g = 0; g < WR; ++g) sacc += (MODE <= 1) ? red[g * NC * ES + t] : red[g];
+    for (int g = 0; g < WR; ++g) sacc += (MODE <= 1) ? red[g * NCMAX * ES + t] : red[g];
     if (t < nout) partial[size_t(blockIdx.x) * kPartialStride + t] = sacc;
   }
   // ===== last CTA sums the per-CTA partials in CTA order =====
@@ -222,22 +234,24 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
 
 // ---- host side ---------------------------------------------------------------------------------------
 template <int CG, int WC, bool CPLX, int MODE>
-static int launch_cfg(cmb_ctx* ctx, const CgsPass& a) {
-  using Cfg = CgsCfg<CG, WC>;
+static int launch_cfg(cmb_ctx* ctx, const CgsPass& a, int cg) {
+  using Cfg = CgsCfg<WC>;
   const int64_t ntiles64 = a.ld / Cfg::T;
   CMB_REQUIRE(a.ld % Cfg::T == 0 && ntiles64 < (int64_t(1) << 31) / Cfg::T, "padded length not tileable");
   const int ntiles = int(ntiles64);
-  const int fixed = Cfg::PW_BYTES + Cfg::RED_BYTES + 2 * 8 * 16 + 64;
-  int stages = (200 * 1024 - fixed) / Cfg::STAGE_BYTES;
-  if (stages > 8) stages = 8;
+  const int nc = cg * WC;
+  const int stage_bytes = (nc * Cfg::T + Cfg::T) * 8;
+  const int fixed = Cfg::PW_BYTES + Cfg::WR * CG * WC * 2 * 8 + 2 * 8 * 16 + 64;
+  int stages = (200 * 1024 - fixed) / stage_bytes;
+  if (stages > 12) stages = 12;
   if (stages < 2) stages = 2;
-  const size_t smem = size_t(stages) * Cfg::STAGE_BYTES + Cfg::PW_BYTES + Cfg::RED_BYTES + size_t(2) * stages * 8;
+  const size_t smem = size_t(stages) * stage_bytes + fixed;
 
-  // tensor map over the chunk of V: dim0 = rows (doubles, contiguous), dim1 = columns
+  // tensor map over the chunk of V: dim0 = rows (doubles, contiguous), dim1 = columns; box = [BOXR x nc]
   CUtensorMap tm;
   cuuint64_t gdim[2] = {cuuint64_t(a.ld), cuuint64_t(a.ncols)};
   cuuint64_t gstr[1] = {cuuint64_t(a.col_stride) * 8};
-  cuuint32_t box[2] = {cuuint32_t(Cfg::BOXR), cuuint32_t(Cfg::NC)};
+  cuuint32_t box[2] = {cuuint32_t(Cfg::BOXR), cuuint32_t(nc)};
   cuuint32_t estr[2] = {1, 1};
   CUresult cr = get_encode_tiled()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(a.V), gdim, gstr, box,
                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -247,10 +261,10 @@ static int launch_cfg(cmb_ctx* ctx, const CgsPass& a) {
     return CMB_ERR_CUDA;
   }
   auto kern = cgs_kernel<CG, WC, CPLX, MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
     CMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
+    attr_set[ctx->device & 63] = true;
   }
   int grid = ctx->num_sms;
   if (grid > ntiles) grid = ntiles;
@@ -259,7 +273,7 @@ static int launch_cfg(cmb_ctx* ctx, const CgsPass& a) {
   {
     LaunchScope ls(ctx, a.family ? a.family : fam[MODE]);
     kern<<<grid, kThreads, smem, ctx->stream>>>(tm, a.x, a.y, a.hin, a.hout, ctx->d_partial, ctx->d_ticket, a.halt,
-                                                a.ncols, ntiles, stages);
+                                                a.ncols, cg, ntiles, stages);
   }
   CMB_CUDA(cudaGetLastError());
   return CMB_OK;
@@ -268,15 +282,13 @@ static int launch_cfg(cmb_ctx* ctx, const CgsPass& a) {
 template <bool CPLX, int MODE>
 static int launch_mode(cmb_ctx* ctx, const CgsPass& a) {
   const int c = a.ncols;
-  if (c <= 1) return launch_cfg<1, 1, CPLX, MODE>(ctx, a);
-  if (c <= 2) return launch_cfg<2, 1, CPLX, MODE>(ctx, a);
-  if (c <= 4) return launch_cfg<4, 1, CPLX, MODE>(ctx, a);
-  if (c <= 8) return launch_cfg<8, 1, CPLX, MODE>(ctx, a);
-  if (c <= 16) return launch_cfg<8, 2, CPLX, MODE>(ctx, a);
-  if (c <= 32) return launch_cfg<8, 4, CPLX, MODE>(ctx, a);
-  if (c <= 64) return launch_cfg<8, 8, CPLX, MODE>(ctx, a);
+  // warps per row tile: fewer column groups (and taller tiles) for few columns, so a tile stays >= ~16 KB
+  if (c <= 8) return launch_cfg<8, 1, CPLX, MODE>(ctx, a, c);
+  if (c <= 16) return launch_cfg<8, 2, CPLX, MODE>(ctx, a, (c + 1) / 2);
+  if (c <= 32) return launch_cfg<8, 4, CPLX, MODE>(ctx, a, (c + 3) / 4);
+  if (c <= 64) return launch_cfg<8, 8, CPLX, MODE>(ctx, a, (c + 7) / 8);
   if constexpr (!CPLX) {
-    if (c <= 128) return launch_cfg<16, 8, CPLX, MODE>(ctx, a);
+    if (c <= 128) return launch_cfg<16, 8, CPLX, MODE>(ctx, a, (c + 7) / 8);
   }
   set_error("cgs pass: %d columns exceed the per-pass maximum", c);
   return CMB_ERR_INVALID;

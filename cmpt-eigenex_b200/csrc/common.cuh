@@ -120,6 +120,23 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_tiled();
 
+// Stream-ordered allocations from the device's default memory pool (release threshold raised to "never" in
+// ctx_init_common), so that building and destroying operators of the same size costs no cudaMalloc/cudaFree.
+template <class T>
+inline int pool_alloc(cmb_ctx* ctx, T** p, size_t bytes) {
+  *p = nullptr;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 16, ctx->stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("out of device memory (%zu bytes): %s", bytes, cudaGetErrorString(e));
+    return CMB_ERR_NOMEM;
+  }
+  return CMB_OK;
+}
+inline void pool_free(cmb_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+
 template <class T>
 inline T* dalloc(size_t n) {
   T* p = nullptr;

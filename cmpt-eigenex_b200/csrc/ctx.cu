@@ -144,6 +144,15 @@ static int ctx_init_common(cmb_ctx* c, int device) {
     return CMB_ERR_UNSUPPORTED;
   }
   c->num_sms = prop.multiProcessorCount;
+  {
+    // keep freed pool memory cached: operator (re)builds then never reach cudaMalloc/cudaFree
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+  }
   CMB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CMB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CMB_CUDA(cudaEventCreate(&c->t0));

@@ -136,9 +136,9 @@ struct SellOp : cmb_op {
   HaloExchange* halo = nullptr;  // row-partitioned shards only
   long long padded_nnz = 0, nnz = 0;
   ~SellOp() override {
-    cudaFree(d_slice_ptr);
-    cudaFree(d_col);
-    cudaFree(d_val);
+    pool_free(ctx, d_slice_ptr);
+    pool_free(ctx, d_col);
+    pool_free(ctx, d_val);
     delete halo;
   }
   int apply(const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) override {
@@ -175,16 +175,16 @@ static int build_sell(SellOp* op, const int64_t* rowptr, const int32_t* col, con
   double* d_cval = nullptr;
   int* d_width = nullptr;
   auto cleanup = [&]() {
-    cudaFree(d_rowptr);
-    cudaFree(d_ccol);
-    cudaFree(d_cval);
-    cudaFree(d_width);
+    pool_free(ctx, d_rowptr);
+    pool_free(ctx, d_ccol);
+    pool_free(ctx, d_cval);
+    pool_free(ctx, d_width);
   };
   int rc = [&]() -> int {
-    CMB_CUDA(cudaMalloc(&d_rowptr, sizeof(long long) * (n + 1)));
-    CMB_CUDA(cudaMalloc(&d_ccol, sizeof(int) * std::max<long long>(nnz, 1)));
-    CMB_CUDA(cudaMalloc(&d_cval, sizeof(double) * es * std::max<long long>(nnz, 1)));
-    CMB_CUDA(cudaMalloc(&d_width, sizeof(int) * std::max<long long>(op->nslices, 1)));
+    CMB_TRY(pool_alloc(ctx, &d_rowptr, sizeof(long long) * (n + 1)));
+    CMB_TRY(pool_alloc(ctx, &d_ccol, sizeof(int) * std::max<long long>(nnz, 1)));
+    CMB_TRY(pool_alloc(ctx, &d_cval, sizeof(double) * es * std::max<long long>(nnz, 1)));
+    CMB_TRY(pool_alloc(ctx, &d_width, sizeof(int) * std::max<long long>(op->nslices, 1)));
     CMB_CUDA(cudaMemcpyAsync(d_rowptr, rowptr, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
     CMB_CUDA(cudaMemcpyAsync(d_ccol, col, sizeof(int) * nnz, cudaMemcpyHostToDevice, ctx->stream));
     CMB_CUDA(cudaMemcpyAsync(d_cval, val, sizeof(double) * es * nnz, cudaMemcpyHostToDevice, ctx->stream));
@@ -203,9 +203,9 @@ static int build_sell(SellOp* op, const int64_t* rowptr, const int32_t* col, con
     sp[0] = 0;
     for (long long s = 0; s < op->nslices; ++s) sp[s + 1] = sp[s] + (long long)width[s] * 32;
     op->padded_nnz = sp[op->nslices];
-    CMB_CUDA(cudaMalloc(&op->d_slice_ptr, sizeof(long long) * (op->nslices + 1)));
-    CMB_CUDA(cudaMalloc(&op->d_col, sizeof(int) * std::max<long long>(op->padded_nnz, 1)));
-    CMB_CUDA(cudaMalloc(&op->d_val, sizeof(double) * es * std::max<long long>(op->padded_nnz, 1)));
+    CMB_TRY(pool_alloc(ctx, &op->d_slice_ptr, sizeof(long long) * (op->nslices + 1)));
+    CMB_TRY(pool_alloc(ctx, &op->d_col, sizeof(int) * std::max<long long>(op->padded_nnz, 1)));
+    CMB_TRY(pool_alloc(ctx, &op->d_val, sizeof(double) * es * std::max<long long>(op->padded_nnz, 1)));
     CMB_CUDA(cudaMemcpyAsync(op->d_slice_ptr, sp.data(), sizeof(long long) * (op->nslices + 1), cudaMemcpyHostToDevice,
                              ctx->stream));
     if (op->nslices > 0) {

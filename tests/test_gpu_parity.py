@@ -502,7 +502,7 @@ def test_arnoldi_shift_deflation_restart(ctx):
     ref.max_eigenvalues = 2
     ref.compute()
     assert abs(es.eigenvalues()[0] - ref.eigenvalues[0]) < 1e-6 * abs(ref.eigenvalues[0])  # unconverged: sensitive
-    assert _sorted_close(es.eigenvalues(), ref.eigenvalues, 1e-4)
+    assert _sorted_close(es.eigenvalues(), ref.eigenvalues, 1e-3)
     # explicit restart (cfg 3): each cycle restarts from the leading Ritz vector; the leading Ritz value improves
     es2 = pkg.ArnoldiEigenSolver(np.float64)
     es2.setMatrixMultiplication(op).setInitialVector(x0).setMinIterations(20).setMaxIterations(20).setMaxEigenvalues(1)
