@@ -91,6 +91,7 @@ def _declare(L):
         "cmb_arnoldi_step": (i32, [vp, vp, vp, dbl, vp, P(dbl), P(i32)]),
         "cmb_krylov_ritz_vectors": (i32, [vp, i32, vp, i64, i64, i64, vp, i64]),
         "cmb_krylov_bytes": (dbl, [vp]),
+        "cmb_debug_cgs_pass": (i32, [vp, i32, i32, i32, P(dbl)]),
         # solver binding
         "cmbs_create": (i32, [i32, i32, P(vp)]),
         "cmbs_destroy": (i32, [vp]),

@@ -511,6 +511,43 @@ int cmb_lanczos_step(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, 
 
 static int ensure_tmp(cmb_krylov* K, double** p, size_t doubles);
 
+// Diagnostic: time `reps` launches of one Gram-Schmidt pass (mode 0/1/2) over the first `ncols` basis columns
+// with CUDA events (columns are allocated on demand; their contents do not matter for timing).
+int cmb_debug_cgs_pass(cmb_krylov* K, int mode, int ncols, int reps, double* ms_per_launch) {
+  CMB_REQUIRE(K && ms_per_launch && mode >= 0 && mode <= 2 && ncols >= 1 && reps >= 1, "bad argument");
+  cmb_ctx* ctx = K->ctx;
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  CMB_TRY(ensure_cols(K, ncols));
+  std::vector<Chunk> chunks;
+  contiguous_chunks(K, 0, ncols, chunks);
+  CMB_REQUIRE(chunks.size() == 1, "diagnostic pass needs a single chunk (ncols <= segment size)");
+  CMB_CUDA(cudaMemsetAsync(K->h1, 0, sizeof(double) * 2 * ncols, ctx->stream));
+  CgsPass p;
+  p.ld = K->ld;
+  p.halt = K->halt;
+  p.V = chunks[0].V;
+  p.ncols = ncols;
+  p.col_stride = chunks[0].col_stride;
+  p.x = K->v;
+  p.y = (mode == 0) ? nullptr : K->w;
+  p.hin = (mode == 0) ? nullptr : K->h1;
+  p.hout = (mode == 2) ? K->scal + 1 : K->h2;
+  CMB_TRY(cgs_pass(ctx, K->cplx, mode, p));  // warm-up
+  cudaEvent_t a, b;
+  CMB_CUDA(cudaEventCreate(&a));
+  CMB_CUDA(cudaEventCreate(&b));
+  CMB_CUDA(cudaEventRecord(a, ctx->stream));
+  for (int r = 0; r < reps; ++r) CMB_TRY(cgs_pass(ctx, K->cplx, mode, p));
+  CMB_CUDA(cudaEventRecord(b, ctx->stream));
+  CMB_CUDA(cudaEventSynchronize(b));
+  float ms = 0.f;
+  CMB_CUDA(cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *ms_per_launch = double(ms) / reps;
+  return CMB_OK;
+}
+
 int cmb_lanczos_residual_norm(cmb_krylov* K, double* out) {
   CMB_REQUIRE(K && out, "null argument");
   CMB_REQUIRE(K->nk >= 1, "no Lanczos vector yet");

@@ -155,6 +155,10 @@ int cmb_arnoldi_step(cmb_krylov* k, cmb_op* op, const void* shift, double thresh
 int cmb_krylov_ritz_vectors(cmb_krylov* k, cmb_dtype coef_dtype, const void* coef, int64_t ldc,
                             int64_t ncoef, int64_t nev, void* x_host, int64_t ldx);
 
+/* diagnostic: mean device time of one Gram-Schmidt pass (mode 0 DOT, 1 UPDATE_DOT, 2 UPDATE_NORM) over the first
+ * ncols columns of the basis, `reps` back-to-back launches timed with CUDA events */
+int cmb_debug_cgs_pass(cmb_krylov* k, int mode, int ncols, int reps, double* ms_per_launch);
+
 /* algorithmic bytes moved by the Krylov steps so far: sum of B_op + (3c+7) n s */
 double cmb_krylov_bytes(const cmb_krylov* k);
 
