@@ -75,10 +75,9 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
     if (lane == 0) {
       prefetch_tmap(&tmV);
       const uint32_t bytes = uint32_t(nc) * T * 8 + (x ? Cfg::X_BYTES : 0);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (it / stages) & 1;
+      int s = 0;
+      uint32_t ph = 0;  // stage index / ring phase kept incrementally (no integer division per tile)
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         mbar_wait(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], bytes);
         double* vs = stage_base + size_t(s) * stage_doubles;
@@ -86,6 +85,10 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
         for (int b = 0; b < Cfg::NBOX; ++b)
           tma_load_2d(vs + size_t(b) * nc * Cfg::BOXR, &tmV, tile * T + b * Cfg::BOXR, 0, &full[s]);
         if (x) bulk_load_1d(vs + nc * T, x + size_t(tile) * T, Cfg::X_BYTES, &full[s]);
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
     return;
@@ -115,10 +118,9 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
   }
   double nrm = 0.0;
 
-  int it = 0;
+  int it = 0, s = 0;
+  uint32_t ph = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int s = it % stages;
-    const uint32_t ph = (it / stages) & 1;
     mbar_wait(&full[s], ph);
     const double* vs = stage_base + size_t(s) * stage_doubles;
     double2 xv = make_double2(0.0, 0.0);
@@ -132,32 +134,41 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
 
     double2 yv = xv;
     if (MODE >= 1) {
-      double2 p = make_double2(0.0, 0.0);
+      // two independent accumulation chains per component (even / odd columns) halve the dependent-FMA latency
+      double2 p = make_double2(0.0, 0.0), p2 = make_double2(0.0, 0.0);
 #pragma unroll
       for (int j = 0; j < CG; ++j) {
         if (j < cg) {
+          double2& q = (j & 1) ? p2 : p;
           if (CPLX) {
-            p.x = fma(v[j].x, hr[j], p.x);
-            p.x = fma(-v[j].y, hi[j], p.x);
-            p.y = fma(v[j].x, hi[j], p.y);
-            p.y = fma(v[j].y, hr[j], p.y);
+            q.x = fma(v[j].x, hr[j], q.x);
+            q.x = fma(-v[j].y, hi[j], q.x);
+            q.y = fma(v[j].x, hi[j], q.y);
+            q.y = fma(v[j].y, hr[j], q.y);
           } else {
-            p.x = fma(v[j].x, hr[j], p.x);
-            p.y = fma(v[j].y, hr[j], p.y);
+            q.x = fma(v[j].x, hr[j], q.x);
+            q.y = fma(v[j].y, hr[j], q.y);
           }
         }
       }
+      p.x += p2.x;
+      p.y += p2.y;
       if (WC > 1) {
         double* buf = pw + size_t(it & 1) * WC * T;
         *reinterpret_cast<double2*>(buf + gc * T + row) = p;
         asm volatile("bar.sync %0, %1;" ::"r"(1 + gr), "r"(WC * 32) : "memory");
-        p = make_double2(0.0, 0.0);
+        double2 q[WC];
 #pragma unroll
-        for (int g = 0; g < WC; ++g) {
-          const double2 q = *reinterpret_cast<const double2*>(buf + g * T + row);
-          p.x += q.x;
-          p.y += q.y;
-        }
+        for (int g = 0; g < WC; ++g) q[g] = *reinterpret_cast<const double2*>(buf + g * T + row);
+        // fixed-shape pairwise tree (same order in every warp: all warps of a row group get identical y)
+#pragma unroll
+        for (int w = 1; w < WC; w <<= 1)
+#pragma unroll
+          for (int g = 0; g + w < WC; g += 2 * w) {
+            q[g].x += q[g + w].x;
+            q[g].y += q[g + w].y;
+          }
+        p = q[0];
       }
       yv.x = xv.x - p.x;
       yv.y = xv.y - p.y;
@@ -184,6 +195,10 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
+    if (++s == stages) {
+      s = 0;
+      ph ^= 1u;
+    }
   }
 
   // ===== CTA-level reduction =====
