@@ -297,13 +297,18 @@ static int launch_cfg(cmb_ctx* ctx, const CgsPass& a, int cg) {
 template <bool CPLX, int MODE>
 static int launch_mode(cmb_ctx* ctx, const CgsPass& a) {
   const int c = a.ncols;
-  // warps per row tile: fewer column groups (and taller tiles) for few columns, so a tile stays >= ~16 KB
+  // Fewest column groups WC such that a warp's share fits the register budget: fewer groups mean taller tiles
+  // (T = 64 * 8 / WC rows) and less (for WC = 1: no) cross-warp exchange per tile.
   if (c <= 8) return launch_cfg<8, 1, CPLX, MODE>(ctx, a, c);
-  if (c <= 16) return launch_cfg<8, 2, CPLX, MODE>(ctx, a, (c + 1) / 2);
-  if (c <= 32) return launch_cfg<8, 4, CPLX, MODE>(ctx, a, (c + 3) / 4);
-  if (c <= 64) return launch_cfg<8, 8, CPLX, MODE>(ctx, a, (c + 7) / 8);
   if constexpr (!CPLX) {
+    if (c <= 16) return launch_cfg<16, 1, CPLX, MODE>(ctx, a, c);
+    if (c <= 32) return launch_cfg<16, 2, CPLX, MODE>(ctx, a, (c + 1) / 2);
+    if (c <= 64) return launch_cfg<16, 4, CPLX, MODE>(ctx, a, (c + 3) / 4);
     if (c <= 128) return launch_cfg<16, 8, CPLX, MODE>(ctx, a, (c + 7) / 8);
+  } else {
+    if (c <= 16) return launch_cfg<8, 2, CPLX, MODE>(ctx, a, (c + 1) / 2);
+    if (c <= 32) return launch_cfg<8, 4, CPLX, MODE>(ctx, a, (c + 3) / 4);
+    if (c <= 64) return launch_cfg<8, 8, CPLX, MODE>(ctx, a, (c + 7) / 8);
   }
   set_error("cgs pass: %d columns exceed the per-pass maximum", c);
   return CMB_ERR_INVALID;

@@ -4,7 +4,7 @@
 //   - CSR input converted on the device to SELL-32 (32-row slices, column-major inside a slice):
 //     thread-per-row, fully coalesced value/index streams, x gathered through L1/L2;
 //   - dense row-major GEMV (cfg 1), warp per row;
-//   - matrix-free spin-1/2 Heisenberg chain (cfg 5), thread per basis state;
+//   - matrix-free spin-1/2 Heisenberg chain (cfg 5): heisenberg.cu;
 //   - legacy host callback (reference signature), staged through pinned host memory.
 // All are HBM-bound; algorithmic bytes per apply are recorded in cmb_op::bytes.
 #include <string.h>
@@ -299,75 +299,6 @@ struct DenseOp : cmb_op {
 };
 
 // ======================================================================================================
-// matrix-free Heisenberg chain (single rank; bit i of the state index = spin i)
-// ======================================================================================================
-template <bool CPLX>
-__global__ void __launch_bounds__(256)
-heis_apply_kernel(int L, int nb, double J, const double* __restrict__ w, double* __restrict__ ucol,
-                  double* __restrict__ v, double shr, double shi, StepScalars sc, double* partial, unsigned* ticket) {
-  double inv;
-  if (!step_prologue(sc, inv)) return;
-  const long long dim = 1ll << L;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  double d0 = 0.0, d1 = 0.0;
-  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < dim; s += stride) {
-    int aligned = 0;
-    double ar = 0.0, ai = 0.0;
-    for (int b = 0; b < nb; ++b) {
-      const int i = b, j = (b + 1 == L) ? 0 : b + 1;
-      if (((s >> i) ^ (s >> j)) & 1) {
-        const long long t = s ^ ((1ll << i) | (1ll << j));
-        if (CPLX) {
-          const double2 xv = reinterpret_cast<const double2*>(w)[t];
-          ar += xv.x;
-          ai += xv.y;
-        } else {
-          ar += w[t];
-        }
-      } else {
-        ++aligned;
-      }
-    }
-    const double diag = 0.25 * J * double(2 * aligned - nb);
-    if (CPLX) {
-      const double2 wi = reinterpret_cast<const double2*>(w)[s];
-      const double ur = wi.x * inv, ui = wi.y * inv;
-      const double yr = (diag * wi.x + 0.5 * J * ar) * inv + (shr * ur - shi * ui);
-      const double yi = (diag * wi.y + 0.5 * J * ai) * inv + (shr * ui + shi * ur);
-      reinterpret_cast<double2*>(ucol)[s] = make_double2(ur, ui);
-      reinterpret_cast<double2*>(v)[s] = make_double2(yr, yi);
-      d0 += ur * yr + ui * yi;
-      d1 += ur * yi - ui * yr;
-    } else {
-      const double wi = w[s];
-      const double ui = wi * inv;
-      const double y = (diag * wi + 0.5 * J * ar) * inv + shr * ui;
-      ucol[s] = ui;
-      v[s] = y;
-      d0 = fma(ui, y, d0);
-    }
-  }
-  grid_sum_finalize<CPLX ? 2 : 1>(d0, d1, partial, ticket, sc.alpha_slot);
-}
-
-struct HeisenbergOp : cmb_op {
-  int L = 0, nb = 0;
-  double J = 1.0;
-  int apply(const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) override {
-    int grid = int(std::min<long long>((n_local + 255) / 256, (long long)ctx->num_sms * 8));
-    LaunchScope ls(ctx, "heisenberg_mf");
-    if (cplx)
-      heis_apply_kernel<true><<<grid, 256, 0, ctx->stream>>>(L, nb, J, w, ucol, v, shr, shi, sc, ctx->d_partial,
-                                                             ctx->d_ticket + 1);
-    else
-      heis_apply_kernel<false><<<grid, 256, 0, ctx->stream>>>(L, nb, J, w, ucol, v, shr, shi, sc, ctx->d_partial,
-                                                              ctx->d_ticket + 1);
-    CMB_CUDA(cudaGetLastError());
-    return CMB_OK;
-  }
-};
-
-// ======================================================================================================
 // legacy host callback (lanczos.hpp:116,389,442): device -> pinned host -> user function -> device
 // ======================================================================================================
 __global__ void scale_step_kernel(const double* __restrict__ w, double* __restrict__ ucol, long long nd,
@@ -510,27 +441,6 @@ int cmb_op_dense_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t
     }
   }
   op->bytes = double(n_global) * double(n_global) * s + 2.0 * double(n_global) * s;
-  *out = op;
-  return CMB_OK;
-}
-
-int cmb_op_heisenberg_create(cmb_ctx* ctx, cmb_dtype dtype, int L, double J, int pbc, cmb_op** out) {
-  CMB_REQUIRE(ctx && out, "null argument");
-  *out = nullptr;
-  CMB_REQUIRE(dtype == CMB_F64 || dtype == CMB_C64, "dtype must be CMB_F64 or CMB_C64");
-  CMB_REQUIRE(L >= 2 && L <= 40, "chain length out of range");
-  if (ctx->nranks > 1) {
-    set_error("the matrix-free Heisenberg operator is single-rank in this build");
-    return CMB_ERR_UNSUPPORTED;
-  }
-  HeisenbergOp* op = new (std::nothrow) HeisenbergOp();
-  if (!op) return CMB_ERR_NOMEM;
-  op_common(op, ctx, dtype, int64_t(1) << L, 0, int64_t(1) << L);
-  op->family = "heisenberg_mf";
-  op->L = L;
-  op->J = J;
-  op->nb = (pbc && L > 2) ? L : L - 1;
-  op->bytes = 2.0 * double(op->n_local) * (op->cplx ? 16.0 : 8.0);  // B_mf = 2 n s
   *out = op;
   return CMB_OK;
 }

@@ -96,6 +96,10 @@ int cmb_op_dense_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t
 /* matrix-free spin-1/2 Heisenberg chain (cfg 5): H = J sum_i [SzSz + (S+S- + S-S+)/2]_{i,i+1}; the
  * top log2(nranks) bits of the state index are the rank. */
 int cmb_op_heisenberg_create(cmb_ctx* ctx, cmb_dtype dtype, int L, double J, int pbc, cmb_op** out);
+/* diagnostic / test entry: the row-partitioned Heisenberg operator with nranks VIRTUAL ranks on one GPU (same
+ * kernels and packing as real ranks, the NVLink exchange replaced by device copies); x, y: full 2^L host vectors */
+int cmb_debug_heisenberg_virtual(cmb_ctx* ctx, cmb_dtype dtype, int L, double J, int pbc, int nranks, const void* x,
+                                 void* y);
 /* legacy host callback with the reference's signature plus a user pointer: out = A*in on LOCAL host
  * slabs (single-rank contexts only).  Costs one D2H + one H2D of an n-vector per Krylov step. */
 typedef void (*cmb_matmul_fn)(const void* in, void* out, void* user);

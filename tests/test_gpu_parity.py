@@ -553,3 +553,22 @@ def test_cfg2_full_size_properties(ctx):
     # algorithmic byte count of SURVEY.md §8(d): 101 * B_spmv + sum_{c=1..100} (3c+7) n s  (+ first-step vectors)
     want = 100 * op.bytes + (3 * 5050 + 700) * n * 8.0
     assert abs(es.deviceBytes() - want) / want < 0.01
+
+
+# ------------------------------------------------------------------------------------------------
+# row-partitioned matrix-free Heisenberg operator (cfg 5) with virtual ranks on one GPU
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,nranks,pbc,dtype", [(10, 2, True, np.float64), (10, 2, False, np.float64),
+                                                (11, 4, True, np.float64), (12, 8, True, np.float64),
+                                                (12, 8, False, np.complex128), (9, 4, True, np.complex128),
+                                                (13, 16, True, np.float64)])
+def test_heisenberg_partitioned_virtual_ranks(ctx, L, nranks, pbc, dtype):
+    import ctypes as C
+
+    n = 1 << L
+    x = syn.start_vector(n, seed=21, dtype=dtype)
+    y = np.empty_like(x)
+    capi.check(capi.lib().cmb_debug_heisenberg_virtual(ctx.h, capi.dtype_code(dtype), L, 1.0, int(pbc), nranks,
+                                                       capi.ptr(x), capi.ptr(y)))
+    yo = core.Operator.heisenberg(L, 1.0, pbc, prefix="z" if dtype == np.complex128 else "d").apply(x)
+    np.testing.assert_allclose(y, yo, atol=1e-14)
