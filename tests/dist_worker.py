@@ -153,6 +153,28 @@ def gpu_main():
             assert np.all(np.abs(res - es.ritzResiduals()) < 1e-9)
             es.close()
         op.close()
+    # matrix-free Heisenberg ring, slabs exchanged over NVLink (cfg 5 at small L)
+    Lm = 14
+    n = 1 << Lm
+    r0, r1 = dist.row_range(n)
+    x0 = syn.start_vector(n, seed=7)
+    op = pkg.DeviceOperator.heisenberg(ctx, Lm, 1.0, True)
+    assert op.rows == r1 - r0 and op.height == n
+    y = op.apply(x0[r0:r1])
+    yr = core.Operator.heisenberg(Lm).apply(x0)
+    assert np.abs(y - yr[r0:r1]).max() < 1e-13
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(op).setInitialVector(x0[r0:r1]).setMaxIterations(200).setMaxEigenvalues(1)
+    es.compute()
+    ref = rs.LanczosEigenSolver("d")
+    ref.set_matrix_multiplication(core.Operator.heisenberg(Lm))
+    ref.init, ref.max_iterations, ref.max_eigenvalues = x0, 200, 1
+    ref.compute()
+    assert abs(es.iterations() - ref.iterations) <= 1
+    assert abs(es.eigenvalues()[0] - ref.eigenvalues[0]) < 1e-10 * abs(ref.eigenvalues[0])
+    results["heisenberg_mf_E0"] = es.eigenvalues()
+    es.close()
+    op.close()
     td.barrier()
     ctx.close()
     if rank == 0:
