@@ -239,21 +239,29 @@ def run_ours(args):
     launches0 = ctx.launch_count()
     ctx.profile(True)
     dev_ms = 0.0
+    host_ms = 0.0
     for _ in range(args.steps):
         ctx.flush_l2()  # L2 flushed between timed iterations (inputs are also far larger than L2)
         ctx.sync()
         barrier()
+        t_host = time.perf_counter()
         ctx.timer_start()
         es.compute()
         dev_ms += ctx.timer_stop()
+        host_ms += (time.perf_counter() - t_host) * 1e3
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count() - launches0  # kernels of this library launched inside the timed region
     fams = {}
-    for fam in ("cgs_dot", "cgs_update_dot", "cgs_update_norm", "spmv_sell", "vec_dot"):
+    for fam in ("cgs_dot", "cgs_update_dot", "cgs_update_norm", "spmv_sell", "vec_dot", "nccl_allreduce", "nccl_halo",
+                "halo_pack"):
         fams[fam] = ctx.profile_get(fam)
     ctx.profile(False)
     dev_ms = max_over_ranks(dev_ms)
+    if os.environ.get("BENCH_DEBUG") and rank == 0:
+        print("device-leg: dev %.1f ms, host wall %.1f ms per solve; families %s" % (
+            dev_ms / args.steps, host_ms / args.steps, {k: (round(v[0] / args.steps, 2), v[1] // args.steps) for k, v in fams.items()}),
+            file=sys.stderr, flush=True)
     value = m * args.steps / (dev_ms * 1e-3)
     eig = es.eigenvalues()
     step_bytes = es.deviceBytes()  # algorithmic bytes of one solve on this rank

@@ -109,6 +109,7 @@ int resolve_profile(cmb_ctx* ctx) {
 
 int allreduce_sum_f64(cmb_ctx* ctx, double* p, size_t count) {
   if (ctx->nranks == 1) return CMB_OK;
+  LaunchScope ls(ctx, "nccl_allreduce");
   int r = ctx->nccl->AllReduce(p, p, count, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
   if (r != 0) {
     set_error("ncclAllReduce failed: %s", ctx->nccl->GetErrorString ? ctx->nccl->GetErrorString(r) : "?");

@@ -195,6 +195,7 @@ int HaloExchange::exchange(cmb_ctx* ctx, const double* w, const int* halt) {
       pack_kernel<1><<<grid, 256, 0, ctx->stream>>>(w, d_send_idx, nsend, d_sendbuf, halt);
     CMB_CUDA(cudaGetLastError());
   }
+  LaunchScope ls(ctx, "nccl_halo");
   int rc = nccl_check(ctx, ctx->nccl->GroupStart(), "ncclGroupStart");
   for (int q = 0; q < P && rc == CMB_OK; ++q) {
     if (q == rank) continue;
