@@ -65,9 +65,7 @@ struct Common : cmbs_solver {
       es.setInitialVector();
       return;
     }
-    typename Solver::VectorType x(n);
-    memcpy(x.data(), v, sizeof(Scalar) * size_t(n));
-    es.setInitialVector(std::move(x));
+    es.setInitialVector(static_cast<const Scalar*>(v), Index(n));
   }
   void set_ortho(int64_t nvec, const void* vecs, int64_t ld) override {
     std::vector<typename Solver::VectorType> o;

@@ -159,6 +159,11 @@ class ArnoldiBase {
     initialVector_ = std::move(inivec);
     return *this;
   }
+  /// additive: copy n scalars straight into the (pinned, reused) start-vector storage
+  ArnoldiBase& setInitialVector(const Scalar* data, Index n) {
+    detail::assign_upload(initialVector_, data, n);
+    return *this;
+  }
   ArnoldiBase& setInitialVector() {  // arnoldi.hpp:162-166
     std::mt19937 rengine;
     VectorType full = makeRandomVector(rengine, matrixHeight_);
@@ -420,6 +425,10 @@ class ArnoldiEigenSolver {
   }
   ArnoldiEigenSolver& setInitialVector(VectorType&& inivec) {
     arnoldiBase_.setInitialVector(std::move(inivec));
+    return *this;
+  }
+  ArnoldiEigenSolver& setInitialVector(const Scalar* data, Index n) {
+    arnoldiBase_.setInitialVector(data, n);
     return *this;
   }
   ArnoldiEigenSolver& setInitialVector() {

@@ -174,6 +174,8 @@ class Vector {
   Index rows() const { return size(); }
   Index cols() const { return 1; }
   void resize(Index n) { d_.resize(static_cast<std::size_t>(n)); }
+  /// resize into page-locked host memory (falls back to pageable): host->device copies run at PCIe rate
+  void resizePinned(Index n) { d_.resize(static_cast<std::size_t>(n), true); }
   S* data() { return d_.data(); }
   const S* data() const { return d_.data(); }
   S& operator[](Index i) { return d_[static_cast<std::size_t>(i)]; }
@@ -281,6 +283,20 @@ std::ostream& operator<<(std::ostream& os, const Matrix<S>& m) {
 #endif  // CMPT_EIGENEX_HAVE_EIGEN
 
 namespace detail {
+// Copy n scalars into a vector that will be uploaded to the device (start vector): large vectors live in pinned
+// memory, and an existing allocation of the right size is reused.
+template <class S>
+inline void assign_upload(Vector<S>& v, const S* src, Index n) {
+#ifdef CMPT_EIGENEX_HAVE_EIGEN
+  v.resize(n);
+#else
+  if (static_cast<std::size_t>(n) * sizeof(S) >= (std::size_t(1) << 20))
+    v.resizePinned(n);
+  else
+    v.resize(n);
+#endif
+  if (n > 0) std::memcpy(static_cast<void*>(v.data()), src, static_cast<std::size_t>(n) * sizeof(S));
+}
 // (Re)size a matrix that will receive device results (Ritz vectors): contents are left uninitialised.
 template <class S>
 inline void resize_result(Matrix<S>& m, Index r, Index c) {

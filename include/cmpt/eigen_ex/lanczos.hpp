@@ -190,6 +190,11 @@ class LanczosBase {
     initialVector_ = std::move(inivec);
     return *this;
   }
+  /// additive: copy n scalars straight into the (pinned, reused) start-vector storage
+  LanczosBase& setInitialVector(const Scalar* data, Index n) {
+    detail::assign_upload(initialVector_, data, n);
+    return *this;
+  }
   /// initial vector of size matrixHeight with random contents, fixed seed (lanczos.hpp:214-218)
   LanczosBase& setInitialVector() {
     std::mt19937 rengine;
@@ -449,6 +454,10 @@ class LanczosEigenSolver {
   }
   LanczosEigenSolver& setInitialVector(VectorType&& inivec) {
     lanczosBase_.setInitialVector(std::move(inivec));
+    return *this;
+  }
+  LanczosEigenSolver& setInitialVector(const Scalar* data, Index n) {
+    lanczosBase_.setInitialVector(data, n);
     return *this;
   }
   LanczosEigenSolver& setInitialVector() {
