@@ -21,6 +21,7 @@
 // being ld/2 interleaved (re,im) pairs; a lane always holds one double2 per column, i.e. one complex
 // element or two real rows.
 #include "common.cuh"
+#include "device_utils.cuh"
 #include "kernels.cuh"
 
 namespace cmb {
@@ -42,7 +43,8 @@ template <int CG, int WC, bool CPLX, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x, double* __restrict__ y,
            const double* __restrict__ hin, double* __restrict__ hout, double* __restrict__ partial,
-           unsigned* __restrict__ ticket, const int* __restrict__ halt, int ncols, int cg, int ntiles, int stages) {
+           unsigned* __restrict__ ticket, const int* __restrict__ halt, int ncols, int cg, int ntiles, int stages,
+           MailPull pull, MailPush push) {
   using Cfg = CgsCfg<WC>;
   constexpr int T = Cfg::T, WR = Cfg::WR;
   constexpr int ES = CPLX ? 2 : 1;  // doubles per coefficient
@@ -102,12 +104,23 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
 
   double hr[CG], hi[CPLX ? CG : 1];
   if (MODE >= 1) {
+    const bool mailed = pull.P > 1;  // coefficients = sum over ranks of the partials pushed into the mailbox
+    if (mailed) mail_wait(pull);
 #pragma unroll
     for (int j = 0; j < CG; ++j) {
       const int col = gc * cg + j;
       const bool ok = (j < cg) && (col < ncols);
-      hr[j] = ok ? hin[col * ES] : 0.0;
-      if (CPLX) hi[j] = ok ? hin[col * ES + 1] : 0.0;
+      if (mailed) {
+        hr[j] = ok ? mail_sum(pull, col * ES) : 0.0;
+        if (CPLX) hi[j] = ok ? mail_sum(pull, col * ES + 1) : 0.0;
+        if (ok && blockIdx.x == 0 && gr == 0 && lane == 0 && pull.writeback) {
+          pull.writeback[col * ES] = hr[j];
+          if (CPLX) pull.writeback[col * ES + 1] = hi[j];
+        }
+      } else {
+        hr[j] = ok ? hin[col * ES] : 0.0;
+        if (CPLX) hi[j] = ok ? hin[col * ES + 1] : 0.0;
+      }
     }
   }
   double ar[CG], ai[CPLX ? CG : 1];
@@ -241,9 +254,17 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
     for (int t = threadIdx.x; t < nout; t += kConsumerWarps * 32) {
       double sacc = 0.0;
       for (int b = 0; b < int(gridDim.x); ++b) sacc += __ldcg(&partial[size_t(b) * kPartialStride + t]);
-      hout[t] = sacc;
+      if (push.P > 1)
+        mail_push_value(push, t, sacc);  // this rank's partial straight into every peer's mailbox (NVLink)
+      else
+        hout[t] = sacc;
     }
     if (threadIdx.x == 0) *ticket = 0u;
+    if (push.P > 1) {
+      __threadfence_system();
+      asm volatile("bar.sync 9, %0;" ::"r"(kConsumerWarps * 32) : "memory");
+      if (threadIdx.x == 0) mail_publish(push);
+    }
   }
 }
 
@@ -288,7 +309,7 @@ static int launch_cfg(cmb_ctx* ctx, const CgsPass& a, int cg) {
   {
     LaunchScope ls(ctx, a.family ? a.family : fam[MODE]);
     kern<<<grid, kThreads, smem, ctx->stream>>>(tm, a.x, a.y, a.hin, a.hout, ctx->d_partial, ctx->d_ticket, a.halt,
-                                                a.ncols, cg, ntiles, stages);
+                                                a.ncols, cg, ntiles, stages, a.pull, a.push);
   }
   CMB_CUDA(cudaGetLastError());
   return CMB_OK;

@@ -51,6 +51,7 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, NcclId /* ncclUniqueId, by value */, int) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
@@ -63,6 +64,30 @@ enum { kNcclFloat64 = 8, kNcclInt8 = 0, kNcclInt32 = 2, kNcclInt64 = 4, kNcclUin
 struct ProfEntry {
   double ms = 0.0;
   uint64_t launches = 0;
+};
+
+// ---- peer-memory mailboxes: the fused "reduce over NVLink" of the Gram-Schmidt coefficients -------------
+// Every rank owns a mailbox in its HBM, mapped into all peers through CUDA IPC.  The CTA that finishes a
+// Gram-Schmidt pass last pushes this rank's partial coefficient vector straight into every peer's mailbox
+// with NVLink stores and then publishes a sequence number; the next kernel waits for the P sequence numbers
+// in its own mailbox and sums the P partials in rank order (identical bits on every rank).  No separate
+// collective kernel runs between the passes.
+constexpr int kMaxPeers = 16;
+constexpr int kMailSlots = 4;     // ring of slots, indexed by sequence number
+constexpr int kMailStride = 272;  // doubles per (slot, sender)
+struct MailPush {                 // producer side (kernel argument)
+  int P = 1, rank = 0;
+  unsigned long long seq = 0;
+  double* data[kMaxPeers];                // slot base in every rank's mailbox (own rank included)
+  unsigned long long* flag[kMaxPeers];    // flag array of that slot in every rank's mailbox
+};
+struct MailPull {                 // consumer side (kernel argument)
+  int P = 1;
+  unsigned long long seq = 0;
+  const double* data = nullptr;           // slot base in the own mailbox: [P][kMailStride]
+  const unsigned long long* flag = nullptr;
+  double* writeback = nullptr;            // optional plain copy of the reduced values (for the host)
+  int* error = nullptr;                   // set to 1 when a peer never arrives (bounded spin)
 };
 
 }  // namespace cmb
@@ -82,6 +107,12 @@ struct cmb_ctx {
   // cross-CTA reduction workspace: partial sums [kMaxGrid][kPartialStride] and a ticket counter
   double* d_partial = nullptr;
   unsigned* d_ticket = nullptr;
+  // peer-memory mailboxes (multi-rank contexts; see cmb::MailPush)
+  bool mail_ok = false;
+  double* mail_data[cmb::kMaxPeers] = {};              // [rank]: base of that rank's mailbox data (mapped here)
+  unsigned long long* mail_flag[cmb::kMaxPeers] = {};  // [rank]: base of that rank's flag array
+  unsigned long long mail_seq = 0;                     // sequence number of the last push (same on all ranks)
+  int* d_mail_error = nullptr;
   // L2 flush buffer
   void* d_flush = nullptr;
   size_t flush_bytes = 0;
@@ -113,6 +144,9 @@ int resolve_profile(cmb_ctx* ctx);
 
 int allreduce_sum_f64(cmb_ctx* ctx, double* dev_ptr, size_t count);  // no-op when nranks == 1
 int allreduce_min_u64(cmb_ctx* ctx, unsigned long long* dev_ptr, size_t count);
+// mailbox bookkeeping (host): the next push gets a fresh sequence number; a pull names the push it consumes
+MailPush mail_next_push(cmb_ctx* ctx);
+MailPull mail_pull_of(cmb_ctx* ctx, unsigned long long seq, double* writeback);
 
 // driver entry point for tensor-map encoding (no link-time libcuda dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

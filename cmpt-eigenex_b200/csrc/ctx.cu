@@ -2,7 +2,10 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "common.cuh"
 
@@ -35,6 +38,7 @@ int nccl_load(NcclApi** out) {
       api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
       api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
       api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+      api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
       api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
       api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
       api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
@@ -126,6 +130,123 @@ int allreduce_min_u64(cmb_ctx* ctx, unsigned long long* p, size_t count) {
     return CMB_ERR_NCCL;
   }
   return CMB_OK;
+}
+
+// ---- peer-memory mailboxes -------------------------------------------------------------------------------
+// Layout of one rank's mailbox: data [kMailSlots][P][kMailStride] doubles, then flags [kMailSlots][P] u64.
+static size_t mail_data_doubles(int P) { return size_t(kMailSlots) * P * kMailStride; }
+
+MailPush mail_next_push(cmb_ctx* ctx) {
+  MailPush m;
+  m.P = ctx->nranks;
+  m.rank = ctx->rank;
+  m.seq = ++ctx->mail_seq;
+  const size_t slot = size_t(m.seq % kMailSlots);
+  for (int q = 0; q < kMaxPeers; ++q) {
+    m.data[q] = nullptr;
+    m.flag[q] = nullptr;
+  }
+  for (int q = 0; q < ctx->nranks; ++q) {
+    m.data[q] = ctx->mail_data[q] + slot * ctx->nranks * kMailStride;
+    m.flag[q] = ctx->mail_flag[q] + slot * ctx->nranks;
+  }
+  return m;
+}
+
+MailPull mail_pull_of(cmb_ctx* ctx, unsigned long long seq, double* writeback) {
+  MailPull m;
+  m.P = ctx->nranks;
+  m.seq = seq;
+  const size_t slot = size_t(seq % kMailSlots);
+  m.data = ctx->mail_data[ctx->rank] + slot * ctx->nranks * kMailStride;
+  m.flag = ctx->mail_flag[ctx->rank] + slot * ctx->nranks;
+  m.writeback = writeback;
+  m.error = ctx->d_mail_error;
+  return m;
+}
+
+// Allocate this rank's mailbox, exchange CUDA IPC handles through NCCL (allgather of raw bytes) and map the
+// peers' mailboxes.  Failure is not fatal: the context then keeps using NCCL allreduce for the coefficients.
+static int mail_setup(cmb_ctx* c) {
+  if (c->nranks < 2 || c->nranks > kMaxPeers || !c->nccl->AllGather) return CMB_OK;
+  if (getenv("CMPT_B200_NO_MAILBOX")) return CMB_OK;
+  const int P = c->nranks;
+  const size_t bytes = mail_data_doubles(P) * sizeof(double) + size_t(kMailSlots) * P * sizeof(unsigned long long);
+  void* base = nullptr;
+  if (cudaMalloc(&base, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return CMB_OK;
+  }
+  cudaMemset(base, 0, bytes);
+  cudaMalloc(&c->d_mail_error, sizeof(int));
+  cudaMemset(c->d_mail_error, 0, sizeof(int));
+  cudaIpcMemHandle_t mine;
+  bool ok = cudaIpcGetMemHandle(&mine, base) == cudaSuccess;
+  // allgather [ok flag + handle] as bytes
+  constexpr size_t kRec = 80;
+  static_assert(sizeof(cudaIpcMemHandle_t) <= kRec - 8, "IPC handle larger than expected");
+  unsigned char rec[kRec] = {0};
+  rec[0] = ok ? 1 : 0;
+  memcpy(rec + 8, &mine, sizeof(mine));
+  unsigned char *d_send = nullptr, *d_recv = nullptr;
+  std::vector<unsigned char> all(kRec * P, 0);
+  cudaMalloc(&d_send, kRec);
+  cudaMalloc(&d_recv, kRec * P);
+  cudaMemcpyAsync(d_send, rec, kRec, cudaMemcpyHostToDevice, c->stream);
+  int nr = c->nccl->AllGather(d_send, d_recv, kRec, kNcclInt8, c->nccl_comm, c->stream);
+  cudaMemcpyAsync(all.data(), d_recv, kRec * P, cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t se = cudaStreamSynchronize(c->stream);
+  cudaFree(d_send);
+  cudaFree(d_recv);
+  bool all_ok = (nr == 0) && (se == cudaSuccess);
+  for (int q = 0; q < P && all_ok; ++q) all_ok = all[kRec * q] == 1;
+  if (all_ok) {
+    for (int q = 0; q < P && all_ok; ++q) {
+      void* p = base;
+      if (q != c->rank) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all.data() + kRec * q + 8, sizeof(h));
+        if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          all_ok = false;
+          break;
+        }
+      }
+      c->mail_data[q] = static_cast<double*>(p);
+      c->mail_flag[q] = reinterpret_cast<unsigned long long*>(static_cast<double*>(p) + mail_data_doubles(P));
+    }
+  }
+  // every rank must agree on whether the mailboxes are usable (a single failure disables them everywhere)
+  double* d_flag = nullptr;
+  cudaMalloc(&d_flag, sizeof(double));
+  const double mineok = all_ok ? 0.0 : 1.0;
+  cudaMemcpyAsync(d_flag, &mineok, sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  c->nccl->AllReduce(d_flag, d_flag, 1, kNcclFloat64, kNcclSum, c->nccl_comm, c->stream);
+  double failures = 1.0;
+  cudaMemcpyAsync(&failures, d_flag, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(d_flag);
+  cudaGetLastError();
+  c->mail_ok = (failures == 0.0);
+  if (!c->mail_ok) {
+    for (int q = 0; q < P; ++q)
+      if (q != c->rank && c->mail_data[q]) cudaIpcCloseMemHandle(c->mail_data[q]);
+    for (int q = 0; q < P; ++q) c->mail_data[q] = nullptr, c->mail_flag[q] = nullptr;
+    cudaFree(base);
+  } else {
+    c->mail_data[c->rank] = static_cast<double*>(base);
+    c->mail_flag[c->rank] = reinterpret_cast<unsigned long long*>(static_cast<double*>(base) + mail_data_doubles(P));
+  }
+  return CMB_OK;
+}
+
+static void mail_teardown(cmb_ctx* c) {
+  if (!c->mail_ok) return;
+  for (int q = 0; q < c->nranks; ++q)
+    if (q != c->rank && c->mail_data[q]) cudaIpcCloseMemHandle(c->mail_data[q]);
+  cudaFree(c->mail_data[c->rank]);
+  cudaFree(c->d_mail_error);
+  c->mail_ok = false;
 }
 
 static int ctx_init_common(cmb_ctx* c, int device) {
@@ -249,6 +370,7 @@ int cmb_ctx_create_dist(int device, int rank, int nranks, const void* nccl_id, c
       delete c;
       return CMB_ERR_NCCL;
     }
+    mail_setup(c);
   }
   *out = c;
   return CMB_OK;
@@ -258,6 +380,17 @@ int cmb_ctx_destroy(cmb_ctx* c) {
   if (!c) return CMB_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->mail_ok) {
+    // unmap the peers' mailboxes, wait until everybody has done so, then free the own one
+    for (int q = 0; q < c->nranks; ++q)
+      if (q != c->rank && c->mail_data[q]) {
+        cudaIpcCloseMemHandle(c->mail_data[q]);
+        c->mail_data[q] = nullptr;
+      }
+    allreduce_sum_f64(c, c->d_partial, 1);
+    cudaStreamSynchronize(c->stream);
+    mail_teardown(c);
+  }
   if (c->nccl_comm && c->nccl) c->nccl->CommDestroy(c->nccl_comm);
   for (auto& p : c->pending) {
     cudaEventDestroy(p.a);

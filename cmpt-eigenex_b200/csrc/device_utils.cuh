@@ -7,9 +7,64 @@ namespace cmb {
 // Every operator apply starts with the same prologue (LanczosBase::updateLanczosSteps, lanczos.hpp:429-439):
 // beta = ||w|| ; if beta <= threshold the step is dropped ; else u = w / beta.  The decision is taken on the
 // device so that a chain of steps can be enqueued without a host round trip; `halt` is sticky.
+// ---- peer-memory mailboxes (see common.cuh) ---------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Wait (whole warp) until every rank has published sequence number m.seq in this rank's mailbox.  The spin is
+// bounded (~2 s): a missing peer raises m.error instead of hanging the GPU.
+__device__ __forceinline__ void mail_wait(const MailPull& m) {
+  const int lane = threadIdx.x & 31;
+  if (lane < m.P) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(m.flag + lane) < m.seq) {
+      if (clock64() - t0 > (1ll << 32)) {
+        *m.error = 1;
+        break;
+      }
+    }
+  }
+  __syncwarp();
+}
+// Sum of the P partials of entry idx, always in rank order: every rank gets identical bits.
+__device__ __forceinline__ double mail_sum(const MailPull& m, int idx) {
+  double s = 0.0;
+  for (int q = 0; q < m.P; ++q) s += ld_relaxed_sys_f64(m.data + q * kMailStride + idx);
+  return s;
+}
+// Push value `v` as entry idx of this rank into every rank's mailbox (NVLink stores).
+__device__ __forceinline__ void mail_push_value(const MailPush& m, int idx, double v) {
+  for (int q = 0; q < m.P; ++q) st_relaxed_sys_f64(m.data[q] + m.rank * kMailStride + idx, v);
+}
+// Publish: call by ONE thread after all pushing threads fenced (__threadfence_system) and synchronised.
+__device__ __forceinline__ void mail_publish(const MailPush& m) {
+  for (int q = 0; q < m.P; ++q) st_release_sys_u64(m.flag[q] + m.rank, m.seq);
+}
+
 __device__ __forceinline__ bool step_prologue(const StepScalars& sc, double& inv) {
   if (*sc.halt) return false;
-  const double beta = sqrt(*sc.nrm2);
+  double nrm2;
+  if (sc.nrm2_pull.P > 1) {
+    mail_wait(sc.nrm2_pull);
+    nrm2 = mail_sum(sc.nrm2_pull, 0);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && sc.nrm2_pull.writeback) *sc.nrm2_pull.writeback = nrm2;
+  } else {
+    nrm2 = *sc.nrm2;
+  }
+  const double beta = sqrt(nrm2);
   const bool first = (blockIdx.x == 0 && threadIdx.x == 0);
   if (first && sc.beta_slot) *sc.beta_slot = beta;
   if (beta <= sc.threshold) {

@@ -16,6 +16,8 @@ struct CgsPass {
   double* hout = nullptr;       // V^H y (modes 0, 1) or ||y||^2 (mode 2)
   const int* halt = nullptr;    // device flag: non-zero turns the launch into a no-op
   const char* family = nullptr; // profiling family override
+  MailPull pull;                // P > 1: hin is the sum of the per-rank partials in the mailbox
+  MailPush push;                // P > 1: the result goes to every peer's mailbox instead of hout
 };
 enum { CGS_DOT = 0, CGS_UPDATE_DOT = 1, CGS_UPDATE_NORM = 2 };
 inline int cgs_max_cols(bool cplx) { return cplx ? 64 : 128; }
@@ -41,7 +43,8 @@ int vec_pick_element(cmb_ctx* ctx, const double* x, const unsigned long long* id
 // Per-step scalars every operator-apply kernel reads (device memory, filled by earlier launches):
 // nrm2 -> beta = sqrt(nrm2); if beta <= threshold the chain halts (lanczos.hpp:433-437).
 struct StepScalars {
-  const double* nrm2;  // ||w||^2 (already reduced over ranks)
+  const double* nrm2;  // ||w||^2 (already reduced over ranks) when nrm2_pull.P == 1
+  MailPull nrm2_pull;  // P > 1: the per-rank partial norms sit in the mailbox (summed in the prologue)
   double threshold;    // halt when sqrt(nrm2) <= threshold (negative: never)
   int* halt;           // sticky halt flag
   double* beta_slot;   // receives sqrt(nrm2)

@@ -47,6 +47,7 @@ struct cmb_krylov {
   double* h_stage = nullptr;  // pinned staging for scalars
   size_t h_stage_elems = 0;
   bool started = false;
+  unsigned long long nrm2_seq = 0;  // non-zero: ||w||^2 is the mailbox reduction with this sequence number
   double residue = 0.0;  // Arnoldi: last residual norm (host copy)
   double bytes = 0.0;
   double *tmp1 = nullptr, *tmp2 = nullptr, *tmpz = nullptr;
@@ -133,6 +134,39 @@ static int total_cols(const std::vector<Chunk>& ch) {
 // Gram-Schmidt of x against the chunk columns, result in y (may alias x); coefficients of the first pass
 // in h1, of the second in h2 (chunk order); ||y||^2 in nrm2_out.  Single chunk: DOT, UPDATE_DOT,
 // UPDATE_NORM (the basis is streamed three times).  Several chunks: one extra DOT sweep.
+// Fused variant for row-partitioned runs (one chunk): the three passes exchange their per-rank partial results
+// through the peer-memory mailboxes (NVLink stores from the finishing CTA, summed in the next kernel's prologue),
+// so no collective kernel runs in between.  *nrm2_seq receives the sequence number under which ||y||^2 will be
+// found by the consumer (the operator apply).
+static int gram_schmidt2_mailed(cmb_krylov* K, const Chunk& c, const double* x, double* y,
+                                unsigned long long* nrm2_seq) {
+  cmb_ctx* ctx = K->ctx;
+  CgsPass p;
+  p.ld = K->ld;
+  p.halt = K->halt;
+  p.V = c.V;
+  p.ncols = c.ncols;
+  p.col_stride = c.col_stride;
+  // pass 1: partial h1 -> mailboxes
+  p.x = x;
+  p.push = mail_next_push(ctx);
+  const unsigned long long s1 = p.push.seq;
+  CMB_TRY(cgs_pass(ctx, K->cplx, CGS_DOT, p));
+  // pass 2: h1 = sum of partials ; y = x - V h1 ; partial h2 -> mailboxes
+  p.y = y;
+  p.pull = mail_pull_of(ctx, s1, K->h1);
+  p.push = mail_next_push(ctx);
+  const unsigned long long s2 = p.push.seq;
+  CMB_TRY(cgs_pass(ctx, K->cplx, CGS_UPDATE_DOT, p));
+  // pass 3: y -= V h2 ; partial ||y||^2 -> mailboxes
+  p.x = y;
+  p.pull = mail_pull_of(ctx, s2, K->h2);
+  p.push = mail_next_push(ctx);
+  *nrm2_seq = p.push.seq;
+  CMB_TRY(cgs_pass(ctx, K->cplx, CGS_UPDATE_NORM, p));
+  return CMB_OK;
+}
+
 static int gram_schmidt2(cmb_krylov* K, const std::vector<Chunk>& chunks, const double* x, double* y,
                          double* nrm2_out) {
   cmb_ctx* ctx = K->ctx;
@@ -247,8 +281,12 @@ static int enqueue_lanczos_orth(cmb_krylov* K, int64_t interval) {
     // full reorthogonalisation: the three-term recurrence is subsumed by CGS pass 1
     // (alpha_k = h1[k], beta_{k-1} ~ h1[k-1]); deflation vectors are just the leading columns.
     contiguous_chunks(K, 0, K->ndefl + k + 1, chunks);
+    K->nrm2_seq = 0;
+    if (K->ctx->mail_ok && chunks.size() == 1)
+      return gram_schmidt2_mailed(K, chunks[0], K->v, K->w, &K->nrm2_seq);
     return gram_schmidt2(K, chunks, K->v, K->w, K->scal);
   }
+  K->nrm2_seq = 0;
   // explicit recurrence w = v - alpha_k u_k - beta_{k-1} u_{k-1} (lanczos.hpp:402-408)
   const int first = (k > 0) ? k - 1 : k;
   contiguous_chunks(K, K->ndefl + first, K->ndefl + k + 1, chunks);
@@ -355,6 +393,7 @@ int cmb_krylov_clear(cmb_krylov* K) {
   CMB_CUDA(cudaSetDevice(K->ctx->device));
   K->nk = 0;
   K->started = false;
+  K->nrm2_seq = 0;
   K->residue = 0.0;
   K->bytes = 0.0;
   CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int) * 4, K->ctx->stream));
@@ -383,6 +422,7 @@ int cmb_krylov_start(cmb_krylov* K, const void* init, double threshold, int* sta
   CMB_CUDA(cudaSetDevice(ctx->device));
   K->nk = 0;
   K->started = false;
+  K->nrm2_seq = 0;
   K->residue = 0.0;
   CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int) * 4, ctx->stream));
   CMB_CUDA(cudaMemcpyAsync(K->w, init, sizeof(double) * K->nd_local, cudaMemcpyHostToDevice, ctx->stream));
@@ -459,6 +499,7 @@ int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, d
     K->nk = nk_save;
     CMB_TRY(rc);
     sc.threshold = threshold;
+    if (K->nrm2_seq) sc.nrm2_pull = mail_pull_of(ctx, K->nrm2_seq, K->scal);  // ||w||^2 sits in the mailbox
     sc.beta_slot = K->beta_dev + k;
     sc.alpha_slot = K->alpha_dev + size_t(k + 1) * 2;
     CMB_TRY(op->apply(K->w, K->col(K->ndefl + k + 1), K->v, shift, 0.0, sc));
@@ -481,6 +522,14 @@ int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, d
   CMB_CUDA(cudaMemcpyAsync(hs + 2 * na + nb, K->halt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CMB_CUDA(cudaStreamSynchronize(ctx->stream));
   const int halted = *reinterpret_cast<int*>(hs + 2 * na + nb);
+  if (ctx->mail_ok) {
+    int mail_err = 0;
+    CMB_CUDA(cudaMemcpy(&mail_err, ctx->d_mail_error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (mail_err) {
+      set_error("a peer rank never published its Gram-Schmidt partials (mailbox wait timed out)");
+      return CMB_ERR_NCCL;
+    }
+  }
   int ok_steps = enq;
   if (halted) {
     ok_steps = 0;
