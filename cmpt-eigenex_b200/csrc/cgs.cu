@@ -251,9 +251,31 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
   asm volatile("bar.sync 9, %0;" ::"r"(kConsumerWarps * 32) : "memory");
   if (s_last) {
     __threadfence();
-    for (int t = threadIdx.x; t < nout; t += kConsumerWarps * 32) {
+    // Sum the per-CTA partials in a fixed pattern (deterministic): G thread groups take interleaved CTAs with
+    // four independent accumulators each (keeps ~4G loads in flight instead of one serial chain of gridDim.x
+    // L2 round trips), then one thread per value adds the G group sums in order.
+    __shared__ double s_fin[kConsumerWarps * 32];
+    const int tid = threadIdx.x, nb = int(gridDim.x);
+    int G = (kConsumerWarps * 32) / nout;
+    G = G < 1 ? 1 : (G > 16 ? 16 : G);
+    if (tid < G * nout) {
+      const int vi = tid % nout, g = tid / nout;
+      const double* pp = partial + vi;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int b = g;
+      for (; b + 3 * G < nb; b += 4 * G) {
+        a0 += __ldcg(pp + size_t(b) * kPartialStride);
+        a1 += __ldcg(pp + size_t(b + G) * kPartialStride);
+        a2 += __ldcg(pp + size_t(b + 2 * G) * kPartialStride);
+        a3 += __ldcg(pp + size_t(b + 3 * G) * kPartialStride);
+      }
+      for (; b < nb; b += G) a0 += __ldcg(pp + size_t(b) * kPartialStride);
+      s_fin[tid] = (a0 + a1) + (a2 + a3);
+    }
+    asm volatile("bar.sync 9, %0;" ::"r"(kConsumerWarps * 32) : "memory");
+    for (int t = tid; t < nout; t += kConsumerWarps * 32) {
       double sacc = 0.0;
-      for (int b = 0; b < int(gridDim.x); ++b) sacc += __ldcg(&partial[size_t(b) * kPartialStride + t]);
+      for (int g = 0; g < G; ++g) sacc += s_fin[g * nout + t];
       if (push.P > 1)
         mail_push_value(push, t, sacc);  // this rank's partial straight into every peer's mailbox (NVLink)
       else
