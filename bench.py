@@ -281,8 +281,15 @@ def run_ours(args):
         per_launch_bytes = alg[dom] * args.steps / dom_n
         per_launch_s = dom_ms * 1e-3 / dom_n
         ach = per_launch_bytes / per_launch_s / 1e9
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[dom]
+            traffic = tr["ratio"] * per_launch_bytes  # measured dram/algorithmic ratio x this run's bytes per launch
+            traffic_src = "ncu --set full capture (profiles/r1b_prof_step_raw.txt): dram bytes / algorithmic bytes = %.4f" % tr["ratio"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_s * 1e3,
                 "families": {k: {"ms": fams[k][0], "launches": fams[k][1],
                                  "GBps": (alg[k] * args.steps / (fams[k][0] * 1e-3) / 1e9) if (k in alg and fams[k][0] > 0) else None}
