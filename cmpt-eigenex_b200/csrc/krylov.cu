@@ -623,10 +623,10 @@ int cmb_lanczos_residual_norm(cmb_krylov* K, double* out) {
   return CMB_OK;
 }
 
-int cmb_arnoldi_step(cmb_krylov* K, cmb_op* op, const void* shift, double threshold, void* hcol, double* residue,
-                     int* status) {
+int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double threshold, int64_t nsteps, void* hcols,
+                    int64_t ldh, double* residues, int64_t* steps_done, int* status) {
   CMB_TRY(check_pair(K, op));
-  CMB_REQUIRE(hcol && residue && status, "null argument");
+  CMB_REQUIRE(hcols && residues && steps_done && status && nsteps >= 0, "bad argument");
   cmb_ctx* ctx = K->ctx;
   CMB_CUDA(cudaSetDevice(ctx->device));
   double shr = 0.0, shi = 0.0;
@@ -635,50 +635,111 @@ int cmb_arnoldi_step(cmb_krylov* K, cmb_op* op, const void* shift, double thresh
     if (K->cplx) shi = static_cast<const double*>(shift)[1];
   }
   *status = CMB_STEP_OK;
+  *steps_done = 0;
+  if (nsteps == 0) return CMB_OK;
   if (K->nk == 0) {
     CMB_REQUIRE(K->started, "cmb_krylov_start must succeed before the first step");
   } else {
     // arnoldiStepIsUtmost (arnoldi.hpp:277-288)
     if (K->nk >= K->n_global) {
       *status = CMB_STEP_FULL;
-      *residue = K->residue;
       return CMB_OK;
     }
     if (K->residue <= threshold) {
       *status = CMB_STEP_BREAKDOWN;
-      *residue = K->residue;
       return CMB_OK;
     }
   }
-  const int k = K->nk;  // index of the vector created now
-  CMB_REQUIRE(K->ndefl + k + 2 < kMaxSlots, "too many Krylov steps");
-  CMB_TRY(ensure_cols(K, K->ndefl + k + 1));
-  StepScalars sc;
-  sc.nrm2 = K->scal;
-  sc.halt = K->halt;
-  sc.threshold = -1.0;  // the host has already tested the residue
-  sc.beta_slot = K->scal + 3;
-  sc.alpha_slot = K->scal + 4;
-  // q_k = w / residue ; v = (A + shift) q_k        (arnoldi.hpp:361-372)
-  CMB_TRY(op->apply(K->w, K->col(K->ndefl + k), K->v, shr, shi, sc));
-  // CGS2 of v against deflation vectors and q_0..q_k ; h(:,k) = h1 + h2 ; residue = ||w||   (:373-385)
-  std::vector<Chunk> chunks;
-  const int c = K->ndefl + k + 1;
-  contiguous_chunks(K, 0, c, chunks);
-  CMB_TRY(gram_schmidt2(K, chunks, K->v, K->w, K->scal));
+  const int k0 = K->nk;
+  if (nsteps > K->n_global - k0) nsteps = K->n_global - k0;  // the basis cannot exceed the dimension
+  CMB_REQUIRE(K->ndefl + k0 + nsteps + 2 < kMaxSlots, "too many Krylov steps");
+  CMB_REQUIRE(ldh >= k0 + nsteps, "ldh too small for the Hessenberg columns");
   const int es = K->es;
-  CMB_TRY(ensure_stage(K, size_t(2 * c * es + 4)));
+  const int cmax = K->ndefl + k0 + int(nsteps);
+  // per-step history of h1, h2 and ||w||^2 so that the whole chain needs one host synchronisation
+  const size_t hstride = size_t(cmax) * es;
+  double* hist = nullptr;
+  CMB_TRY(pool_alloc(ctx, &hist, sizeof(double) * (2 * hstride + 1) * size_t(nsteps)));
+  int rc = CMB_OK;
+  for (int64_t s = 0; s < nsteps && rc == CMB_OK; ++s) {
+    const int k = k0 + int(s);  // index of the vector created now
+    rc = ensure_cols(K, K->ndefl + k + 1);
+    if (rc != CMB_OK) break;
+    StepScalars sc;
+    sc.nrm2 = K->scal;
+    sc.halt = K->halt;
+    // the host has tested the residue of the state it knows; later steps of the chain test it on the device
+    sc.threshold = (s == 0) ? -1.0 : threshold;
+    sc.beta_slot = K->scal + 3;
+    sc.alpha_slot = K->scal + 4;
+    // q_k = w / residue ; v = (A + shift) q_k        (arnoldi.hpp:361-372)
+    rc = op->apply(K->w, K->col(K->ndefl + k), K->v, shr, shi, sc);
+    if (rc != CMB_OK) break;
+    // CGS2 of v against deflation vectors and q_0..q_k ; h(:,k) = h1 + h2 ; residue = ||w||   (:373-385)
+    std::vector<Chunk> chunks;
+    const int c = K->ndefl + k + 1;
+    contiguous_chunks(K, 0, c, chunks);
+    rc = gram_schmidt2(K, chunks, K->v, K->w, K->scal);
+    if (rc != CMB_OK) break;
+    double* slot = hist + size_t(s) * (2 * hstride + 1);
+    cudaMemcpyAsync(slot, K->h1, sizeof(double) * c * es, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemcpyAsync(slot + hstride, K->h2, sizeof(double) * c * es, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemcpyAsync(slot + 2 * hstride, K->scal, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+    add_step_bytes(K, op, c);
+  }
+  if (rc == CMB_OK) rc = ensure_stage(K, (2 * hstride + 1) * size_t(nsteps) + 8);
+  int halted = 0;
+  if (rc == CMB_OK) {
+    double* hs = K->h_stage;
+    cudaError_t e = cudaMemcpyAsync(hs, hist, sizeof(double) * (2 * hstride + 1) * size_t(nsteps), cudaMemcpyDeviceToHost,
+                                    ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(hs + (2 * hstride + 1) * size_t(nsteps), K->halt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      set_error("cmb_arnoldi_run: %s", cudaGetErrorString(e));
+      rc = CMB_ERR_CUDA;
+    } else {
+      halted = *reinterpret_cast<int*>(hs + (2 * hstride + 1) * size_t(nsteps));
+    }
+  }
+  pool_free(ctx, hist);
+  CMB_TRY(rc);
+  // steps are valid until a residue <= threshold appears (that step is still valid; the next one was refused)
   double* hs = K->h_stage;
-  CMB_CUDA(cudaMemcpyAsync(hs, K->h1, sizeof(double) * c * es, cudaMemcpyDeviceToHost, ctx->stream));
-  CMB_CUDA(cudaMemcpyAsync(hs + c * es, K->h2, sizeof(double) * c * es, cudaMemcpyDeviceToHost, ctx->stream));
-  CMB_CUDA(cudaMemcpyAsync(hs + 2 * c * es, K->scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
-  double* hout = static_cast<double*>(hcol);
-  for (int i = 0; i < (k + 1) * es; ++i) hout[i] = hs[K->ndefl * es + i] + hs[c * es + K->ndefl * es + i];
-  K->residue = sqrt(hs[2 * c * es]);
-  *residue = K->residue;
-  K->nk = k + 1;
-  add_step_bytes(K, op, c);
+  int64_t done = 0;
+  for (int64_t s = 0; s < nsteps; ++s) {
+    const double* slot = hs + size_t(s) * (2 * hstride + 1);
+    const int k = k0 + int(s);
+    double* hout = static_cast<double*>(hcols) + size_t(s) * ldh * es;
+    for (int i = 0; i < (k + 1) * es; ++i) hout[i] = slot[K->ndefl * es + i] + slot[hstride + K->ndefl * es + i];
+    residues[s] = sqrt(slot[2 * hstride]);
+    ++done;
+    if (residues[s] <= threshold) break;
+  }
+  if (halted) {
+    *status = CMB_STEP_BREAKDOWN;
+    CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int), ctx->stream));
+    if (done < nsteps) {
+      // the chain stopped on the device: w and ||w||^2 still describe the last valid step
+      CMB_CUDA(cudaMemcpyAsync(K->scal, hs + size_t(done - 1) * (2 * hstride + 1) + 2 * hstride, sizeof(double),
+                               cudaMemcpyHostToDevice, ctx->stream));
+      CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  K->residue = residues[done - 1];
+  K->nk = k0 + int(done);
+  *steps_done = done;
+  return CMB_OK;
+}
+
+int cmb_arnoldi_step(cmb_krylov* K, cmb_op* op, const void* shift, double threshold, void* hcol, double* residue,
+                     int* status) {
+  CMB_REQUIRE(K && hcol && residue && status, "null argument");
+  int64_t done = 0;
+  double res = K->residue;
+  CMB_TRY(cmb_arnoldi_run(K, op, shift, threshold, 1, hcol, K->nk + 2, &res, &done, status));
+  *residue = done ? res : K->residue;
   return CMB_OK;
 }
 

@@ -21,6 +21,7 @@
 #include <map>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "detail/hessenberg_eigen.hpp"
@@ -245,9 +246,14 @@ class ArnoldiBase {
   }
 
   /// one Arnoldi step (arnoldi.hpp:312-392)
-  bool updateArnoldiSteps() {
-    if (matrixHeight_ <= 0) return false;
-    if (!matrixMultiplication_ && !deviceOperator_) return false;
+  bool updateArnoldiSteps() { return updateArnoldiSteps(1) == 1; }
+
+  /// additive: up to `count` consecutive calls of updateArnoldiSteps() enqueued on the device with a single host
+  /// synchronisation at the end.  Returns how many of them returned true.
+  Index updateArnoldiSteps(Index count) {
+    if (matrixHeight_ <= 0) return 0;
+    if (!matrixMultiplication_ && !deviceOperator_) return 0;
+    if (count <= 0) return 0;
     dev_.prepare(deviceOperator_, matrixMultiplication_, matrixHeight_, reserveSize_);
     if (nvectors_ == 0) {
       // setInitialArnoldivector (arnoldi.hpp:245-269)
@@ -256,28 +262,36 @@ class ArnoldiBase {
       dev_.setDeflation(orthogonalizingVectors_, localHeight());
       int st = 0;
       detail::check(cmb_krylov_start(dev_.handle(), initialVector_.data(), threshold_, &st), "cmb_krylov_start");
-      if (st != CMB_STEP_OK) return false;
+      if (st != CMB_STEP_OK) return 0;
     } else if (arnoldiStepIsUtmost()) {
-      return false;
+      return 0;
     }
-    const Index k = nvectors_;
-    std::vector<Scalar> col(static_cast<std::size_t>(k) + 2, Scalar(0));
-    double res = 0.0;
+    const Index k0 = nvectors_;
+    if (count > matrixHeight_ - k0) count = matrixHeight_ - k0;
+    if (count <= 0) return 0;
+    const Index ldh = k0 + count + 2;
+    std::vector<Scalar> cols(static_cast<std::size_t>(ldh) * static_cast<std::size_t>(count), Scalar(0));
+    std::vector<double> res(static_cast<std::size_t>(count), 0.0);
+    std::int64_t done = 0;
     int status = 0;
-    int rc = cmb_arnoldi_step(dev_.handle(), dev_.op(), &eigenvalueShift_, threshold_, col.data(), &res, &status);
+    int rc = cmb_arnoldi_run(dev_.handle(), dev_.op(), &eigenvalueShift_, threshold_, count, cols.data(), ldh, res.data(),
+                             &done, &status);
     dev_.rethrowCallbackError();
-    detail::check(rc, "cmb_arnoldi_step");
-    if (status != CMB_STEP_OK) return false;
-    if (k > 0) {
-      h_[k - 1].resize(k + 1);
-      h_[k - 1][k] = Scalar(residue_);  // sub-diagonal entry of the previous column (arnoldi.hpp:362-363)
+    detail::check(rc, "cmb_arnoldi_run");
+    for (Index s = 0; s < static_cast<Index>(done); ++s) {
+      const Index k = k0 + s;
+      if (k > 0) {
+        h_[k - 1].resize(k + 1);
+        h_[k - 1][k] = Scalar(residue_);  // sub-diagonal entry of the previous column (arnoldi.hpp:362-363)
+      }
+      std::vector<Scalar> col(static_cast<std::size_t>(k) + 2, Scalar(0));
+      for (Index i = 0; i <= k; ++i) col[i] = cols[static_cast<std::size_t>(s) * ldh + i];
+      h_.push_back(col);
+      residue_ = res[static_cast<std::size_t>(s)];
+      nvectors_ = k + 1;
+      ++iterations_;
     }
-    col[k + 1] = Scalar(0.0);
-    h_.push_back(col);
-    residue_ = res;
-    nvectors_ = k + 1;
-    ++iterations_;
-    return true;
+    return static_cast<Index>(done);
   }
 
   /// dense copy of the basis, n x (number of Hessenberg columns) (arnoldi.hpp:398-409)
@@ -293,8 +307,10 @@ class ArnoldiBase {
   }
 
   /// Hessenberg matrix of the current step (arnoldi.hpp:415-432)
-  MatrixType makeHessenbergMatrix() const {
-    Index hsize = static_cast<Index>(h_.size());
+  MatrixType makeHessenbergMatrix() const { return makeHessenbergMatrix(static_cast<Index>(h_.size())); }
+  /// additive: the leading hsize x hsize block, i.e. the Hessenberg matrix as it was after hsize steps
+  MatrixType makeHessenbergMatrix(Index hsize) const {
+    if (hsize > static_cast<Index>(h_.size())) hsize = static_cast<Index>(h_.size());
     if (hsize > matrixHeight_) hsize = matrixHeight_;
     MatrixType hess = MatrixType::Zero(hsize, hsize);
     for (Index c = 0, nc = hess.cols(); c < nc; ++c) {
@@ -561,8 +577,19 @@ class ArnoldiEigenSolver {
           }
         }
       }
-      arnoldiBase_.updateArnoldiSteps();
+      // steps no stop rule can interrupt (iterations < minIterations) go to the device as one batch; their
+      // per-trip bookkeeping is replayed afterwards from the Hessenberg columns (same values, same logs)
+      Index batch = 1;
+      if (arnoldiBase_.iterations() < minIterations()) {
+        batch = minIterations() - arnoldiBase_.iterations();
+        const Index room = matrixHeight() - arnoldiBase_.arnoldivectorsSize();
+        if (batch > room) batch = room;
+        if (batch < 1) batch = 1;
+      }
+      const Index before = arnoldiBase_.arnoldivectorsSize();
+      const Index done = arnoldiBase_.updateArnoldiSteps(batch);
       if (arnoldiBase_.arnoldivectorsSize() == 0) set_initialvector_is_fail = true;
+      replayTrips_(before, done);
       solveHessenberg_(false);
     }
     // eigenvectors of H are needed once, at exit (the reference recomputes them every trip)
@@ -607,6 +634,46 @@ class ArnoldiEigenSolver {
   struct FromComplex<std::complex<R>, Dummy> {
     static std::complex<R> get(const ComplexScalar& z) { return z; }
   };
+
+  /// Convergence-log entries of the states with before+1 .. before+done-1 Arnoldi vectors (the trips a batched
+  /// updateArnoldiSteps(done) skipped): eigenvalues of the leading Hessenberg blocks, sorted by descending |lambda|,
+  /// computed on a few host threads and appended in trip order.
+  void replayTrips_(Index before, Index done) {
+    const Index ntrips = done - 1;
+    if (ntrips <= 0) return;
+    std::vector<std::vector<ComplexScalar>> ritz(static_cast<std::size_t>(ntrips));
+    auto work = [&](Index t) {
+      const MatrixType h = arnoldiBase_.makeHessenbergMatrix(before + 1 + t);
+      HessenbergEigenSolver<Scalar> solver;
+      solver.compute(h, false);
+      std::vector<ComplexScalar>& ev = ritz[static_cast<std::size_t>(t)];
+      ev.resize(static_cast<std::size_t>(solver.eigenvalues().size()));
+      for (std::size_t i = 0; i < ev.size(); ++i) ev[i] = solver.eigenvalues()[static_cast<Index>(i)];
+      std::stable_sort(ev.begin(), ev.end(),
+                       [](const ComplexScalar& a, const ComplexScalar& b) { return std::abs(a) > std::abs(b); });
+    };
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads > 8) nthreads = 8;
+    if (nthreads < 1 || ntrips < 4) nthreads = 1;
+    if (nthreads == 1) {
+      for (Index t = 0; t < ntrips; ++t) work(t);
+    } else {
+      std::vector<std::thread> pool;
+      for (unsigned w = 0; w < nthreads; ++w)
+        pool.emplace_back([&, w]() {
+          for (Index t = static_cast<Index>(w); t < ntrips; t += static_cast<Index>(nthreads)) work(t);
+        });
+      for (auto& th : pool) th.join();
+    }
+    for (Index t = 0; t < ntrips; ++t) {
+      const std::vector<ComplexScalar>& ev = ritz[static_cast<std::size_t>(t)];
+      for (auto& indexForConvergence : indicesForConvergence_) {
+        Index i = getFormalIndex(indexForConvergence, static_cast<Index>(ev.size()));
+        if (i < 0) continue;
+        convergenceLog_[indexForConvergence].push_back(ev[static_cast<std::size_t>(i)]);
+      }
+    }
+  }
 
   /// Hessenberg eigenproblem of the current step, sorted by descending |lambda| (arnoldi.hpp:805-822)
   void solveHessenberg_(bool vectors) {

@@ -152,6 +152,12 @@ int cmb_lanczos_residual_norm(cmb_krylov* k, double* out);
 int cmb_arnoldi_step(cmb_krylov* k, cmb_op* op, const void* shift, double threshold, void* hcol,
                      double* residue, int* status);
 
+/* up to nsteps Arnoldi steps enqueued without host synchronisation in between (the device stops the chain when a
+ * residue <= threshold appears).  Column j of hcols (leading dimension ldh, dtype elements) receives
+ * h(0..k_j, k_j) of the j-th new column, residues[j] its residual norm. */
+int cmb_arnoldi_run(cmb_krylov* k, cmb_op* op, const void* shift, double threshold, int64_t nsteps, void* hcols,
+                    int64_t ldh, double* residues, int64_t* steps_done, int* status);
+
 /* Ritz-vector assembly (lanczos.hpp:797-817, arnoldi.hpp:841-865): X(:,e) = sum_m coef(m,e) * basis_m,
  * normalised, multiplied by the conjugate phase of its first non-zero element.  coef is column-major
  * ncoef x nev with leading dimension ldc, of coef_dtype; X is written to host memory (local slab,
