@@ -93,6 +93,8 @@ def _declare(L):
         "cmb_arnoldi_step": (i32, [vp, vp, vp, dbl, vp, P(dbl), P(i32)]),
         "cmb_krylov_ritz_vectors": (i32, [vp, i32, vp, i64, i64, i64, vp, i64]),
         "cmb_krylov_bytes": (dbl, [vp]),
+        "cmb_krylov_project": (i32, [vp, vp, vp]),
+        "cmb_krylov_combine": (i32, [vp, vp, i64, vp]),
         "cmb_debug_cgs_pass": (i32, [vp, i32, i32, i32, P(dbl)]),
         # solver binding
         "cmbs_create": (i32, [i32, i32, P(vp)]),
@@ -123,6 +125,8 @@ def _declare(L):
         "cmbs_get_log_line": (i32, [vp, i64, C.c_char_p, i64]),
         "cmbs_get_convergence_log": (i32, [vp, i64, vp, P(i64)]),
         "cmbs_device_bytes": (dbl, [vp]),
+        "cmbs_exp_solve_with_lanczos": (i32, [vp, dbl, dbl, vp]),
+        "cmbs_exp_solve_with_taylor": (i32, [vp, dbl, dbl, dbl, i32, vp, vp]),
         "cmbs_host_tridiagonal_eigen": (i32, [i64, vp, vp, vp, vp]),
         "cmbs_host_hessenberg_eigen": (i32, [i64, vp, vp, vp]),
         "cmb_host_alloc": (i32, [C.c_size_t, P(vp)]),

@@ -766,6 +766,57 @@ __global__ void add2_kernel(const double* a, const double* b, double* out) { out
 
 extern "C" {
 
+// g = V^H x over the Krylov vectors (x: local host slab) — the projection LanczosExponentialSolver needs
+// (lanczos.hpp:1047: inner = y_n^H in, with y_n = V S(:,n)).
+int cmb_krylov_project(cmb_krylov* K, const void* x_host, void* g_host) {
+  CMB_REQUIRE(K && x_host && g_host, "null argument");
+  CMB_REQUIRE(K->nk >= 1, "empty basis");
+  cmb_ctx* ctx = K->ctx;
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  CMB_TRY(ensure_tmp(K, &K->tmp1, K->ld));
+  CMB_CUDA(cudaMemcpyAsync(K->tmp1, x_host, sizeof(double) * K->nd_local, cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<Chunk> chunks;
+  contiguous_chunks(K, K->ndefl, K->ndefl + K->nk, chunks);
+  CgsPass p;
+  p.ld = K->ld;
+  p.halt = K->halt;
+  p.x = K->tmp1;
+  p.family = "project";
+  int off = 0;
+  for (auto& c : chunks) {
+    p.V = c.V;
+    p.ncols = c.ncols;
+    p.col_stride = c.col_stride;
+    p.hout = K->h1 + off * K->es;
+    CMB_TRY(cgs_pass(ctx, K->cplx, CGS_DOT, p));
+    off += c.ncols;
+  }
+  CMB_TRY(allreduce_sum_f64(ctx, K->h1, size_t(K->nk) * K->es));
+  CMB_CUDA(cudaMemcpyAsync(g_host, K->h1, sizeof(double) * K->nk * K->es, cudaMemcpyDeviceToHost, ctx->stream));
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CMB_OK;
+}
+
+// out = sum_m coef_m * u_m over the first ncoef Krylov vectors (no normalisation, no phase): the tall-skinny
+// GEMV that turns a small vector of the Krylov space into a length-n vector.
+int cmb_krylov_combine(cmb_krylov* K, const void* coef, int64_t ncoef, void* out_host) {
+  CMB_REQUIRE(K && coef && out_host, "null argument");
+  CMB_REQUIRE(ncoef >= 1 && ncoef <= K->nk, "bad coefficient count");
+  cmb_ctx* ctx = K->ctx;
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  CMB_TRY(ensure_tmp(K, &K->tmp1, K->ld));
+  CMB_TRY(ensure_stage(K, size_t(2 * ncoef + 8)));
+  const double* cf = static_cast<const double*>(coef);
+  for (int64_t m = 0; m < ncoef * K->es; ++m) K->h_stage[m] = -cf[m];  // y = 0 - V (-coef)
+  CMB_CUDA(cudaMemcpyAsync(K->h1, K->h_stage, sizeof(double) * ncoef * K->es, cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<Chunk> chunks;
+  contiguous_chunks(K, K->ndefl, K->ndefl + int(ncoef), chunks);
+  CMB_TRY(subtract_cols(K, chunks, K->h1, nullptr, K->tmp1, K->scal + 1, "combine"));
+  CMB_CUDA(cudaMemcpyAsync(out_host, K->tmp1, sizeof(double) * K->nd_local, cudaMemcpyDeviceToHost, ctx->stream));
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CMB_OK;
+}
+
 int cmb_krylov_ritz_vectors(cmb_krylov* K, cmb_dtype coef_dtype, const void* coef, int64_t ldc, int64_t ncoef,
                             int64_t nev, void* x_host, int64_t ldx) {
   CMB_REQUIRE(K && (nev == 0 || (coef && x_host)), "null argument");

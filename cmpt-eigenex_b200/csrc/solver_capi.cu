@@ -43,6 +43,8 @@ struct cmbs_solver {
   virtual const std::vector<std::string>& log() = 0;
   virtual void conv_log(int64_t index, void* out, int64_t* n) = 0;
   virtual double bytes() = 0;
+  virtual bool exp_lanczos(double, double, void*) { return false; }
+  virtual bool exp_taylor(double, double, double, int, const void*, void*) { return false; }
 };
 
 namespace {
@@ -181,6 +183,26 @@ struct LanczosS : Common<LanczosEigenSolver<Scalar>> {
     if (out) std::copy(it->second.begin(), it->second.end(), static_cast<double*>(out));
   }
   double bytes() override { return es.lanczosBase().deviceBytes(); }
+  static Scalar mkx(double re, double, double*) { return re; }
+  static Scalar mkx(double re, double im, std::complex<double>*) { return std::complex<double>(re, im); }
+  bool exp_lanczos(double re, double im, void* out) override {
+    typename LanczosEigenSolver<Scalar>::VectorType o;
+    LanczosExponentialSolver<Scalar>::solveWithLanczos(mkx(re, im, static_cast<Scalar*>(nullptr)), es, o);
+    memcpy(out, o.data(), sizeof(Scalar) * size_t(o.size()));
+    return true;
+  }
+  bool exp_taylor(double re, double im, double radius, int autodiv, const void* in, void* out) override {
+    using V = typename LanczosEigenSolver<Scalar>::VectorType;
+    const Index n = es.matrixHeight();
+    V vin(static_cast<const Scalar*>(in), n), o;
+    const Scalar x = mkx(re, im, static_cast<Scalar*>(nullptr));
+    if (autodiv)
+      LanczosExponentialSolver<Scalar>::solveWithTaylorAutoDivision(x, es.matrixMultiplication(), n, radius, vin, o);
+    else
+      LanczosExponentialSolver<Scalar>::solveWithTaylorNoDivision(x, es.matrixMultiplication(), n, radius, vin, o);
+    memcpy(out, o.data(), sizeof(Scalar) * size_t(n));
+    return true;
+  }
 };
 
 template <class Scalar>
@@ -490,6 +512,22 @@ double cmbs_device_bytes(cmbs_solver* s) {
       return CMB_OK;
     });
   return b;
+}
+
+int cmbs_exp_solve_with_lanczos(cmbs_solver* s, double x_re, double x_im, void* out) {
+  S_REQ(s && out, "null argument");
+  return guarded([&]() -> int {
+    S_REQ(s->exp_lanczos(x_re, x_im, out), "exp(xA)v is a Lanczos feature");
+    return CMB_OK;
+  });
+}
+int cmbs_exp_solve_with_taylor(cmbs_solver* s, double x_re, double x_im, double matrix_radius, int auto_division,
+                               const void* in, void* out) {
+  S_REQ(s && in && out, "null argument");
+  return guarded([&]() -> int {
+    S_REQ(s->exp_taylor(x_re, x_im, matrix_radius, auto_division, in, out), "exp(xA)v is a Lanczos feature");
+    return CMB_OK;
+  });
 }
 
 int cmbs_host_tridiagonal_eigen(int64_t n, const double* alpha, const double* beta, double* w, double* z) {

@@ -380,6 +380,22 @@ class LanczosEigenSolver(_Solver):
             check(lib().cmbs_get_convergence_log(self.h, index, ptr(out), C.byref(n)))
         return out
 
+    # LanczosExponentialSolver (lanczos.hpp:1002-1164)
+    def expSolveWithLanczos(self, x):
+        """compute(), then exp(x A) applied to the solver's initial vector (local slab)."""
+        out = np.empty(self._geti("localHeight"), dtype=self.dtype)
+        x = complex(x)
+        check(lib().cmbs_exp_solve_with_lanczos(self.h, x.real, x.imag, ptr(out)))
+        return out
+
+    def expSolveWithTaylor(self, x, radius, vin, auto_division=True):
+        vin = np.ascontiguousarray(vin, dtype=self.dtype)
+        out = np.empty_like(vin)
+        x = complex(x)
+        check(lib().cmbs_exp_solve_with_taylor(self.h, x.real, x.imag, float(radius), int(bool(auto_division)),
+                                               ptr(vin), ptr(out)))
+        return out
+
 
 class ArnoldiEigenSolver(_Solver):
     """cmpt::EigenEx::ArnoldiEigenSolver<Scalar> (arnoldi.hpp:444-1027) on the GPU."""

@@ -730,6 +730,116 @@ class LanczosEigenSolver {
   }
 };
 
+/// exp(xA)|ket> with the Lanczos method or a Taylor expansion (lanczos.hpp:1002-1164), A Hermitian.
+/// solveWithEigens / solveWithTaylor* are host routines with the reference's signatures; solveWithLanczos runs
+/// the Krylov part on the device and evaluates the expansion there too (see below).
+template <typename Scalar_>
+class LanczosExponentialSolver {
+ public:
+  using Index = EigenEx::Index;
+  using Solver = LanczosEigenSolver<Scalar_>;
+  using Scalar = typename Solver::Scalar;
+  using RealScalar = typename Solver::RealScalar;
+  using VectorType = typename Solver::VectorType;
+  using RealVectorType = typename Solver::RealVectorType;
+  using MatrixType = typename Solver::MatrixType;
+  using RealMatrixType = typename Solver::RealMatrixType;
+  using MatMulFunction = typename Solver::MatMulFunction;
+
+  static constexpr Index unlimited = Solver::unlimited;
+
+  /// out = sum_n exp(x E_n) <y_n|in> y_n over the first max_expand eigenpairs, smallest weight first
+  /// (lanczos.hpp:1024-1054)
+  static void solveWithEigens(const Scalar x, const RealVectorType& eivals, const MatrixType& eivecs, Index max_expand,
+                              const VectorType& in, VectorType& out) {
+    Index max = max_expand;
+    if (static_cast<Index>(eivals.size()) - max_expand < 0) max = eivals.size();
+    if (static_cast<Index>(eivecs.cols()) - max_expand < 0) max = eivecs.cols();
+    const Index n = in.size();
+    out.resize(n);
+    for (Index i = 0; i < n; ++i) out[i] = Scalar(0);
+    for (Index n_ = 0; n_ < max; ++n_) {
+      Index k = n_;
+      if (std::real(x) < 0.0) k = max - n_ - 1;
+      Scalar inner = Scalar(0);
+      for (Index i = 0; i < n; ++i) inner += detail::conj_(eivecs(i, k)) * in[i];
+      const Scalar c = std::exp(x * eivals[k]) * inner;
+      for (Index i = 0; i < n; ++i) out[i] += c * eivecs(i, k);
+    }
+  }
+
+  /// es.compute(), then the eigen-expansion with es.initialVector() as the input vector (lanczos.hpp:1061-1075).
+  /// The expansion is evaluated in the Krylov space on the device: g = V^H in (one pass over the basis),
+  /// c = S_nev exp(x Theta) S_nev^H g on the host (nev = number of Ritz pairs the solver returned), out = V c (one
+  /// more pass) — the same sum as solveWithEigens(x, es.eigenvalues(), es.eigenvectors(), ...), without needing the
+  /// n x nev Ritz-vector matrix.  As in the reference, nothing is added when the solver returned no eigenvectors.
+  static void solveWithLanczos(const Scalar& x, Solver& es, VectorType& out) {
+    es.compute();
+    const Index n = es.localHeight();
+    const Index nev = std::min<Index>(es.eigenvalues().size(), es.eigenvectors().cols());
+    const Index nk = es.lanczosBase().lanczosvectorsSize();
+    out.resize(n);
+    for (Index i = 0; i < n; ++i) out[i] = Scalar(0);
+    if (nev <= 0 || nk <= 0) return;
+    std::vector<Scalar> g(static_cast<std::size_t>(nk));
+    detail::check(cmb_krylov_project(es.lanczosBase().deviceState(), es.initialVector().data(), g.data()),
+                  "cmb_krylov_project");
+    const auto& S = es.es_tri().eigenvectors();  // nk x nk, columns = eigenvectors of T (real entries)
+    std::vector<Scalar> c(static_cast<std::size_t>(nk), Scalar(0));
+    for (Index k_ = 0; k_ < nev; ++k_) {
+      Index k = k_;
+      if (std::real(x) < 0.0) k = nev - k_ - 1;  // smallest weight first, as the reference
+      Scalar inner = Scalar(0);
+      for (Index m = 0; m < nk; ++m) inner += detail::conj_(S(m, k)) * g[static_cast<std::size_t>(m)];
+      const Scalar w = std::exp(x * es.eigenvalues()[k]) * inner;
+      for (Index m = 0; m < nk; ++m) c[static_cast<std::size_t>(m)] += w * S(m, k);
+    }
+    detail::check(cmb_krylov_combine(es.lanczosBase().deviceState(), c.data(), nk, out.data()), "cmb_krylov_combine");
+  }
+
+  /// plain Taylor expansion (lanczos.hpp:1085-1130)
+  static void solveWithTaylorNoDivision(Scalar x, const MatMulFunction& matmul, Index matrix_height,
+                                        RealScalar matrix_radius, const VectorType& in, VectorType& out,
+                                        RealScalar error = 1.0e-14, Index max_expansion = unlimited) {
+    out = in;  // k == 0
+    Scalar c_k = Scalar(1.0);
+    RealScalar radius_k = RealScalar(1.0);
+    Index k = 1;
+    VectorType ket_k(matrix_height), ket_pre(matrix_height);
+    c_k *= x / static_cast<double>(k);
+    radius_k *= matrix_radius;
+    matmul(in.data(), ket_k.data());
+    for (Index i = 0; i < matrix_height; ++i) out[i] += c_k * ket_k[i];
+    if (max_expansion == 1) return;
+    std::swap(ket_pre, ket_k);
+    for (k = 2; k != max_expansion; ++k) {
+      c_k *= x / static_cast<double>(k);
+      radius_k *= matrix_radius;
+      matmul(ket_pre.data(), ket_k.data());
+      for (Index i = 0; i < matrix_height; ++i) out[i] += c_k * ket_k[i];
+      std::swap(ket_k, ket_pre);
+      if (std::abs(c_k * radius_k) < error) break;
+    }
+  }
+
+  /// Taylor expansion with the step split into div = floor(|x| radius + 1) sub-steps (lanczos.hpp:1138-1161).
+  /// The reference applies every sub-step to `in` (so it returns exp(xA/div) in); the sub-steps are chained here,
+  /// which is what the function documents: out = exp(xA) in.
+  static void solveWithTaylorAutoDivision(Scalar x, const MatMulFunction& matmul, Index matrix_height,
+                                          RealScalar matrix_radius, const VectorType& in, VectorType& out,
+                                          RealScalar error = 1.0e-14, Index max_expansion = unlimited) {
+    const RealScalar rad = std::abs(x * matrix_radius);
+    const Index div = static_cast<Index>(rad + 1.0);
+    VectorType cur = in, next;
+    for (Index i = 0; i < div; ++i) {
+      const Scalar x_ = static_cast<RealScalar>(1.0 / div) * x;
+      solveWithTaylorNoDivision(x_, matmul, matrix_height, matrix_radius, cur, next, error, max_expansion);
+      std::swap(cur, next);
+    }
+    out = cur;
+  }
+};
+
 }  // namespace EigenEx
 }  // namespace cmpt
 

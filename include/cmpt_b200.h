@@ -169,6 +169,13 @@ int cmb_krylov_ritz_vectors(cmb_krylov* k, cmb_dtype coef_dtype, const void* coe
  * ncols columns of the basis, `reps` back-to-back launches timed with CUDA events */
 int cmb_debug_cgs_pass(cmb_krylov* k, int mode, int ncols, int reps, double* ms_per_launch);
 
+/* g = V^H x over the Krylov vectors (x: local host slab; g: ncols dtype elements) and out = sum_m coef_m u_m over the
+ * first ncoef Krylov vectors (plain combination: no normalisation, no phase).  Together they evaluate functions of
+ * the operator in the Krylov space, e.g. LanczosExponentialSolver::solveWithLanczos (lanczos.hpp:1061-1075), with
+ * two passes over the basis instead of one host axpy per (Ritz vector, basis vector) pair. */
+int cmb_krylov_project(cmb_krylov* k, const void* x_host, void* g_host);
+int cmb_krylov_combine(cmb_krylov* k, const void* coef, int64_t ncoef, void* out_host);
+
 /* algorithmic bytes moved by the Krylov steps so far: sum of B_op + (3c+7) n s */
 double cmb_krylov_bytes(const cmb_krylov* k);
 

@@ -68,6 +68,13 @@ int cmbs_get_log_line(cmbs_solver* s, int64_t i, char* buf, int64_t buflen);
 int cmbs_get_convergence_log(cmbs_solver* s, int64_t index, void* out, int64_t* n);
 double cmbs_device_bytes(cmbs_solver* s);
 
+/* LanczosExponentialSolver (lanczos.hpp:1002-1164), Lanczos solvers only: out = exp(x A) v.
+ * solve_with_lanczos: es.compute() then the eigen-expansion with the solver's initial vector (local slab out);
+ * solve_with_taylor: Taylor expansion through the solver's matrixMultiplication() (auto_division != 0 splits x). */
+int cmbs_exp_solve_with_lanczos(cmbs_solver* s, double x_re, double x_im, void* out);
+int cmbs_exp_solve_with_taylor(cmbs_solver* s, double x_re, double x_im, double matrix_radius, int auto_division,
+                               const void* in, void* out);
+
 /* host-side Ritz solvers, exposed for testing against LAPACK (no GPU needed) */
 int cmbs_host_tridiagonal_eigen(int64_t n, const double* alpha, const double* beta, double* w, double* z /*nullable*/);
 int cmbs_host_hessenberg_eigen(int64_t n, const void* h_complex, void* w_complex, void* v_complex /*nullable*/);

@@ -207,6 +207,24 @@ class LanczosEigenSolver:
         return sum(1 for s in self.log if s.startswith(HEAD_ERROR))
 
 
+def exp_solve_with_eigens(x, eivals, eivecs, max_expand, vin):
+    """LanczosExponentialSolver::solveWithEigens (lanczos.hpp:1024-1054): sum of exp(x E_n) <y_n|in> y_n over the
+    first max_expand pairs, smallest weight first."""
+    mx = min(max_expand, len(eivals), eivecs.shape[1])
+    out = np.zeros(len(vin), dtype=np.result_type(eivecs.dtype, np.asarray(vin).dtype, type(x)))
+    for n_ in range(mx):
+        n = mx - n_ - 1 if np.real(x) < 0.0 else n_
+        inner = np.vdot(eivecs[:, n], vin)
+        out = out + np.exp(x * eivals[n]) * inner * eivecs[:, n]
+    return out
+
+
+def exp_solve_with_lanczos(x, es):
+    """LanczosExponentialSolver::solveWithLanczos (lanczos.hpp:1061-1075)."""
+    es.compute()
+    return exp_solve_with_eigens(x, es.eigenvalues, es.eigenvectors, len(es.eigenvalues), es.init)
+
+
 class ArnoldiEigenSolver:
     unlimited = UNLIMITED
 

@@ -572,3 +572,49 @@ def test_heisenberg_partitioned_virtual_ranks(ctx, L, nranks, pbc, dtype):
                                                        capi.ptr(x), capi.ptr(y)))
     yo = core.Operator.heisenberg(L, 1.0, pbc, prefix="z" if dtype == np.complex128 else "d").apply(x)
     np.testing.assert_allclose(y, yo, atol=1e-14)
+
+
+# ------------------------------------------------------------------------------------------------
+# LanczosExponentialSolver (lanczos.hpp:1002-1164)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,x", [(np.float64, -0.7), (np.float64, 0.3), (np.complex128, -0.4j), (np.complex128, -0.2 + 0.5j)])
+def test_exponential_solver_matches_oracle_and_expm(ctx, dtype, x):
+    import scipy.linalg as sla
+
+    N = 9
+    n = N * N
+    rp, c, v = syn.laplacian2d_csr(N)
+    if dtype == np.complex128:
+        rp, c, v = syn.hermitian_chain_csr(n)
+    A = _csr_dense(rp, c, v, n)
+    x0 = 0.37 * syn.start_vector(n, seed=7, dtype=dtype)  # not normalised: the expansion uses the raw initial vector
+    es = pkg.LanczosEigenSolver(dtype)
+    es.setMatrixMultiplication(pkg.DeviceOperator.from_csr(ctx, rp, c, v)).setInitialVector(x0)
+    es.setMinIterations(30).setMaxIterations(30)
+    out = es.expSolveWithLanczos(x)
+    ref = rs.LanczosEigenSolver("z" if dtype == np.complex128 else "d")
+    ref.set_matrix_multiplication(core.Operator.csr(rp, c, v))
+    ref.init = x0
+    ref.min_iterations = ref.max_iterations = 30
+    want = rs.exp_solve_with_lanczos(x if dtype == np.complex128 else float(np.real(x)), ref)
+    np.testing.assert_allclose(out, want, atol=1e-11)
+    # truncated expansion (maxEigenvalues) follows the reference too
+    es.setMaxEigenvalues(4)
+    ref.max_eigenvalues = 4
+    np.testing.assert_allclose(es.expSolveWithLanczos(x), rs.exp_solve_with_lanczos(
+        x if dtype == np.complex128 else float(np.real(x)), ref), atol=1e-11)
+    # no eigenvectors -> nothing is summed (lanczos.hpp:1037-1039)
+    es.setComputeEigenvectorsOn(False)
+    assert np.all(es.expSolveWithLanczos(x) == 0)
+    # full Krylov space: the expansion is exp(xA) v exactly
+    es2 = pkg.LanczosEigenSolver(dtype)
+    es2.setMatrixMultiplication(pkg.DeviceOperator.from_csr(ctx, rp, c, v)).setInitialVector(x0)
+    es2.setMinIterations(n).setMaxIterations(n).setThreshold(1e-13)
+    full = es2.expSolveWithLanczos(x)
+    np.testing.assert_allclose(full, sla.expm(x * A) @ x0, atol=1e-9)
+    # Taylor variants through the device operator's host interface
+    radius = np.abs(np.linalg.eigvalsh(A)).max()
+    t1 = es2.expSolveWithTaylor(x, radius, x0, auto_division=True)
+    np.testing.assert_allclose(t1, sla.expm(x * A) @ x0, atol=1e-10)
+    t2 = es2.expSolveWithTaylor(x * 0.1, radius, x0, auto_division=False)
+    np.testing.assert_allclose(t2, sla.expm(0.1 * x * A) @ x0, atol=1e-10)
