@@ -69,3 +69,16 @@ def test_sample_device_csr_and_continue():
     exact = float(re.search(r"exact lowest eigenvalue (\S+)\)", out).group(1))
     assert abs(low - exact) < 1e-5 and low >= exact - 1e-12
     assert "log: INFO      EigenSolver<ScalarType>::continueToCompute(...) was called" in out
+
+
+@pytest.mark.gpu
+def test_sample_triplets_on_ramp():
+    # COO container -> shrink -> Gershgorin range -> callback and device operator
+    out = _run("sample_triplets")
+    m = re.search(r"triplets (\d+) -> (\d+), gershgorin range \[(\S+), (\S+)\]", out)
+    assert int(m.group(1)) == 300 * 3 + 2 * 299 and int(m.group(2)) == 300 + 2 * 299
+    assert abs(float(m.group(3)) - 0.0) < 1e-12 and abs(float(m.group(4)) - 4.0) < 1e-12
+    assert float(re.search(r"max \|callback - device\| = (\S+)", out).group(1)) < 1e-11
+    low = float(re.search(r"device  : (\S+)", out).group(1))
+    exact = float(re.search(r"exact lowest: (\S+)", out).group(1))
+    assert abs(low - exact) < 1e-9
