@@ -84,6 +84,46 @@ spmv_sell_kernel(const long long* __restrict__ slice_ptr, const int* __restrict_
   grid_sum_finalize<CPLX ? 2 : 1>(d0, d1, partial, ticket, sc.alpha_slot);
 }
 
+// Uniform-width variant (every slice has exactly W columns: stencils such as the 5-point Laplacian or the 7-point
+// convection-diffusion operator).  W is a compile-time constant, so all W index loads, W value loads and then all W
+// gathers of a row are issued back to back (one dependent phase instead of a runtime loop) and no slice pointer is
+// read.  Real scalars only; everything else goes through the generic kernel.
+template <int W>
+__global__ void __launch_bounds__(256)
+spmv_sell_uniform_kernel(const int* __restrict__ col, const double* __restrict__ val, long long nrows, long long nslices,
+                         const double* __restrict__ w, const double* __restrict__ halo, double* __restrict__ ucol,
+                         double* __restrict__ v, double shr, StepScalars sc, double* partial, unsigned* ticket) {
+  double inv;
+  if (!step_prologue(sc, inv)) return;
+  const int lane = threadIdx.x & 31;
+  const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  double d0 = 0.0;
+  for (long long slice = gwarp; slice < nslices; slice += nwarps) {
+    const long long base = slice * (W * 32) + lane;
+    const long long r = slice * 32 + lane;
+    int c[W];
+    double a[W], xv[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) c[k] = __ldg(col + base + k * 32);
+#pragma unroll
+    for (int k = 0; k < W; ++k) a[k] = __ldg(val + base + k * 32);
+#pragma unroll
+    for (int k = 0; k < W; ++k) xv[k] = (c[k] < nrows) ? w[c[k]] : halo[c[k] - nrows];
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < W; ++k) acc = fma(a[k], xv[k], acc);
+    if (r < nrows) {
+      const double ui = w[r] * inv;
+      const double y = acc * inv + shr * ui;
+      ucol[r] = ui;
+      v[r] = y;
+      d0 = fma(ui, y, d0);
+    }
+  }
+  grid_sum_finalize<1>(d0, 0.0, partial, ticket, sc.alpha_slot);
+}
+
 __global__ void sell_width_kernel(const long long* __restrict__ rowptr, long long nrows, long long nslices,
                                   int* __restrict__ width) {
   const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -135,6 +175,7 @@ struct SellOp : cmb_op {
   double* d_val = nullptr;
   HaloExchange* halo = nullptr;  // row-partitioned shards only
   long long padded_nnz = 0, nnz = 0;
+  int uniform_width = 0;  // > 0: every slice has this width (fast path for real scalars)
   ~SellOp() override {
     pool_free(ctx, d_slice_ptr);
     pool_free(ctx, d_col);
@@ -152,6 +193,28 @@ struct SellOp : cmb_op {
     int grid = int(std::min<long long>(blocks, (long long)ctx->num_sms * 8));
     if (grid < 1) grid = 1;
     LaunchScope ls(ctx, "spmv_sell");
+#define CMB_SELL_UNIFORM(W)                                                                                        \
+  case W:                                                                                                          \
+    spmv_sell_uniform_kernel<W><<<grid, 256, 0, ctx->stream>>>(d_col, d_val, n_local, nslices, w, d_halo, ucol, v, \
+                                                               shr, sc, ctx->d_partial, ctx->d_ticket + 1);        \
+    CMB_CUDA(cudaGetLastError());                                                                                  \
+    return CMB_OK;
+    if (!cplx && shi == 0.0) {
+      switch (uniform_width) {
+        CMB_SELL_UNIFORM(1)
+        CMB_SELL_UNIFORM(2)
+        CMB_SELL_UNIFORM(3)
+        CMB_SELL_UNIFORM(4)
+        CMB_SELL_UNIFORM(5)
+        CMB_SELL_UNIFORM(6)
+        CMB_SELL_UNIFORM(7)
+        CMB_SELL_UNIFORM(8)
+        CMB_SELL_UNIFORM(9)
+        default:
+          break;
+      }
+    }
+#undef CMB_SELL_UNIFORM
     if (cplx)
       spmv_sell_kernel<true><<<grid, 256, 0, ctx->stream>>>(d_slice_ptr, d_col, d_val, n_local, nslices, w, d_halo,
                                                             ucol, v, shr, shi, sc, ctx->d_partial, ctx->d_ticket + 1);
@@ -199,10 +262,22 @@ static int build_sell(SellOp* op, const int64_t* rowptr, const int32_t* col, con
     std::vector<int> width(op->nslices);
     CMB_CUDA(cudaMemcpyAsync(width.data(), d_width, sizeof(int) * op->nslices, cudaMemcpyDeviceToHost, ctx->stream));
     CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // stencil-like matrices: pad every slice to the maximum width when that costs < 5 % extra entries, which
+    // enables the fully unrolled uniform-width kernel
+    int maxw = 0;
+    for (long long s = 0; s < op->nslices; ++s) maxw = std::max(maxw, width[s]);
+    if (maxw >= 1 && maxw <= 9 && double(maxw) * 32.0 * double(op->nslices) <= 1.05 * double(std::max<long long>(nnz, 1)))
+      for (long long s = 0; s < op->nslices; ++s) width[s] = maxw;
     std::vector<long long> sp(op->nslices + 1);
     sp[0] = 0;
     for (long long s = 0; s < op->nslices; ++s) sp[s + 1] = sp[s] + (long long)width[s] * 32;
     op->padded_nnz = sp[op->nslices];
+    op->uniform_width = (op->nslices > 0) ? width[0] : 0;
+    for (long long s = 0; s < op->nslices; ++s)
+      if (width[s] != op->uniform_width) {
+        op->uniform_width = 0;
+        break;
+      }
     CMB_TRY(pool_alloc(ctx, &op->d_slice_ptr, sizeof(long long) * (op->nslices + 1)));
     CMB_TRY(pool_alloc(ctx, &op->d_col, sizeof(int) * std::max<long long>(op->padded_nnz, 1)));
     CMB_TRY(pool_alloc(ctx, &op->d_val, sizeof(double) * es * std::max<long long>(op->padded_nnz, 1)));
