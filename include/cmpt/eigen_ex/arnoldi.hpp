@@ -380,6 +380,7 @@ class ArnoldiEigenSolver {
   }
   const std::vector<Index>& indicesForConvergence() const { return indicesForConvergence_; }
   ArnoldiEigenSolver& setIndicesForConvergence(const std::vector<Index>& iCovs) {
+    resolvePending_();  // pending log entries belong to the old index set
     indicesForConvergence_ = iCovs;
     return *this;
   }
@@ -466,7 +467,14 @@ class ArnoldiEigenSolver {
   std::vector<std::string> log_;
   MatrixType hessenbergMatrix_;
   DenseEigenSolver des_;
-  std::map<Index, std::vector<ComplexScalar>> convergenceLog_;
+  mutable std::map<Index, std::vector<ComplexScalar>> convergenceLog_;
+  // trips skipped by batched stepping whose convergence-log entries have not been computed yet (resolved on the
+  // first access to the log): {first state, number of calls, insert position per tracked index}
+  struct PendingReplay {
+    Index before, done;
+    std::map<Index, std::size_t> pos;
+  };
+  mutable std::vector<PendingReplay> pendingReplay_;
 
  public:
   const ComplexVectorType& eigenvalues() const { return eigenvalues_; }
@@ -475,7 +483,10 @@ class ArnoldiEigenSolver {
   const std::vector<std::string>& log() const { return log_; }
   const MatrixType& hessenbergMatrix() const { return hessenbergMatrix_; }
   const DenseEigenSolver& des() const { return des_; }
-  const std::map<Index, std::vector<ComplexScalar>>& convergenceLog() const { return convergenceLog_; }
+  const std::map<Index, std::vector<ComplexScalar>>& convergenceLog() const {
+    resolvePending_();
+    return convergenceLog_;
+  }
 
   /// additive: Ritz residual bounds residue * |Y(last, i)| of the returned eigenpairs
   RealVectorType ritzResiduals() const {
@@ -506,6 +517,7 @@ class ArnoldiEigenSolver {
     eigenvectors_.resize(0, 0);
     log_.clear();
     convergenceLog_.clear();
+    pendingReplay_.clear();
     return *this;
   }
 
@@ -589,7 +601,7 @@ class ArnoldiEigenSolver {
       const Index before = arnoldiBase_.arnoldivectorsSize();
       const Index done = arnoldiBase_.updateArnoldiSteps(batch);
       if (arnoldiBase_.arnoldivectorsSize() == 0) set_initialvector_is_fail = true;
-      replayTrips_(before, done);
+      deferReplay_(before, done);
       solveHessenberg_(false);
     }
     // eigenvectors of H are needed once, at exit (the reference recomputes them every trip)
@@ -635,11 +647,29 @@ class ArnoldiEigenSolver {
     static std::complex<R> get(const ComplexScalar& z) { return z; }
   };
 
-  /// Convergence-log entries of the states with before+1 .. before+done-1 Arnoldi vectors (the trips a batched
-  /// updateArnoldiSteps(done) skipped): eigenvalues of the leading Hessenberg blocks, sorted by descending |lambda|,
-  /// computed on a few host threads and appended in trip order.
-  void replayTrips_(Index before, Index done) {
-    const Index ntrips = done - 1;
+  /// The trips a batched updateArnoldiSteps(done) skipped (states with before+1 .. before+done-1 Arnoldi vectors)
+  /// owe the convergence log one entry per tracked index each.  They are recorded here and computed only when the
+  /// log is read (convergenceLog(), the convergence test): a fixed-length run never pays for them inside compute().
+  void deferReplay_(Index before, Index done) {
+    if (done - 1 <= 0) return;
+    PendingReplay p;
+    p.before = before;
+    p.done = done;
+    for (auto& idx : indicesForConvergence_) {
+      auto it = convergenceLog_.find(idx);
+      p.pos[idx] = (it == convergenceLog_.end()) ? 0 : it->second.size();
+    }
+    pendingReplay_.push_back(p);
+  }
+  void resolvePending_() const {
+    // later batches first: inserting them does not move the insert positions of earlier ones
+    for (auto it = pendingReplay_.rbegin(); it != pendingReplay_.rend(); ++it) replayTrips_(*it);
+    pendingReplay_.clear();
+  }
+  /// Eigenvalues of the leading Hessenberg blocks of the skipped states, sorted by descending |lambda|, computed on
+  /// a few host threads and inserted in trip order at the recorded positions.
+  void replayTrips_(const PendingReplay& pr) const {
+    const Index before = pr.before, ntrips = pr.done - 1;
     if (ntrips <= 0) return;
     std::vector<std::vector<ComplexScalar>> ritz(static_cast<std::size_t>(ntrips));
     auto work = [&](Index t) {
@@ -665,13 +695,17 @@ class ArnoldiEigenSolver {
         });
       for (auto& th : pool) th.join();
     }
-    for (Index t = 0; t < ntrips; ++t) {
-      const std::vector<ComplexScalar>& ev = ritz[static_cast<std::size_t>(t)];
-      for (auto& indexForConvergence : indicesForConvergence_) {
-        Index i = getFormalIndex(indexForConvergence, static_cast<Index>(ev.size()));
+    for (auto& kv : pr.pos) {
+      std::vector<ComplexScalar> vals;
+      for (Index t = 0; t < ntrips; ++t) {
+        const std::vector<ComplexScalar>& ev = ritz[static_cast<std::size_t>(t)];
+        Index i = getFormalIndex(kv.first, static_cast<Index>(ev.size()));
         if (i < 0) continue;
-        convergenceLog_[indexForConvergence].push_back(ev[static_cast<std::size_t>(i)]);
+        vals.push_back(ev[static_cast<std::size_t>(i)]);
       }
+      if (vals.empty()) continue;
+      std::vector<ComplexScalar>& dst = convergenceLog_[kv.first];
+      dst.insert(dst.begin() + static_cast<std::ptrdiff_t>(std::min(kv.second, dst.size())), vals.begin(), vals.end());
     }
   }
 
@@ -727,6 +761,7 @@ class ArnoldiEigenSolver {
   }
 
   bool isConverged_() {  // arnoldi.hpp:969-996
+    resolvePending_();
     if (eigenvalues_.size() < 2) return false;
     RealScalar scale = std::abs(eigenvalues_[0] - eigenvalues_[eigenvalues_.size() - 1]);
     for (auto& idxFroConvergence : indicesForConvergence_) {

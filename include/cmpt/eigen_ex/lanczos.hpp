@@ -387,6 +387,7 @@ class LanczosEigenSolver {
   }
   const std::vector<Index>& indicesForConvergence() const { return indicesForConvergence_; }
   LanczosEigenSolver& setIndicesForConvergence(const std::vector<Index>& iCovs) {
+    resolvePending_();  // pending log entries belong to the old index set
     indicesForConvergence_ = iCovs;
     return *this;
   }
@@ -479,14 +480,24 @@ class LanczosEigenSolver {
   MatrixType eigenvectors_;
   std::vector<std::string> log_;
   TridiagonalEigenSolver<Scalar> es_tri_;
-  std::map<Index, std::vector<RealScalar>> convergenceLog_;
+  mutable std::map<Index, std::vector<RealScalar>> convergenceLog_;
+  // trips skipped by batched stepping whose convergence-log entries have not been computed yet (resolved on the
+  // first access to the log): {first state, number of calls, insert position per tracked index}
+  struct PendingReplay {
+    Index before, done;
+    std::map<Index, std::size_t> pos;
+  };
+  mutable std::vector<PendingReplay> pendingReplay_;
 
  public:
   const RealVectorType& eigenvalues() const { return eigenvalues_; }
   const MatrixType& eigenvectors() const { return eigenvectors_; }
   const std::vector<std::string>& log() const { return log_; }
   const TridiagonalEigenSolver<Scalar>& es_tri() const { return es_tri_; }
-  const std::map<Index, std::vector<RealScalar>>& convergenceLog() const { return convergenceLog_; }
+  const std::map<Index, std::vector<RealScalar>>& convergenceLog() const {
+    resolvePending_();
+    return convergenceLog_;
+  }
 
   /// additive: Ritz residual bounds ||A x_i - theta_i x_i|| = |beta_next * S(last, i)| of the returned eigenpairs,
   /// beta_next = ||A u_k - alpha_k u_k - beta_{k-1} u_{k-1}|| (one fused device pass; the kept beta after a breakdown)
@@ -528,6 +539,7 @@ class LanczosEigenSolver {
     eigenvectors_.resize(0, 0);
     log_.clear();
     convergenceLog_.clear();
+    pendingReplay_.clear();
     return *this;
   }
 
@@ -601,7 +613,7 @@ class LanczosEigenSolver {
       const Index done = lanczosBase_.updateLanczosSteps(batch);
       if (lanczosBase_.lanczosvectorsSize() == 0) set_initialvector_is_fail = true;
       // replay the trips of the intermediate states (their tridiagonal problems are independent of each other)
-      replayTrips_(before, done);
+      deferReplay_(before, done);
       solveTridiagonal_(static_cast<Index>(lanczosBase_.alpha().size()), false);
     }
 
@@ -639,40 +651,61 @@ class LanczosEigenSolver {
     es_tri_.computeRaw(lanczosBase_.alpha().data(), lanczosBase_.beta().data(), static_cast<int>(k), vectors);
   }
 
-  /// Convergence-log entries of the states with before+1 .. before+done-1 Lanczos vectors, i.e. the trips a
-  /// batched updateLanczosSteps(done) skipped.  The Ritz values of each T_j are computed on a few host threads,
-  /// then appended in trip order, exactly as updateConvergenceLog_ would have done.
-  void replayTrips_(Index before, Index done) {
-    const Index ntrips = done - 1;
+  /// The trips a batched updateLanczosSteps(done) skipped (states with before+1 .. before+done-1 Lanczos vectors)
+  /// owe the convergence log one entry per tracked index each.  They are recorded here and computed only when the
+  /// log is read (convergenceLog(), the convergence test): a fixed-length run never pays for them inside compute().
+  void deferReplay_(Index before, Index done) {
+    if (done - 1 <= 0) return;
+    PendingReplay p;
+    p.before = before;
+    p.done = done;
+    for (auto& idx : indicesForConvergence_) {
+      auto it = convergenceLog_.find(idx);
+      p.pos[idx] = (it == convergenceLog_.end()) ? 0 : it->second.size();
+    }
+    pendingReplay_.push_back(p);
+  }
+  void resolvePending_() const {
+    // later batches first: inserting them does not move the insert positions of earlier ones
+    for (auto it = pendingReplay_.rbegin(); it != pendingReplay_.rend(); ++it) replayTrips_(*it);
+    pendingReplay_.clear();
+  }
+  /// Ritz values of each skipped T_j on a few host threads, inserted in trip order at the recorded positions —
+  /// exactly the entries updateConvergenceLog_ would have appended trip by trip.
+  void replayTrips_(const PendingReplay& pr) const {
+    const Index before = pr.before, ntrips = pr.done - 1;
     if (ntrips <= 0) return;
     std::vector<std::vector<RealScalar>> ritz(static_cast<std::size_t>(ntrips));
     const RealScalar* a = lanczosBase_.alpha().data();
     const RealScalar* b = lanczosBase_.beta().data();
-    auto work = [&](Index t0, Index t1) {
-      for (Index t = t0; t < t1; ++t)
-        detail::tridiagonal_eigenvalues<RealScalar>(a, b, static_cast<int>(before + 1 + t), ritz[static_cast<std::size_t>(t)]);
+    auto work = [&](Index t) {
+      detail::tridiagonal_eigenvalues<RealScalar>(a, b, static_cast<int>(before + 1 + t), ritz[static_cast<std::size_t>(t)]);
     };
     unsigned nthreads = std::thread::hardware_concurrency();
     if (nthreads > 8) nthreads = 8;
     if (nthreads < 1 || ntrips < 8) nthreads = 1;
     if (nthreads == 1) {
-      work(0, ntrips);
+      for (Index t = 0; t < ntrips; ++t) work(t);
     } else {
       // interleave so that every thread gets small and large problems
       std::vector<std::thread> pool;
       for (unsigned w = 0; w < nthreads; ++w)
         pool.emplace_back([&, w]() {
-          for (Index t = static_cast<Index>(w); t < ntrips; t += static_cast<Index>(nthreads)) work(t, t + 1);
+          for (Index t = static_cast<Index>(w); t < ntrips; t += static_cast<Index>(nthreads)) work(t);
         });
       for (auto& th : pool) th.join();
     }
-    for (Index t = 0; t < ntrips; ++t) {
-      const std::vector<RealScalar>& ev = ritz[static_cast<std::size_t>(t)];
-      for (auto& indexForConvergence : indicesForConvergence_) {
-        Index i = getFormalIndex(indexForConvergence, static_cast<Index>(ev.size()));
+    for (auto& kv : pr.pos) {
+      std::vector<RealScalar> vals;
+      for (Index t = 0; t < ntrips; ++t) {
+        const std::vector<RealScalar>& ev = ritz[static_cast<std::size_t>(t)];
+        Index i = getFormalIndex(kv.first, static_cast<Index>(ev.size()));
         if (i < 0) continue;
-        convergenceLog_[indexForConvergence].push_back(ev[static_cast<std::size_t>(i)]);
+        vals.push_back(ev[static_cast<std::size_t>(i)]);
       }
+      if (vals.empty()) continue;
+      std::vector<RealScalar>& dst = convergenceLog_[kv.first];
+      dst.insert(dst.begin() + static_cast<std::ptrdiff_t>(std::min(kv.second, dst.size())), vals.begin(), vals.end());
     }
   }
 
@@ -699,6 +732,7 @@ class LanczosEigenSolver {
 
   /// judge convergence with current convergenceLog_ (lanczos.hpp:869-896)
   bool isConverged_() {
+    resolvePending_();
     if (es_tri_.eigenvalues().size() < 2) return false;
     RealScalar scale = es_tri_.eigenvalues()[0] - es_tri_.eigenvalues()[es_tri_.eigenvalues().size() - 1];
     for (auto& idxFroConvergence : indicesForConvergence_) {
