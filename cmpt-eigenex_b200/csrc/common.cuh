@@ -90,6 +90,27 @@ struct MailPull {                 // consumer side (kernel argument)
   int* error = nullptr;                   // set to 1 when a peer never arrives (bounded spin)
 };
 
+// Halo exchange through peer memory (halo.cu): the owner of the rows stores the values a peer needs straight into
+// that peer's receive buffer over NVLink and then raises a per-sender flag there; the consumer (the SpMV kernel)
+// waits on its own flags.  Receive buffers are double-buffered by the parity of the exchange number.
+struct HaloPush {                       // producer side (kernel argument)
+  int P = 1, rank = 0;
+  long long send_off[kMaxPeers + 1];    // slice of the send-index list that goes to each peer
+  double* dst[kMaxPeers];               // where this rank's block starts in the peer's buffer 0
+  long long stride[kMaxPeers];          // distance (doubles) between the peer's buffers 0 and 1
+  unsigned long long* flag[kMaxPeers];  // this rank's flag in the peer's memory
+  unsigned long long* xseq = nullptr;   // local count of executed exchanges
+  unsigned* ticket = nullptr;
+};
+struct HaloPull {                       // consumer side (kernel argument)
+  const double* base = nullptr;         // receive buffer 0 (or the NCCL receive buffer when flag == nullptr)
+  long long stride = 0;
+  const unsigned long long* flag = nullptr;  // [P] per-sender flags in local memory; nullptr: nothing to wait for
+  const unsigned long long* xseq = nullptr;
+  int P = 1, rank = 0;
+  int* error = nullptr;
+};
+
 }  // namespace cmb
 
 // ---- the context ---------------------------------------------------------------------------------
@@ -147,6 +168,9 @@ int allreduce_min_u64(cmb_ctx* ctx, unsigned long long* dev_ptr, size_t count);
 // mailbox bookkeeping (host): the next push gets a fresh sequence number; a pull names the push it consumes
 MailPush mail_next_push(cmb_ctx* ctx);
 MailPull mail_pull_of(cmb_ctx* ctx, unsigned long long seq, double* writeback);
+// collective CUDA-IPC mapping of one cudaMalloc'ed buffer per rank (all-or-nothing; ctx.cu)
+bool ipc_share(cmb_ctx* ctx, void* base, void** mapped);
+void ipc_unshare(cmb_ctx* ctx, void** mapped);
 
 // driver entry point for tensor-map encoding (no link-time libcuda dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -165,29 +165,21 @@ MailPull mail_pull_of(cmb_ctx* ctx, unsigned long long seq, double* writeback) {
   return m;
 }
 
-// Allocate this rank's mailbox, exchange CUDA IPC handles through NCCL (allgather of raw bytes) and map the
-// peers' mailboxes.  Failure is not fatal: the context then keeps using NCCL allreduce for the coefficients.
-static int mail_setup(cmb_ctx* c) {
-  if (c->nranks < 2 || c->nranks > kMaxPeers || !c->nccl->AllGather) return CMB_OK;
-  if (getenv("CMPT_B200_NO_MAILBOX")) return CMB_OK;
+// Collective: every rank passes the base of a cudaMalloc'ed buffer; CUDA IPC handles travel through NCCL (allgather
+// of raw bytes) and every peer's buffer gets mapped here (mapped[q], mapped[rank] = base).  All-or-nothing: returns
+// true on every rank or false on every rank (then nothing stays mapped).
+bool ipc_share(cmb_ctx* c, void* base, void** mapped) {
   const int P = c->nranks;
-  const size_t bytes = mail_data_doubles(P) * sizeof(double) + size_t(kMailSlots) * P * sizeof(unsigned long long);
-  void* base = nullptr;
-  if (cudaMalloc(&base, bytes) != cudaSuccess) {
-    cudaGetLastError();
-    return CMB_OK;
-  }
-  cudaMemset(base, 0, bytes);
-  cudaMalloc(&c->d_mail_error, sizeof(int));
-  cudaMemset(c->d_mail_error, 0, sizeof(int));
+  for (int q = 0; q < P; ++q) mapped[q] = nullptr;
+  if (P < 2 || P > kMaxPeers || !c->nccl || !c->nccl->AllGather) return false;
   cudaIpcMemHandle_t mine;
-  bool ok = cudaIpcGetMemHandle(&mine, base) == cudaSuccess;
-  // allgather [ok flag + handle] as bytes
+  const bool ok = base && cudaIpcGetMemHandle(&mine, base) == cudaSuccess;
+  if (!ok) cudaGetLastError();
   constexpr size_t kRec = 80;
   static_assert(sizeof(cudaIpcMemHandle_t) <= kRec - 8, "IPC handle larger than expected");
   unsigned char rec[kRec] = {0};
   rec[0] = ok ? 1 : 0;
-  memcpy(rec + 8, &mine, sizeof(mine));
+  if (ok) memcpy(rec + 8, &mine, sizeof(mine));
   unsigned char *d_send = nullptr, *d_recv = nullptr;
   std::vector<unsigned char> all(kRec * P, 0);
   cudaMalloc(&d_send, kRec);
@@ -201,7 +193,7 @@ static int mail_setup(cmb_ctx* c) {
   bool all_ok = (nr == 0) && (se == cudaSuccess);
   for (int q = 0; q < P && all_ok; ++q) all_ok = all[kRec * q] == 1;
   if (all_ok) {
-    for (int q = 0; q < P && all_ok; ++q) {
+    for (int q = 0; q < P; ++q) {
       void* p = base;
       if (q != c->rank) {
         cudaIpcMemHandle_t h;
@@ -212,11 +204,10 @@ static int mail_setup(cmb_ctx* c) {
           break;
         }
       }
-      c->mail_data[q] = static_cast<double*>(p);
-      c->mail_flag[q] = reinterpret_cast<unsigned long long*>(static_cast<double*>(p) + mail_data_doubles(P));
+      mapped[q] = p;
     }
   }
-  // every rank must agree on whether the mailboxes are usable (a single failure disables them everywhere)
+  // every rank must agree on whether the mapping is usable (a single failure disables it everywhere)
   double* d_flag = nullptr;
   cudaMalloc(&d_flag, sizeof(double));
   const double mineok = all_ok ? 0.0 : 1.0;
@@ -227,15 +218,47 @@ static int mail_setup(cmb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(d_flag);
   cudaGetLastError();
-  c->mail_ok = (failures == 0.0);
-  if (!c->mail_ok) {
-    for (int q = 0; q < P; ++q)
-      if (q != c->rank && c->mail_data[q]) cudaIpcCloseMemHandle(c->mail_data[q]);
-    for (int q = 0; q < P; ++q) c->mail_data[q] = nullptr, c->mail_flag[q] = nullptr;
-    cudaFree(base);
+  if (failures != 0.0) {
+    ipc_unshare(c, mapped);
+    return false;
+  }
+  return true;
+}
+
+void ipc_unshare(cmb_ctx* c, void** mapped) {
+  for (int q = 0; q < c->nranks; ++q) {
+    if (q != c->rank && mapped[q]) cudaIpcCloseMemHandle(mapped[q]);
+    mapped[q] = nullptr;
+  }
+  cudaGetLastError();
+}
+
+// Allocate this rank's mailbox and map the peers' mailboxes.  Failure is not fatal: the context then keeps using
+// NCCL allreduce for the coefficients.
+static int mail_setup(cmb_ctx* c) {
+  if (c->nranks < 2 || c->nranks > kMaxPeers || !c->nccl->AllGather) return CMB_OK;
+  if (getenv("CMPT_B200_NO_MAILBOX")) return CMB_OK;
+  const int P = c->nranks;
+  const size_t bytes = mail_data_doubles(P) * sizeof(double) + size_t(kMailSlots) * P * sizeof(unsigned long long);
+  void* base = nullptr;
+  if (cudaMalloc(&base, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    base = nullptr;
   } else {
-    c->mail_data[c->rank] = static_cast<double*>(base);
-    c->mail_flag[c->rank] = reinterpret_cast<unsigned long long*>(static_cast<double*>(base) + mail_data_doubles(P));
+    cudaMemset(base, 0, bytes);
+  }
+  cudaMalloc(&c->d_mail_error, sizeof(int));
+  cudaMemset(c->d_mail_error, 0, sizeof(int));
+  void* mapped[kMaxPeers];
+  c->mail_ok = ipc_share(c, base, mapped);
+  if (!c->mail_ok) {
+    for (int q = 0; q < P; ++q) c->mail_data[q] = nullptr, c->mail_flag[q] = nullptr;
+    if (base) cudaFree(base);
+  } else {
+    for (int q = 0; q < P; ++q) {
+      c->mail_data[q] = static_cast<double*>(mapped[q]);
+      c->mail_flag[q] = reinterpret_cast<unsigned long long*>(static_cast<double*>(mapped[q]) + mail_data_doubles(P));
+    }
   }
   return CMB_OK;
 }

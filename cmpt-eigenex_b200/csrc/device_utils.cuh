@@ -54,6 +54,31 @@ __device__ __forceinline__ void mail_publish(const MailPush& m) {
   for (int q = 0; q < m.P; ++q) st_release_sys_u64(m.flag[q] + m.rank, m.seq);
 }
 
+// Consumer side of the peer-memory halo exchange: wait until every peer has published the exchange the preceding
+// push kernel of this rank counted in *xseq, then return the receive buffer of that parity.  Called by all threads
+// of the CTA.  The spin is bounded like mail_wait.
+__device__ __forceinline__ const double* halo_acquire(const HaloPull& h) {
+  if (!h.flag) return h.base;
+  __shared__ unsigned long long s_halo_seq;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const unsigned long long seq = *h.xseq;
+    if (lane < h.P && lane != h.rank) {
+      const long long t0 = clock64();
+      while (ld_acquire_sys_u64(h.flag + lane) < seq) {
+        if (clock64() - t0 > (1ll << 32)) {
+          *h.error = 1;
+          break;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) s_halo_seq = seq;
+  }
+  __syncthreads();
+  return h.base + (s_halo_seq & 1ull) * h.stride;
+}
+
 __device__ __forceinline__ bool step_prologue(const StepScalars& sc, double& inv) {
   if (*sc.halt) return false;
   double nrm2;

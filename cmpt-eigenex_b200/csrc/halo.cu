@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <thread>
 
+#include "device_utils.cuh"
 #include "halo.cuh"
 
 namespace cmb {
@@ -106,10 +107,110 @@ __global__ void pack_kernel(const double* __restrict__ w, const int* __restrict_
   }
 }
 
+// Peer-memory variant of pack + send: the gathered values go straight into each peer's receive buffer (NVLink
+// stores), then the last CTA raises this rank's flag at every peer (also at those that get no data: the consumer
+// waits for all of them, which is what makes two receive buffers enough) and counts the exchange in *xseq.
+template <int ES>
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const double* __restrict__ w, const int* __restrict__ idx, HaloPush hp, const int* __restrict__ halt) {
+  if (*halt) return;
+  const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(hp.xseq) + 1ull;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int q = 0; q < hp.P; ++q) {
+    const long long a = hp.send_off[q], b = hp.send_off[q + 1];
+    if (b <= a) continue;
+    double* dst = hp.dst[q] + (seq & 1ull) * hp.stride[q];
+    for (long long i = a + t; i < b; i += stride) {
+      const long long s = idx[i];
+#pragma unroll
+      for (int e = 0; e < ES; ++e) dst[(i - a) * ES + e] = w[s * ES + e];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(hp.ticket, 1u);
+    if (prev == gridDim.x - 1) {
+      __threadfence_system();
+      for (int q = 0; q < hp.P; ++q)
+        if (q != hp.rank) st_release_sys_u64(hp.flag[q], seq);
+      *hp.xseq = seq;
+      *hp.ticket = 0u;
+    }
+  }
+}
+
 HaloExchange::~HaloExchange() {
+  if (p2p_ctx) {
+    cudaStreamSynchronize(p2p_ctx->stream);
+    ipc_unshare(p2p_ctx, p2p_mapped);
+    cudaFree(push.xseq);
+    cudaFree(push.ticket);
+    cudaFree(p2p_base);
+  }
   cudaFree(d_send_idx);
   cudaFree(d_sendbuf);
   cudaFree(d_halo);
+}
+
+// Collective.  cnt is the P x P matrix of halo counts (cnt[q*P + r] = entries rank q reads from rank r).
+int HaloExchange::setup_p2p(cmb_ctx* ctx, const std::vector<double>& cnt) {
+  if (!ctx->mail_ok || getenv("CMPT_B200_NO_P2P_HALO")) return CMB_OK;  // mail_ok: IPC between all ranks works
+  constexpr size_t kFlagBytes = 256;
+  static_assert(kMaxPeers * sizeof(unsigned long long) <= kFlagBytes, "flag block too small");
+  const size_t bytes = kFlagBytes + 2 * sizeof(double) * size_t(es) * size_t(std::max<int64_t>(nrecv, 1));
+  void* base = nullptr;
+  if (cudaMalloc(&base, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    base = nullptr;
+  } else {
+    cudaMemsetAsync(base, 0, bytes, ctx->stream);
+  }
+  unsigned long long* xseq = nullptr;
+  unsigned* ticket = nullptr;
+  bool ok = base && cudaMalloc(&xseq, sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMalloc(&ticket, sizeof(unsigned)) == cudaSuccess;
+  if (ok) {
+    cudaMemsetAsync(xseq, 0, sizeof(unsigned long long), ctx->stream);
+    cudaMemsetAsync(ticket, 0, sizeof(unsigned), ctx->stream);
+  }
+  cudaStreamSynchronize(ctx->stream);
+  void* mapped[kMaxPeers];
+  if (!ipc_share(ctx, ok ? base : nullptr, mapped)) {
+    cudaFree(base);
+    cudaFree(xseq);
+    cudaFree(ticket);
+    cudaGetLastError();
+    return CMB_OK;  // NCCL path stays
+  }
+  p2p = true;
+  p2p_ctx = ctx;
+  p2p_base = base;
+  push.P = P;
+  push.rank = rank;
+  push.xseq = xseq;
+  push.ticket = ticket;
+  for (int q = 0; q <= P; ++q) push.send_off[q] = send_off[q];
+  for (int q = 0; q < P; ++q) {
+    p2p_mapped[q] = mapped[q];
+    int64_t off = 0, tot = 0;
+    for (int r = 0; r < P; ++r) {
+      if (r < rank) off += int64_t(cnt[size_t(q) * P + r]);
+      tot += int64_t(cnt[size_t(q) * P + r]);
+    }
+    push.dst[q] = reinterpret_cast<double*>(static_cast<char*>(mapped[q]) + kFlagBytes) + off * es;
+    push.stride[q] = std::max<int64_t>(tot, 1) * es;
+    push.flag[q] = static_cast<unsigned long long*>(mapped[q]) + rank;
+  }
+  pull.base = reinterpret_cast<const double*>(static_cast<char*>(base) + kFlagBytes);
+  pull.stride = std::max<int64_t>(nrecv, 1) * es;
+  pull.flag = static_cast<const unsigned long long*>(base);
+  pull.xseq = xseq;
+  pull.P = P;
+  pull.rank = rank;
+  pull.error = ctx->d_mail_error;
+  return CMB_OK;
 }
 
 int HaloExchange::setup(cmb_ctx* ctx, int64_t n, int es_, const std::vector<int32_t>& halo_cols,
@@ -179,13 +280,26 @@ int HaloExchange::setup(cmb_ctx* ctx, int64_t n, int es_, const std::vector<int3
     sidx[i] = int32_t(l);
   }
   CMB_CUDA(cudaMemcpyAsync(d_send_idx, sidx.data(), sizeof(int32_t) * nsend, cudaMemcpyHostToDevice, ctx->stream));
-  CMB_CUDA(cudaMalloc(&d_sendbuf, sizeof(double) * es * std::max<int64_t>(nsend, 1)));
-  CMB_CUDA(cudaMalloc(&d_halo, sizeof(double) * es * std::max<int64_t>(nrecv, 1)));
   CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  CMB_TRY(setup_p2p(ctx, cnt));
+  if (!p2p) {
+    CMB_CUDA(cudaMalloc(&d_sendbuf, sizeof(double) * es * std::max<int64_t>(nsend, 1)));
+    CMB_CUDA(cudaMalloc(&d_halo, sizeof(double) * es * std::max<int64_t>(nrecv, 1)));
+  }
   return CMB_OK;
 }
 
 int HaloExchange::exchange(cmb_ctx* ctx, const double* w, const int* halt) {
+  if (p2p) {
+    LaunchScope ls(ctx, "halo_push");
+    const int grid = int(std::max<int64_t>(1, std::min<int64_t>((nsend + 255) / 256, int64_t(ctx->num_sms) * 4)));
+    if (es == 2)
+      halo_push_kernel<2><<<grid, 256, 0, ctx->stream>>>(w, d_send_idx, push, halt);
+    else
+      halo_push_kernel<1><<<grid, 256, 0, ctx->stream>>>(w, d_send_idx, push, halt);
+    CMB_CUDA(cudaGetLastError());
+    return CMB_OK;
+  }
   if (nsend > 0) {
     LaunchScope ls(ctx, "halo_pack");
     const int grid = int(std::max<int64_t>(1, std::min<int64_t>((nsend + 255) / 256, int64_t(ctx->num_sms) * 8)));

@@ -18,10 +18,27 @@ struct HaloExchange {
   int32_t* d_send_idx = nullptr;
   double* d_sendbuf = nullptr;
   double* d_halo = nullptr;
+  // peer-memory push path (CUDA IPC over NVLink); NCCL send/recv is the fallback when the mapping is unavailable
+  bool p2p = false;
+  cmb_ctx* p2p_ctx = nullptr;
+  void* p2p_base = nullptr;  // own allocation: [kMaxPeers flags, padded to 256 B][2 x nrecv*es doubles]
+  void* p2p_mapped[kMaxPeers] = {};
+  HaloPush push;
+  HaloPull pull;
   ~HaloExchange();
   int setup(cmb_ctx* ctx, int64_t n_global, int es, const std::vector<int32_t>& halo_cols,
             const std::vector<int64_t>& per_owner);
   int exchange(cmb_ctx* ctx, const double* w, const int* halt);
+  // what the consuming kernel needs: which buffer to gather from and which flags to wait on
+  HaloPull pull_args() const {
+    if (p2p) return pull;
+    HaloPull h;
+    h.base = d_halo;
+    return h;
+  }
+
+ private:
+  int setup_p2p(cmb_ctx* ctx, const std::vector<double>& cnt);
 };
 
 }  // namespace cmb

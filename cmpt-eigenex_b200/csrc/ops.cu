@@ -23,11 +23,12 @@ namespace cmb {
 template <bool CPLX>
 __global__ void __launch_bounds__(256)
 spmv_sell_kernel(const long long* __restrict__ slice_ptr, const int* __restrict__ col, const double* __restrict__ val,
-                 long long nrows, long long nslices, const double* __restrict__ w, const double* __restrict__ halo,
+                 long long nrows, long long nslices, const double* __restrict__ w, HaloPull hp,
                  double* __restrict__ ucol, double* __restrict__ v, double shr, double shi, StepScalars sc,
                  double* partial, unsigned* ticket) {
   double inv;
   if (!step_prologue(sc, inv)) return;
+  const double* __restrict__ halo = halo_acquire(hp);
   const int lane = threadIdx.x & 31;
   const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -91,10 +92,11 @@ spmv_sell_kernel(const long long* __restrict__ slice_ptr, const int* __restrict_
 template <int W>
 __global__ void __launch_bounds__(256)
 spmv_sell_uniform_kernel(const int* __restrict__ col, const double* __restrict__ val, long long nrows, long long nslices,
-                         const double* __restrict__ w, const double* __restrict__ halo, double* __restrict__ ucol,
+                         const double* __restrict__ w, HaloPull hp, double* __restrict__ ucol,
                          double* __restrict__ v, double shr, StepScalars sc, double* partial, unsigned* ticket) {
   double inv;
   if (!step_prologue(sc, inv)) return;
+  const double* __restrict__ halo = halo_acquire(hp);
   const int lane = threadIdx.x & 31;
   const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -183,11 +185,11 @@ struct SellOp : cmb_op {
     delete halo;
   }
   int apply(const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) override {
-    const double* d_halo = nullptr;
+    HaloPull d_halo;
     if (halo) {
       // NVLink halo exchange of the un-normalised w (1/beta is applied inside the SpMV)
       CMB_TRY(halo->exchange(ctx, w, sc.halt));
-      d_halo = halo->d_halo;
+      d_halo = halo->pull_args();
     }
     long long blocks = (nslices + 7) / 8;
     int grid = int(std::min<long long>(blocks, (long long)ctx->num_sms * 8));
