@@ -13,20 +13,46 @@
 //                                             of the partner's slab (packed by the sender)
 // The slabs travel as the un-normalised w (NVLink, ncclSend/ncclRecv group); 1/beta is applied to the sum.
 // Fused with the step's normalisation and the alpha dot like every other operator (op.cuh).
+#include <string.h>
+
 #include <algorithm>
+#include <type_traits>
+#include <vector>
 
 #include "device_utils.cuh"
 #include "op.cuh"
 
 namespace cmb {
 
-constexpr int kMaxFull = 6;  // rank-rank bonds (p <= 7)
+constexpr int kMaxFull = 6;        // rank-rank bonds (p <= 7)
+
+// The local bonds are a nearest-neighbour stencil on the bits of the state index: element s gathers from
+// s ^ (3 << b).  One pass of the kernel stages TILES of 2^tb elements (64 KB) in shared memory and serves from a tile
+// every bond whose two bits lie inside it.  A tile is the set of indices that share all bits outside
+//     {0 .. a-1}  (contiguous run of 256 bytes: keeps global accesses coalesced)   and   {h .. h+tb-a-1}  (the window),
+// so the first pass (a = tb, contiguous tiles) covers bonds 0 .. tb-2 and every further pass moves the window up.
+// The passes' contributions add up in v; the diagonal term splits over the passes the same way.
+// Data movement: persistent CTAs, one producer thread feeding a 3-stage ring of tiles through TMA (a bulk copy for
+// the contiguous tiles of the first pass, a 3-D tensor box {run, 1, window} for the others), 16 consumer warps.
+struct HeisPass {
+  int tb;     // tile bits
+  int a;      // contiguous low bits of the tile
+  int h;      // global position of tile bit a (start of the window)
+  int k0;     // this pass serves the bonds joining tile bits (k, k+1), k0 <= k < tb-1 ...
+  int wrapb;  // ... and, when set, the periodic bond joining tile bits tb-1 and 0 (single rank only)
+  int first;  // writes u and v, adds the remote bonds and the shift
+  int last;   // computes the alpha dot
+};
+
+constexpr int kHeisConsumers = 512;  // 16 warps (128 registers each); thread 0 also feeds the ring
+constexpr int kHeisThreads = kHeisConsumers;
+constexpr int kHeisStages = 3;
+constexpr int kHeisTileBytes = 65536;
+constexpr int kHeisSmem = kHeisStages * kHeisTileBytes + 2 * kHeisStages * 8;
 
 struct HeisArgs {
   int Ll;             // local bits
   int nb;             // total number of bonds (for the diagonal)
-  int n_local_bonds;  // bonds (i,i+1), i+1 < Ll
-  int local_wrap;     // single rank + PBC: bond (Ll-1, 0) is local
   int aligned_uniform;  // rank-rank bonds whose two rank bits agree
   int n_full;           // rank-rank bonds whose rank bits differ: full partner slabs
   const double* full[kMaxFull];
@@ -37,73 +63,262 @@ struct HeisArgs {
   double J;
 };
 
+// Two neighbouring tile elements (t0 even, t0 + 1): the unit of work of one thread.  For every bond that does not
+// involve tile bit 0 the two share the aligned/anti-aligned decision and their partners are neighbours too, so one
+// test and one 16-byte shared-memory load serve both.
 template <bool CPLX>
-__global__ void __launch_bounds__(256)
-heis_apply_kernel(HeisArgs a, const double* __restrict__ w, double* __restrict__ ucol, double* __restrict__ v,
-                  double shr, double shi, StepScalars sc, double* partial, unsigned* ticket) {
-  double inv;
-  if (!step_prologue(sc, inv)) return;
-  const long long dim = 1ll << a.Ll;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long top = 1ll << (a.Ll - 1);
-  double d0 = 0.0, d1 = 0.0;
-  auto ld = [&](const double* p, long long i, double& re, double& im) {
-    if (CPLX) {
-      const double2 z = reinterpret_cast<const double2*>(p)[i];
-      re += z.x;
-      im += z.y;
+struct HeisPair {
+  double r0, i0, r1, i1;
+  __device__ __forceinline__ static HeisPair zero() { return HeisPair{0.0, 0.0, 0.0, 0.0}; }
+  __device__ __forceinline__ static HeisPair load(const double* base, long long t0) {
+    HeisPair p;
+    if constexpr (CPLX) {
+      const double2 e0 = reinterpret_cast<const double2*>(base)[t0];
+      const double2 e1 = reinterpret_cast<const double2*>(base)[t0 + 1];
+      p.r0 = e0.x, p.i0 = e0.y, p.r1 = e1.x, p.i1 = e1.y;
     } else {
-      re += p[i];
+      const double2 e = *reinterpret_cast<const double2*>(base + t0);
+      p.r0 = e.x, p.r1 = e.y, p.i0 = 0.0, p.i1 = 0.0;
     }
-  };
-  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < dim; s += stride) {
-    int aligned = a.aligned_uniform;
-    double ar = 0.0, ai = 0.0;
-    for (int b = 0; b < a.n_local_bonds; ++b) {
-      if (((s >> b) ^ (s >> (b + 1))) & 1)
-        ld(w, s ^ (3ll << b), ar, ai);
-      else
-        ++aligned;
-    }
-    if (a.local_wrap) {
-      if (((s >> (a.Ll - 1)) ^ s) & 1)
-        ld(w, s ^ (top | 1ll), ar, ai);
-      else
-        ++aligned;
-    }
-    for (int k = 0; k < a.n_full; ++k) ld(a.full[k], s, ar, ai);
-    if (a.has_straddle) {
-      if (int((s >> (a.Ll - 1)) & 1) != a.rb0)
-        ld(a.half, s & (top - 1), ar, ai);
-      else
-        ++aligned;
-    }
-    if (a.has_wrap) {
-      if (int(s & 1) != a.rt)
-        ld(a.wrap, s >> 1, ar, ai);
-      else
-        ++aligned;
-    }
-    const double diag = 0.25 * a.J * double(2 * aligned - a.nb);
-    if (CPLX) {
-      const double2 wi = reinterpret_cast<const double2*>(w)[s];
-      const double ur = wi.x * inv, ui = wi.y * inv;
-      const double yr = (diag * wi.x + 0.5 * a.J * ar) * inv + (shr * ur - shi * ui);
-      const double yi = (diag * wi.y + 0.5 * a.J * ai) * inv + (shr * ui + shi * ur);
-      reinterpret_cast<double2*>(ucol)[s] = make_double2(ur, ui);
-      reinterpret_cast<double2*>(v)[s] = make_double2(yr, yi);
-      d0 += ur * yr + ui * yi;
-      d1 += ur * yi - ui * yr;
+    return p;
+  }
+  __device__ __forceinline__ void store(double* base, long long t0) const {
+    if constexpr (CPLX) {
+      reinterpret_cast<double2*>(base)[t0] = make_double2(r0, i0);
+      reinterpret_cast<double2*>(base)[t0 + 1] = make_double2(r1, i1);
     } else {
-      const double wi = w[s];
-      const double ui = wi * inv;
-      const double y = (diag * wi + 0.5 * a.J * ar) * inv + shr * ui;
-      ucol[s] = ui;
-      v[s] = y;
-      d0 = fma(ui, y, d0);
+      *reinterpret_cast<double2*>(base + t0) = make_double2(r0, r1);
     }
   }
-  grid_sum_finalize<CPLX ? 2 : 1>(d0, d1, partial, ticket, sc.alpha_slot);
+  __device__ __forceinline__ void add(const HeisPair& o) {
+    r0 += o.r0, r1 += o.r1;
+    if constexpr (CPLX) i0 += o.i0, i1 += o.i1;
+  }
+  __device__ __forceinline__ void add_if(const HeisPair& o, bool c) {
+    r0 += c ? o.r0 : 0.0, r1 += c ? o.r1 : 0.0;
+    if constexpr (CPLX) i0 += c ? o.i0 : 0.0, i1 += c ? o.i1 : 0.0;
+  }
+  // element 0 += o.element 1   /   element 1 += o.element 0
+  __device__ __forceinline__ void add_cross(const HeisPair& o, bool into0) {
+    if (into0) {
+      r0 += o.r1;
+      if constexpr (CPLX) i0 += o.i1;
+    } else {
+      r1 += o.r0;
+      if constexpr (CPLX) i1 += o.i0;
+    }
+  }
+};
+
+// FIRST / LAST: role of the pass (compile time, so that the unrolled pair loop carries no uniform branches for them)
+template <bool CPLX, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(kHeisThreads, 1)
+heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap tm, const double* __restrict__ w,
+                  double* __restrict__ ucol, double* __restrict__ v, double shr, double shi, StepScalars sc,
+                  double* partial, unsigned* ticket) {
+  using Pair = HeisPair<CPLX>;
+  constexpr int ES = CPLX ? 2 : 1;
+  constexpr int PPT = CPLX ? 4 : 8;  // pairs per consumer thread in a full tile
+  extern __shared__ __align__(128) unsigned char heis_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(heis_smem + kHeisStages * kHeisTileBytes);
+  uint64_t* empty = full + kHeisStages;
+  double inv;
+  if (!step_prologue(sc, inv)) return;  // idempotent: every pass of one apply takes the same decision
+  const int tb = ps.tb;
+  const int npairs = 1 << (tb - 1);
+  const int nmid = ps.h - ps.a;  // index bits between the contiguous run and the window
+  const long long ntiles = 1ll << (a.Ll - tb);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kHeisStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kHeisConsumers / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  double d0 = 0.0, d1 = 0.0;
+  // ring feeder (thread 0): one TMA per tile into stage `s`, signalled on full[s]
+  const uint32_t tile_bytes = uint32_t(sizeof(double) * ES) << tb;
+  const bool contiguous = (ps.a == tb);
+  auto feed = [&](long long tile, int s) {
+    mbar_arrive_expect_tx(&full[s], tile_bytes);
+    void* dst = heis_smem + size_t(s) * kHeisTileBytes;
+    if (contiguous)
+      bulk_load_1d(dst, w + (size_t(tile) << tb) * ES, tile_bytes, &full[s]);
+    else
+      tma_load_3d(dst, &tm, 0, int(tile & ((1ll << nmid) - 1)), int((tile >> nmid) << (tb - ps.a)), &full[s]);
+  };
+  if (threadIdx.x == 0) {
+    if (!contiguous) prefetch_tmap(&tm);
+    for (int s = 0; s < kHeisStages; ++s) {
+      const long long tile = blockIdx.x + (long long)s * gridDim.x;
+      if (tile < ntiles) feed(tile, s);
+    }
+  }
+  {
+    const int lowmask = (1 << ps.a) - 1;
+    const long long top = 1ll << (a.Ll - 1);
+    const double hJ = 0.5 * a.J, qJ = 0.25 * a.J;
+    const int kfirst = ps.k0 > 1 ? ps.k0 : 1;
+    const int kmask = ((1 << (tb - 1)) - 1) & ~((1 << kfirst) - 1);  // gray-code bits of the bonds k >= kfirst
+    const bool bond0 = (ps.k0 == 0 && tb >= 2);
+    const int nlocal = (tb - 1 - ps.k0) + ps.wrapb;
+    // bonds whose diagonal term this pass accounts for (the remote bonds ride with the first pass)
+    const bool remote = (a.n_full | a.has_straddle | a.has_wrap) != 0;
+    const int nb_pass = nlocal + (FIRST ? a.aligned_uniform + a.n_full + a.has_straddle + a.has_wrap : 0);
+    // pair g = threadIdx.x + 512 j  ->  tile element t0 = 2 g = tl + (j << 10); the tile -> global index map is a
+    // bit deposit, so it splits into a per-thread part (hoisted) and a per-iteration part
+    const int tl = 2 * threadIdx.x;  // < 1024
+    const int gm = (tl ^ (tl >> 1)) & kmask & 0x1fe;  // bonds 1..8: anti-aligned and served by this pass
+    const int anti_tid = __popc(gm);
+    const int b9 = (tl >> 9) & 1, b1 = (tl >> 1) & 1;
+    const long long s_tid = (long long)(tl & lowmask) | ((long long)(tl >> ps.a) << ps.h);
+    auto s_iter = [&](int j) -> long long {
+      const int tj = j << 10;
+      return (long long)(tj & lowmask) | ((long long)(tj >> ps.a) << ps.h);
+    };
+    int st = 0;
+    uint32_t ph = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long base =
+          (((tile & ((1ll << nmid) - 1)) << ps.a) | ((tile >> nmid) << (ps.h + tb - ps.a))) + s_tid;
+      Pair yold[PPT];
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        yold[j] = Pair::zero();
+        if (!FIRST && int(threadIdx.x) + kHeisConsumers * j < npairs) yold[j] = Pair::load(v, base + s_iter(j));
+      }
+      mbar_wait(&full[st], ph);
+      const double* sm = reinterpret_cast<const double*>(heis_smem + size_t(st) * kHeisTileBytes);
+      // This thread's pairs are t0(j) = tl | (j << 10): tile bits 0..9 are the thread's, bits 10.. are j (compile
+      // time after unrolling).  Bonds k <= 8 therefore have a per-thread aligned/anti-aligned pattern (gm) and one
+      // test serves all PPT pairs; bonds 10 and 11 are decided by j alone.  Loads may touch stage bytes outside a
+      // small tile (tb < 13) for pairs that do not exist; those results are never stored.
+      Pair acc[PPT];
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) acc[j] = Pair::zero();
+#pragma unroll
+      for (int k = 1; k <= 8; ++k) {
+        if (gm & (1 << k)) {
+          const int po = tl ^ (3 << k);
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) acc[j].add(Pair::load(sm, po | (j << 10)));
+        }
+      }
+      if (kmask & (1 << 9)) {  // tile bits 9 (thread) and 10 (j bit 0)
+        const int po = tl ^ (1 << 9);
+#pragma unroll
+        for (int j = 0; j < PPT; ++j)
+          if (b9 != (j & 1)) acc[j].add(Pair::load(sm, po | ((j ^ 1) << 10)));
+      }
+      if (kmask & (1 << 10)) {  // tile bits 10, 11 = j bits 0, 1
+#pragma unroll
+        for (int j = 0; j < PPT; ++j)
+          if (((j ^ (j >> 1)) & 1) != 0) acc[j].add(Pair::load(sm, tl | ((j ^ 3) << 10)));
+      }
+      if (PPT > 4 && (kmask & (1 << 11))) {  // tile bits 11, 12 = j bits 1, 2
+#pragma unroll
+        for (int j = 0; j < PPT; ++j)
+          if (((j ^ (j >> 1)) & 2) != 0) acc[j].add(Pair::load(sm, tl | ((j ^ 6) << 10)));
+      }
+      if (bond0) {  // tile bits 0 and 1: exactly one of the two elements of a pair is anti-aligned
+        const int po = tl ^ 2;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) acc[j].add_cross(Pair::load(sm, po | (j << 10)), b1 != 0);
+      }
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        const int g = int(threadIdx.x) + kHeisConsumers * j;
+        if (g < npairs) {
+          const int t0 = tl | (j << 10);
+          const long long s0 = base + s_iter(j);
+          const Pair x = Pair::load(sm, t0);
+          // anti-aligned bonds: thread part + bond 9 + the j-only bonds 10, 11 (+ bond 0, per element)
+          int anti0 = anti_tid + ((kmask >> 9) & (b9 ^ (j & 1))) + __popc(((j ^ (j >> 1)) << 10) & kmask);
+          int anti1 = anti0;
+          if (bond0) {
+            anti0 += b1;
+            anti1 += 1 - b1;
+          }
+          if (ps.wrapb) {  // tile bits tb-1 and 0 (single rank, periodic chain)
+            const int bt = (t0 >> (tb - 1)) & 1;
+            acc[j].add_cross(Pair::load(sm, t0 ^ (1 << (tb - 1))), bt != 0);
+            anti0 += bt;
+            anti1 += 1 - bt;
+          }
+          if (FIRST && remote) {
+            anti0 += a.n_full;
+            anti1 += a.n_full;
+#pragma unroll
+            for (int k = 0; k < kMaxFull; ++k)
+              if (k < a.n_full) acc[j].add(Pair::load(a.full[k], s0));
+            if (a.has_straddle) {
+              if (int((s0 >> (a.Ll - 1)) & 1) != a.rb0) {
+                acc[j].add(Pair::load(a.half, s0 & (top - 1)));
+                ++anti0;
+                ++anti1;
+              }
+            }
+            if (a.has_wrap) {  // partner element (s >> 1) of the packed half slab, for the element whose bit 0 != rt
+              const double* q = a.wrap + (s0 >> 1) * ES;
+              if (a.rt) {
+                acc[j].r0 += q[0];
+                if constexpr (CPLX) acc[j].i0 += q[1];
+                ++anti0;
+              } else {
+                acc[j].r1 += q[0];
+                if constexpr (CPLX) acc[j].i1 += q[1];
+                ++anti1;
+              }
+            }
+          }
+          const double dg0 = qJ * double(nb_pass - 2 * anti0), dg1 = qJ * double(nb_pass - 2 * anti1);
+          Pair u, y;
+          u.r0 = x.r0 * inv, u.r1 = x.r1 * inv, u.i0 = x.i0 * inv, u.i1 = x.i1 * inv;
+          y.r0 = (dg0 * x.r0 + hJ * acc[j].r0) * inv;
+          y.r1 = (dg1 * x.r1 + hJ * acc[j].r1) * inv;
+          y.i0 = y.i1 = 0.0;
+          if constexpr (CPLX) {
+            y.i0 = (dg0 * x.i0 + hJ * acc[j].i0) * inv;
+            y.i1 = (dg1 * x.i1 + hJ * acc[j].i1) * inv;
+          }
+          if (FIRST) {
+            y.r0 += shr * u.r0, y.r1 += shr * u.r1;
+            if constexpr (CPLX) {
+              y.r0 -= shi * u.i0, y.r1 -= shi * u.i1;
+              y.i0 += shr * u.i0 + shi * u.r0, y.i1 += shr * u.i1 + shi * u.r1;
+            }
+            u.store(ucol, s0);
+          } else {
+            y.add(yold[j]);
+          }
+          y.store(v, s0);
+          if (LAST) {
+            d0 = fma(u.r0, y.r0, d0);
+            d0 = fma(u.r1, y.r1, d0);
+            if constexpr (CPLX) {
+              d0 += u.i0 * y.i0 + u.i1 * y.i1;
+              d1 += u.r0 * y.i0 - u.i0 * y.r0 + u.r1 * y.i1 - u.i1 * y.r1;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[st]);
+      if (threadIdx.x == 0) {  // refill this stage with the tile kHeisStages ahead once all 16 warps released it
+        const long long nt = tile + (long long)kHeisStages * gridDim.x;
+        if (nt < ntiles) {
+          mbar_wait(&empty[st], ph);
+          feed(nt, st);
+        }
+      }
+      if (++st == kHeisStages) {
+        st = 0;
+        ph ^= 1u;
+      }
+    }
+  }
+  if (LAST) grid_sum_finalize<CPLX ? 2 : 1>(d0, d1, partial, ticket, sc.alpha_slot);
 }
 
 // out[i] = w[2 i + parity] : the elements a wrap-bond partner needs
@@ -156,6 +371,7 @@ struct HeisenbergOp : cmb_op {
   double* d_recv = nullptr;  // receive buffers, one region per needed remote bond
   double* d_pack = nullptr;  // packed parity half for the wrap bond
   std::vector<size_t> recv_off;
+  std::vector<HeisPass> passes;
   ~HeisenbergOp() override {
     pool_free(ctx, d_recv);
     pool_free(ctx, d_pack);
@@ -166,10 +382,53 @@ struct HeisenbergOp : cmb_op {
     memset(&a, 0, sizeof(a));
     a.Ll = plan.Ll;
     a.nb = plan.nb;
-    a.n_local_bonds = plan.Ll - 1;
-    a.local_wrap = (plan.p == 0 && plan.nb == plan.L) ? 1 : 0;
     a.J = J;
     return a;
+  }
+
+  // Tiling of the local bonds (see HeisPass).  64 KB tiles: 2^13 doubles or 2^12 complex numbers; window passes
+  // keep runs of 256 bytes and move an 8-bit window (box rows of a TMA tensor map are limited to 256).
+  void plan_passes() {
+    passes.clear();
+    const int Ll = plan.Ll, TB = cplx ? 12 : 13, arun = cplx ? 4 : 5, wb = TB - arun;
+    const bool local_wrap = (plan.p == 0 && plan.nb == plan.L);
+    HeisPass q;
+    memset(&q, 0, sizeof(q));
+    q.tb = std::min(Ll, TB);
+    q.a = q.h = q.tb;
+    q.wrapb = (Ll <= TB && local_wrap) ? 1 : 0;
+    q.first = 1;
+    passes.push_back(q);
+    int next = q.tb - 1;  // first bond not served yet (bond b joins bits b and b+1)
+    while (next <= Ll - 2) {
+      memset(&q, 0, sizeof(q));
+      q.tb = TB;
+      q.a = arun;
+      q.h = std::min(next, Ll - wb);  // the last window is pulled down so that it ends at the top bit
+      q.k0 = q.a + (next - q.h);
+      q.wrapb = (q.h + wb == Ll && local_wrap) ? 1 : 0;
+      next = q.h + wb - 1;
+      passes.push_back(q);
+    }
+    passes.back().last = 1;
+  }
+
+  // 3-D view of a local vector for the tiles of a window pass: {run, index bits between run and window, the rest}
+  int window_map(const HeisPass& ps, const double* w, CUtensorMap* tm) const {
+    const int es = cplx ? 2 : 1;
+    cuuint64_t gdim[3] = {cuuint64_t(es) << ps.a, cuuint64_t(1) << (ps.h - ps.a), cuuint64_t(1) << (plan.Ll - ps.h)};
+    cuuint64_t gstr[2] = {(cuuint64_t(8 * es) << ps.a), (cuuint64_t(8 * es) << ps.h)};
+    cuuint32_t box[3] = {cuuint32_t(es) << ps.a, 1u, 1u << (ps.tb - ps.a)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = get_encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(w), gdim, gstr, box,
+                                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed (%d) for the Heisenberg window a=%d h=%d Ll=%d", int(cr), ps.a, ps.h,
+                plan.Ll);
+      return CMB_ERR_CUDA;
+    }
+    return CMB_OK;
   }
 
   int alloc_dist() {
@@ -212,15 +471,44 @@ struct HeisenbergOp : cmb_op {
 
   int launch(const HeisArgs& a, const double* w, double* ucol, double* v, double shr, double shi,
              const StepScalars& sc) {
-    int grid = int(std::min<long long>((n_local + 255) / 256, (long long)ctx->num_sms * 8));
-    LaunchScope ls(ctx, "heisenberg_mf");
-    if (cplx)
-      heis_apply_kernel<true><<<grid, 256, 0, ctx->stream>>>(a, w, ucol, v, shr, shi, sc, ctx->d_partial,
-                                                             ctx->d_ticket + 1);
-    else
-      heis_apply_kernel<false><<<grid, 256, 0, ctx->stream>>>(a, w, ucol, v, shr, shi, sc, ctx->d_partial,
-                                                              ctx->d_ticket + 1);
-    CMB_CUDA(cudaGetLastError());
+    if (passes.empty()) plan_passes();
+    for (const HeisPass& ps : passes) {
+      CUtensorMap tm;
+      memset(&tm, 0, sizeof(tm));
+      if (ps.a != ps.tb) CMB_TRY(window_map(ps, w, &tm));
+      LaunchScope ls(ctx, "heisenberg_mf");
+      const long long ntiles = 1ll << (plan.Ll - ps.tb);
+      const int grid = int(std::min<long long>(ntiles, (long long)ctx->num_sms));
+#define CMB_HEIS_LAUNCH(C, F, L)                                                                                     \
+  do {                                                                                                               \
+    static bool attr = false;                                                                                        \
+    if (!attr) {                                                                                                     \
+      CMB_CUDA(cudaFuncSetAttribute(heis_apply_kernel<C, F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                    kHeisSmem));                                                                     \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    heis_apply_kernel<C, F, L><<<grid, kHeisThreads, kHeisSmem, ctx->stream>>>(a, ps, tm, w, ucol, v, shr, shi, sc,  \
+                                                                               ctx->d_partial, ctx->d_ticket + 1);   \
+  } while (0)
+      const int role = (ps.first ? 2 : 0) | (ps.last ? 1 : 0);
+      if (cplx) {
+        switch (role) {
+          case 3: CMB_HEIS_LAUNCH(true, true, true); break;
+          case 2: CMB_HEIS_LAUNCH(true, true, false); break;
+          case 1: CMB_HEIS_LAUNCH(true, false, true); break;
+          default: CMB_HEIS_LAUNCH(true, false, false); break;
+        }
+      } else {
+        switch (role) {
+          case 3: CMB_HEIS_LAUNCH(false, true, true); break;
+          case 2: CMB_HEIS_LAUNCH(false, true, false); break;
+          case 1: CMB_HEIS_LAUNCH(false, false, true); break;
+          default: CMB_HEIS_LAUNCH(false, false, false); break;
+        }
+      }
+#undef CMB_HEIS_LAUNCH
+      CMB_CUDA(cudaGetLastError());
+    }
     return CMB_OK;
   }
 

@@ -54,6 +54,24 @@ def cpu_sample(make_solver, m_sample, threads):
     return m_sample / (time.perf_counter() - t0)
 
 
+FAMS = ("cgs_dot", "cgs_update_dot", "cgs_update_norm", "spmv_sell", "heisenberg_mf", "gemv_dense", "vec_dot")
+
+
+def families(fn):
+    """per-family device time (ms) and launch count of one call of fn (CUDA events around every launch)"""
+    ctx.sync()
+    ctx.profile(True)
+    fn()
+    ctx.sync()
+    out = {}
+    for f in FAMS:
+        ms, cnt = ctx.profile_get(f)
+        if cnt:
+            out[f] = [round(ms, 3), cnt]
+    ctx.profile(False)
+    return out
+
+
 def emit(d):
     print(json.dumps(d), flush=True)
 
@@ -176,7 +194,8 @@ if "cfg5" in want:
     es.setComputeEigenvectorsOn(False).setReserveSize(m + 1)
     best, mean = timed(es.compute, reps=3)
     rr = es.ritzResiduals()
-    emit({"cfg": 5, "what": "matrix-free Heisenberg ring L=%d on ONE GPU (cfg 5 is L=30 on 8), Lanczos m=40" % L,
+    fam5 = families(es.compute)
+    emit({"cfg": 5, "families_ms": fam5, "what": "matrix-free Heisenberg ring L=%d on ONE GPU (cfg 5 is L=30 on 8), Lanczos m=40" % L,
           "gpu_it_per_s": m / best, "gpu_ms": best * 1e3, "algorithmic_GBps": es.deviceBytes() / best / 1e9,
           "lowest_ritz": float(es.eigenvalues()[0]), "E0_per_site": float(es.eigenvalues()[0]) / L,
           "ritz_residual": float(rr[0])})
