@@ -40,8 +40,8 @@ struct HeisPass {
   int h;      // global position of tile bit a (start of the window)
   int k0;     // this pass serves the bonds joining tile bits (k, k+1), k0 <= k < tb-1 ...
   int wrapb;  // ... and, when set, the periodic bond joining tile bits tb-1 and 0 (single rank only)
-  int first;  // writes u and v, adds the remote bonds and the shift
-  int last;   // computes the alpha dot
+  int main;   // the contiguous pass, run last: writes u, adds the remote bonds and the shift, computes the alpha dot
+  int rmw;    // adds to the v of the earlier passes (the first pass of an apply just writes v)
 };
 
 constexpr int kHeisConsumers = 512;  // 16 warps (128 registers each); thread 0 also feeds the ring
@@ -61,6 +61,12 @@ struct HeisArgs {
   int has_wrap, rt;  // bond (L-1, 0) across ranks
   const double* wrap;
   double J;
+  // peer-memory exchange: partners copy their slabs into this rank's receive buffer and then set flag[k] = seq;
+  // the contiguous pass waits for the flags named in flag_mask before it touches the slabs
+  const unsigned long long* flag;
+  unsigned long long seq;
+  unsigned flag_mask;
+  int* error;
 };
 
 // Two neighbouring tile elements (t0 even, t0 + 1): the unit of work of one thread.  For every bond that does not
@@ -110,8 +116,8 @@ struct HeisPair {
   }
 };
 
-// FIRST / LAST: role of the pass (compile time, so that the unrolled pair loop carries no uniform branches for them)
-template <bool CPLX, bool FIRST, bool LAST>
+// MAIN / RMW: role of the pass (compile time, so that the unrolled pair loop carries no uniform branches for them)
+template <bool CPLX, bool MAIN, bool RMW>
 __global__ void __launch_bounds__(kHeisThreads, 1)
 heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap tm, const double* __restrict__ w,
                   double* __restrict__ ucol, double* __restrict__ v, double shr, double shi, StepScalars sc,
@@ -128,6 +134,17 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
   const int npairs = 1 << (tb - 1);
   const int nmid = ps.h - ps.a;  // index bits between the contiguous run and the window
   const long long ntiles = 1ll << (a.Ll - tb);
+  if (MAIN && a.flag != nullptr && threadIdx.x < 32) {
+    if ((a.flag_mask >> threadIdx.x) & 1u) {
+      const long long t0 = clock64();
+      while (ld_acquire_sys_u64(a.flag + threadIdx.x) < a.seq) {
+        if (clock64() - t0 > (1ll << 32)) {  // bounded (~2 s): a missing partner raises the error flag
+          *a.error = 1;
+          break;
+        }
+      }
+    }
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kHeisStages; ++s) {
       mbar_init(&full[s], 1);
@@ -165,7 +182,7 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
     const int nlocal = (tb - 1 - ps.k0) + ps.wrapb;
     // bonds whose diagonal term this pass accounts for (the remote bonds ride with the first pass)
     const bool remote = (a.n_full | a.has_straddle | a.has_wrap) != 0;
-    const int nb_pass = nlocal + (FIRST ? a.aligned_uniform + a.n_full + a.has_straddle + a.has_wrap : 0);
+    const int nb_pass = nlocal + (MAIN ? a.aligned_uniform + a.n_full + a.has_straddle + a.has_wrap : 0);
     // pair g = threadIdx.x + 512 j  ->  tile element t0 = 2 g = tl + (j << 10); the tile -> global index map is a
     // bit deposit, so it splits into a per-thread part (hoisted) and a per-iteration part
     const int tl = 2 * threadIdx.x;  // < 1024
@@ -186,7 +203,7 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         yold[j] = Pair::zero();
-        if (!FIRST && int(threadIdx.x) + kHeisConsumers * j < npairs) yold[j] = Pair::load(v, base + s_iter(j));
+        if (RMW && int(threadIdx.x) + kHeisConsumers * j < npairs) yold[j] = Pair::load(v, base + s_iter(j));
       }
       mbar_wait(&full[st], ph);
       const double* sm = reinterpret_cast<const double*>(heis_smem + size_t(st) * kHeisTileBytes);
@@ -246,7 +263,7 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
             anti0 += bt;
             anti1 += 1 - bt;
           }
-          if (FIRST && remote) {
+          if (MAIN && remote) {
             anti0 += a.n_full;
             anti1 += a.n_full;
 #pragma unroll
@@ -282,18 +299,17 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
             y.i0 = (dg0 * x.i0 + hJ * acc[j].i0) * inv;
             y.i1 = (dg1 * x.i1 + hJ * acc[j].i1) * inv;
           }
-          if (FIRST) {
+          if (MAIN) {
             y.r0 += shr * u.r0, y.r1 += shr * u.r1;
             if constexpr (CPLX) {
               y.r0 -= shi * u.i0, y.r1 -= shi * u.i1;
               y.i0 += shr * u.i0 + shi * u.r0, y.i1 += shr * u.i1 + shi * u.r1;
             }
             u.store(ucol, s0);
-          } else {
-            y.add(yold[j]);
           }
+          if (RMW) y.add(yold[j]);
           y.store(v, s0);
-          if (LAST) {
+          if (MAIN) {
             d0 = fma(u.r0, y.r0, d0);
             d0 = fma(u.r1, y.r1, d0);
             if constexpr (CPLX) {
@@ -318,7 +334,7 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
       }
     }
   }
-  if (LAST) grid_sum_finalize<CPLX ? 2 : 1>(d0, d1, partial, ticket, sc.alpha_slot);
+  if (MAIN) grid_sum_finalize<CPLX ? 2 : 1>(d0, d1, partial, ticket, sc.alpha_slot);
 }
 
 // out[i] = w[2 i + parity] : the elements a wrap-bond partner needs
@@ -372,9 +388,45 @@ struct HeisenbergOp : cmb_op {
   double* d_pack = nullptr;  // packed parity half for the wrap bond
   std::vector<size_t> recv_off;
   std::vector<HeisPass> passes;
+  // peer-memory exchange (CUDA IPC + copy engines): every rank owns [flags | receive buffer 0 | receive buffer 1],
+  // mapped into its partners, which copy their slabs into it (cudaMemcpyAsync on side streams, overlapping the window
+  // passes) and then publish the exchange number in the flag of that bond.  NCCL send/recv is the fallback.
+  static constexpr int kMaxRemote = kMaxFull + 2;
+  static constexpr size_t kFlagBytes = 256;
+  static constexpr int kSeqSlots = 4096;
+  bool p2p = false;
+  void* p2p_base = nullptr;
+  void* p2p_mapped[kMaxPeers] = {};
+  size_t p2p_tot = 0;                           // doubles per receive buffer of this rank
+  std::vector<size_t> peer_off, peer_tot;       // per remote bond: where my slab goes in the partner's buffer / its size
+  unsigned long long xseq = 0;                  // exchanges enqueued so far (same on every rank)
+  unsigned long long* h_seq = nullptr;          // pinned source words of the flag copies
+  static constexpr int kMaxSplit = 4;            // a slab travels as up to 4 concurrent copies (one copy engine each)
+  int nsplit = 2;
+  cudaStream_t xstream[kMaxRemote][kMaxSplit] = {};
+  cudaEvent_t ev_ready = nullptr, ev_done[kMaxRemote] = {}, ev_chunk[kMaxRemote][kMaxSplit] = {};
   ~HeisenbergOp() override {
-    pool_free(ctx, d_recv);
-    pool_free(ctx, d_pack);
+    if (p2p) {
+      cudaStreamSynchronize(ctx->stream);
+      for (int i = 0; i < kMaxRemote; ++i) {
+        for (int c = 0; c < kMaxSplit; ++c) {
+          if (xstream[i][c]) {
+            cudaStreamSynchronize(xstream[i][c]);
+            cudaStreamDestroy(xstream[i][c]);
+          }
+          if (ev_chunk[i][c]) cudaEventDestroy(ev_chunk[i][c]);
+        }
+        if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+      }
+      if (ev_ready) cudaEventDestroy(ev_ready);
+      ipc_unshare(ctx, p2p_mapped);
+      cudaFree(p2p_base);
+      cudaFreeHost(h_seq);
+    }
+    if (ctx) {
+      pool_free(ctx, d_recv);
+      pool_free(ctx, d_pack);
+    }
   }
 
   HeisArgs base_args() const {
@@ -392,25 +444,27 @@ struct HeisenbergOp : cmb_op {
     passes.clear();
     const int Ll = plan.Ll, TB = cplx ? 12 : 13, arun = cplx ? 4 : 5, wb = TB - arun;
     const bool local_wrap = (plan.p == 0 && plan.nb == plan.L);
-    HeisPass q;
-    memset(&q, 0, sizeof(q));
-    q.tb = std::min(Ll, TB);
-    q.a = q.h = q.tb;
-    q.wrapb = (Ll <= TB && local_wrap) ? 1 : 0;
-    q.first = 1;
-    passes.push_back(q);
-    int next = q.tb - 1;  // first bond not served yet (bond b joins bits b and b+1)
+    HeisPass m;  // the contiguous pass: bonds 0 .. tb-2; runs last because it also consumes the remote slabs
+    memset(&m, 0, sizeof(m));
+    m.tb = std::min(Ll, TB);
+    m.a = m.h = m.tb;
+    m.wrapb = (Ll <= TB && local_wrap) ? 1 : 0;
+    m.main = 1;
+    int next = m.tb - 1;  // first bond not served yet (bond b joins bits b and b+1)
     while (next <= Ll - 2) {
+      HeisPass q;
       memset(&q, 0, sizeof(q));
       q.tb = TB;
       q.a = arun;
       q.h = std::min(next, Ll - wb);  // the last window is pulled down so that it ends at the top bit
       q.k0 = q.a + (next - q.h);
       q.wrapb = (q.h + wb == Ll && local_wrap) ? 1 : 0;
+      q.rmw = passes.empty() ? 0 : 1;
       next = q.h + wb - 1;
       passes.push_back(q);
     }
-    passes.back().last = 1;
+    m.rmw = passes.empty() ? 0 : 1;
+    passes.push_back(m);
   }
 
   // 3-D view of a local vector for the tiles of a window pass: {run, index bits between run and window, the rest}
@@ -442,8 +496,68 @@ struct HeisenbergOp : cmb_op {
       if (!r.needed) continue;
       tot += (r.kind == 3) ? slab : half;
     }
-    CMB_TRY(pool_alloc(ctx, &d_recv, sizeof(double) * std::max<size_t>(tot, 2)));
     CMB_TRY(pool_alloc(ctx, &d_pack, sizeof(double) * std::max<size_t>(half, 2)));
+    CMB_TRY(setup_p2p(tot));
+    if (!p2p) CMB_TRY(pool_alloc(ctx, &d_recv, sizeof(double) * std::max<size_t>(tot, 2)));
+    return CMB_OK;
+  }
+
+  static size_t plan_offsets(const HeisPlan& pl, size_t slab, std::vector<size_t>* off) {
+    size_t tot = 0;
+    for (auto& r : pl.remote) {
+      if (off) off->push_back(tot);
+      if (r.needed) tot += (r.kind == 3) ? slab : slab / 2;
+    }
+    return tot;
+  }
+
+  // Collective (every rank of the context creates the operator).  Failure of any step leaves p2p == false.
+  int setup_p2p(size_t tot) {
+    if (!ctx->mail_ok || getenv("CMPT_B200_NO_P2P_HALO") || int(plan.remote.size()) > kMaxRemote) return CMB_OK;
+    const size_t es = cplx ? 2 : 1, slab = size_t(n_local) * es;
+    const size_t bytes = kFlagBytes + 2 * sizeof(double) * std::max<size_t>(tot, 2);
+    void* base = nullptr;
+    if (cudaMalloc(&base, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      base = nullptr;
+    } else {
+      cudaMemsetAsync(base, 0, kFlagBytes, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+    }
+    void* mapped[kMaxPeers];
+    if (!ipc_share(ctx, base, mapped)) {
+      cudaFree(base);
+      cudaGetLastError();
+      return CMB_OK;
+    }
+    bool ok = cudaHostAlloc(reinterpret_cast<void**>(&h_seq), sizeof(unsigned long long) * kSeqSlots,
+                            cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming) == cudaSuccess;
+    if (const char* e = getenv("CMPT_B200_XCHG_SPLIT")) nsplit = std::max(1, std::min(kMaxSplit, atoi(e)));
+    for (size_t k = 0; k < plan.remote.size() && ok; ++k) {
+      ok = cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming) == cudaSuccess;
+      for (int c = 0; c < nsplit && ok; ++c)
+        ok = cudaStreamCreateWithFlags(&xstream[k][c], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ev_chunk[k][c], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) {  // local resource failure after the collective part: cannot fall back on one rank only
+      set_error("Heisenberg peer exchange: stream/event/pinned allocation failed");
+      return CMB_ERR_CUDA;
+    }
+    p2p = true;
+    p2p_base = base;
+    p2p_tot = std::max<size_t>(tot, 2);
+    for (int q = 0; q < ctx->nranks; ++q) p2p_mapped[q] = mapped[q];
+    peer_off.clear();
+    peer_tot.clear();
+    for (size_t k = 0; k < plan.remote.size(); ++k) {
+      HeisPlan pp;
+      pp.build(plan.L, plan.pbc, ctx->nranks, plan.remote[k].partner);
+      std::vector<size_t> off;
+      const size_t ptot = plan_offsets(pp, slab, &off);
+      peer_off.push_back(off[k]);  // both partners enumerate the remote bonds in the same order
+      peer_tot.push_back(std::max<size_t>(ptot, 2));
+    }
     return CMB_OK;
   }
 
@@ -479,18 +593,18 @@ struct HeisenbergOp : cmb_op {
       LaunchScope ls(ctx, "heisenberg_mf");
       const long long ntiles = 1ll << (plan.Ll - ps.tb);
       const int grid = int(std::min<long long>(ntiles, (long long)ctx->num_sms));
-#define CMB_HEIS_LAUNCH(C, F, L)                                                                                     \
+#define CMB_HEIS_LAUNCH(C, M, R)                                                                                     \
   do {                                                                                                               \
     static bool attr = false;                                                                                        \
     if (!attr) {                                                                                                     \
-      CMB_CUDA(cudaFuncSetAttribute(heis_apply_kernel<C, F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+      CMB_CUDA(cudaFuncSetAttribute(heis_apply_kernel<C, M, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                     kHeisSmem));                                                                     \
       attr = true;                                                                                                   \
     }                                                                                                                \
-    heis_apply_kernel<C, F, L><<<grid, kHeisThreads, kHeisSmem, ctx->stream>>>(a, ps, tm, w, ucol, v, shr, shi, sc,  \
+    heis_apply_kernel<C, M, R><<<grid, kHeisThreads, kHeisSmem, ctx->stream>>>(a, ps, tm, w, ucol, v, shr, shi, sc,  \
                                                                                ctx->d_partial, ctx->d_ticket + 1);   \
   } while (0)
-      const int role = (ps.first ? 2 : 0) | (ps.last ? 1 : 0);
+      const int role = (ps.main ? 2 : 0) | (ps.rmw ? 1 : 0);
       if (cplx) {
         switch (role) {
           case 3: CMB_HEIS_LAUNCH(true, true, true); break;
@@ -535,6 +649,7 @@ struct HeisenbergOp : cmb_op {
       bool has_wrap = false;
       for (auto& r : plan.remote) has_wrap |= (r.kind == 4);
       if (has_wrap) CMB_TRY(pack_wrap(w, 1 - rt, d_pack, sc.halt));
+      if (p2p) return apply_p2p(a, w, ucol, v, shr, shi, sc);
       auto chk = [&](int r, const char* what) -> int {
         if (r != 0) {
           set_error("%s failed: %s", what, ctx->nccl->GetErrorString ? ctx->nccl->GetErrorString(r) : "?");
@@ -568,6 +683,67 @@ struct HeisenbergOp : cmb_op {
       remote_args(a, d_recv);
     }
     return launch(a, w, ucol, v, shr, shi, sc);
+  }
+
+  // Exchange through peer memory.  The copies are unconditional (a halted chain still moves its stale w: the
+  // kernels are no-ops then, and every rank keeps the same exchange count).  Receive buffers alternate with the
+  // exchange number: a partner can only start exchange x+2 after it consumed my exchange x+1, which I sent after my
+  // contiguous pass of exchange x, so the buffer it overwrites is no longer being read.
+  int apply_p2p(HeisArgs& a, const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) {
+    const size_t es = cplx ? 2 : 1;
+    const size_t slab = size_t(n_local) * es, half = slab / 2;
+    const int rb0 = plan.rank & 1;
+    const unsigned long long x = ++xseq;
+    const size_t par = size_t(x & 1ull);
+    if ((x & 255ull) == 0)  // keeps the pinned flag words of exchanges still in flight from being reused
+      for (size_t k = 0; k < plan.remote.size(); ++k) CMB_CUDA(cudaStreamSynchronize(xstream[k][0]));
+    CMB_CUDA(cudaEventRecord(ev_ready, ctx->stream));  // w (and the packed wrap half) are final
+    unsigned mask = 0;
+    {
+      for (size_t k = 0; k < plan.remote.size(); ++k) {
+        const HeisRemote& r = plan.remote[k];
+        if (!r.needed) continue;
+        mask |= 1u << k;
+        const double* src = w;
+        size_t count = slab;
+        if (r.kind == 2) {
+          src = w + size_t(1 - rb0) * half;
+          count = half;
+        } else if (r.kind == 4) {
+          src = d_pack;
+          count = half;
+        }
+        char* pbase = static_cast<char*>(p2p_mapped[r.partner]);
+        double* dst = reinterpret_cast<double*>(pbase + kFlagBytes) + par * peer_tot[k] + peer_off[k];
+        unsigned long long* word = h_seq + ((x * kMaxRemote + k) % kSeqSlots);
+        *word = x;
+        // the slab goes as nsplit concurrent copies; the flag follows on stream 0 once all of them are done
+        const int ns = (count >= (size_t(1) << 16)) ? nsplit : 1;
+        const size_t chunk = ((count + ns - 1) / ns + 1) & ~size_t(1);
+        for (int c = 0; c < ns; ++c) {
+          const size_t b = std::min(count, size_t(c) * chunk), e = std::min(count, b + chunk);
+          CMB_CUDA(cudaStreamWaitEvent(xstream[k][c], ev_ready, 0));
+          if (e > b)
+            CMB_CUDA(cudaMemcpyAsync(dst + b, src + b, sizeof(double) * (e - b), cudaMemcpyDefault, xstream[k][c]));
+          if (c > 0) CMB_CUDA(cudaEventRecord(ev_chunk[k][c], xstream[k][c]));
+        }
+        for (int c = 1; c < ns; ++c) CMB_CUDA(cudaStreamWaitEvent(xstream[k][0], ev_chunk[k][c], 0));
+        CMB_CUDA(cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(pbase) + k, word, sizeof(unsigned long long),
+                                 cudaMemcpyDefault, xstream[k][0]));
+        CMB_CUDA(cudaEventRecord(ev_done[k], xstream[k][0]));
+      }
+    }
+    const double* recv = reinterpret_cast<const double*>(static_cast<char*>(p2p_base) + kFlagBytes) + par * p2p_tot;
+    remote_args(a, recv);
+    a.flag = static_cast<const unsigned long long*>(p2p_base);
+    a.seq = x;
+    a.flag_mask = mask;
+    a.error = ctx->d_mail_error;
+    CMB_TRY(launch(a, w, ucol, v, shr, shi, sc));
+    // whoever overwrites w or the pack buffer next must come after the copies that read them
+    for (size_t k = 0; k < plan.remote.size(); ++k)
+      if (mask & (1u << k)) CMB_CUDA(cudaStreamWaitEvent(ctx->stream, ev_done[k], 0));
+    return CMB_OK;
   }
 };
 

@@ -94,8 +94,18 @@ if "cfg5" in want:
     best = timed(es.compute, reps=2)
     rr = es.ritzResiduals()
     byts = dist.all_sum(es.deviceBytes())
+    ctx.sync()
+    ctx.profile(True)
+    es.compute()
+    ctx.sync()
+    fams = {}
+    for f in ("cgs_dot", "cgs_update_dot", "cgs_update_norm", "heisenberg_mf", "halo_pack", "nccl_allreduce"):
+        ms, cnt = ctx.profile_get(f)
+        if cnt:
+            fams[f] = [round(ms, 2), cnt]
+    ctx.profile(False)
     if rank == 0:
-        print(json.dumps({"cfg": 5, "n_gpus": world, "what": "matrix-free Heisenberg ring L=%d, Lanczos m=%d" % (L, m),
+        print(json.dumps({"cfg": 5, "families_ms_rank0": fams, "n_gpus": world, "what": "matrix-free Heisenberg ring L=%d, Lanczos m=%d" % (L, m),
                           "it_per_s": m / best, "ms": best * 1e3, "algorithmic_GBps_total": byts / best / 1e9,
                           "lowest_ritz": float(es.eigenvalues()[0]), "E0_per_site": float(es.eigenvalues()[0]) / L,
                           "ritz_residual": float(rr[0])}), flush=True)
