@@ -285,7 +285,7 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
     if (push.P > 1) {
       __threadfence_system();
       asm volatile("bar.sync 9, %0;" ::"r"(kConsumerWarps * 32) : "memory");
-      if (threadIdx.x == 0) mail_publish(push);
+      mail_publish(push, threadIdx.x);
     }
   }
 }

@@ -49,9 +49,10 @@ __device__ __forceinline__ double mail_sum(const MailPull& m, int idx) {
 __device__ __forceinline__ void mail_push_value(const MailPush& m, int idx, double v) {
   for (int q = 0; q < m.P; ++q) st_relaxed_sys_f64(m.data[q] + m.rank * kMailStride + idx, v);
 }
-// Publish: call by ONE thread after all pushing threads fenced (__threadfence_system) and synchronised.
-__device__ __forceinline__ void mail_publish(const MailPush& m) {
-  for (int q = 0; q < m.P; ++q) st_release_sys_u64(m.flag[q] + m.rank, m.seq);
+// Publish: called by the first m.P threads of the CTA (one peer each, so that the P release stores and their NVLink
+// round trips overlap) after all pushing threads fenced (__threadfence_system) and synchronised.
+__device__ __forceinline__ void mail_publish(const MailPush& m, int q) {
+  if (q < m.P) st_release_sys_u64(m.flag[q] + m.rank, m.seq);
 }
 
 // Consumer side of the peer-memory halo exchange: wait until every peer has published the exchange the preceding

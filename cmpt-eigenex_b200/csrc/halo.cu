@@ -129,12 +129,13 @@ halo_push_kernel(const double* __restrict__ w, const int* __restrict__ idx, Halo
   }
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(hp.ticket, 1u);
-    if (prev == gridDim.x - 1) {
-      __threadfence_system();
-      for (int q = 0; q < hp.P; ++q)
-        if (q != hp.rank) st_release_sys_u64(hp.flag[q], seq);
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = (atomicAdd(hp.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    // one peer per thread: the release stores (and their NVLink round trips) overlap
+    if (threadIdx.x < hp.P && int(threadIdx.x) != hp.rank) st_release_sys_u64(hp.flag[threadIdx.x], seq);
+    if (threadIdx.x == 0) {
       *hp.xseq = seq;
       *hp.ticket = 0u;
     }
