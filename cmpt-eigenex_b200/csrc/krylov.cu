@@ -51,6 +51,11 @@ struct cmb_krylov {
   double residue = 0.0;  // Arnoldi: last residual norm (host copy)
   double bytes = 0.0;
   double *tmp1 = nullptr, *tmp2 = nullptr, *tmpz = nullptr;
+  // Ritz-vector assembly: two output buffers so that the device->host copy of one vector (copy stream) overlaps the
+  // assembly of the next
+  double* xout[2] = {nullptr, nullptr};
+  size_t xout_doubles = 0;
+  cudaEvent_t ev_x[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
   unsigned long long* d_idx = nullptr;
 
   double* col(int j) const { return segs[j / seg_cols] + int64_t(j % seg_cols) * ld; }
@@ -382,6 +387,11 @@ int cmb_krylov_destroy(cmb_krylov* K) {
   cudaFree(K->tmp1);
   cudaFree(K->tmp2);
   cudaFree(K->tmpz);
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(K->xout[b]);
+    if (K->ev_x[b]) cudaEventDestroy(K->ev_x[b]);
+    if (K->ev_c[b]) cudaEventDestroy(K->ev_c[b]);
+  }
   cudaFree(K->d_idx);
   if (K->h_stage) cudaFreeHost(K->h_stage);
   delete K;
@@ -829,30 +839,45 @@ int cmb_krylov_ritz_vectors(cmb_krylov* K, cmb_dtype coef_dtype, const void* coe
   if (nev == 0) return CMB_OK;
   const int ces = ccplx ? 2 : 1;
   const bool widen = ccplx && !K->cplx;  // real basis, complex coefficients (ArnoldiEigenSolver<double>)
-  CMB_TRY(ensure_tmp(K, &K->tmp1, K->ld));
   if (widen) {
+    CMB_TRY(ensure_tmp(K, &K->tmp1, K->ld));
     CMB_TRY(ensure_tmp(K, &K->tmp2, K->ld));
-    CMB_TRY(ensure_tmp(K, &K->tmpz, 2 * K->ld));
   }
+  const size_t out_need = size_t(widen ? 2 * K->ld : K->ld);
+  if (K->xout_doubles < out_need) {
+    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(K->xout[b]);
+      K->xout[b] = nullptr;
+    }
+    K->xout_doubles = 0;
+  }
+  for (int b = 0; b < 2; ++b) {
+    CMB_TRY(ensure_tmp(K, &K->xout[b], out_need));
+    if (!K->ev_x[b]) CMB_CUDA(cudaEventCreateWithFlags(&K->ev_x[b], cudaEventDisableTiming));
+    if (!K->ev_c[b]) CMB_CUDA(cudaEventCreateWithFlags(&K->ev_c[b], cudaEventDisableTiming));
+  }
+  K->xout_doubles = std::max(K->xout_doubles, out_need);
   std::vector<Chunk> chunks;
   contiguous_chunks(K, K->ndefl, K->ndefl + int(ncoef), chunks);
   CMB_TRY(ensure_stage(K, size_t(nev) * size_t(4 * ncoef + 8)));  // one staging slice per vector: no host sync in the loop
   const double* cf = static_cast<const double*>(coef);
   const size_t out_es = ccplx ? 2 : 1;
+  const size_t out_ld = out_need;
   for (int64_t e = 0; e < nev; ++e) {
     double* hs = K->h_stage + size_t(e) * size_t(4 * ncoef + 8);
     const double* ce = cf + size_t(e) * ldc * ces;
-    double* xdev = nullptr;
+    const int b = int(e & 1);
+    double* xdev = K->xout[b];
+    if (e >= 2) CMB_CUDA(cudaStreamWaitEvent(ctx->stream, K->ev_c[b], 0));  // its previous content is on the host
     if (ncoef == 0) {
-      CMB_CUDA(cudaMemsetAsync(K->tmp1, 0, sizeof(double) * K->ld, ctx->stream));
+      CMB_CUDA(cudaMemsetAsync(xdev, 0, sizeof(double) * out_ld, ctx->stream));
       CMB_CUDA(cudaMemsetAsync(K->scal + 1, 0, sizeof(double), ctx->stream));
-      xdev = K->tmp1;
     } else if (!widen) {
       // x = 0 - V (-coef)
       for (int64_t m = 0; m < ncoef * ces; ++m) hs[m] = -ce[m];
       CMB_CUDA(cudaMemcpyAsync(K->h1, hs, sizeof(double) * ncoef * ces, cudaMemcpyHostToDevice, ctx->stream));
-      CMB_TRY(subtract_cols(K, chunks, K->h1, nullptr, K->tmp1, K->scal + 1, "ritz_assemble"));
-      xdev = K->tmp1;
+      CMB_TRY(subtract_cols(K, chunks, K->h1, nullptr, xdev, K->scal + 1, "ritz_assemble"));
     } else {
       for (int64_t m = 0; m < ncoef; ++m) {
         hs[m] = -ce[2 * m];
@@ -864,12 +889,11 @@ int cmb_krylov_ritz_vectors(cmb_krylov* K, cmb_dtype coef_dtype, const void* coe
       {
         LaunchScope ls(ctx, "vec_scale");
         const int grid = int(std::max<long long>(1, std::min<long long>((K->ld + 255) / 256, (long long)ctx->num_sms * 8)));
-        interleave_kernel<<<grid, 256, 0, ctx->stream>>>(K->tmp1, K->tmp2, K->tmpz, K->ld);
+        interleave_kernel<<<grid, 256, 0, ctx->stream>>>(K->tmp1, K->tmp2, xdev, K->ld);
         add2_kernel<<<1, 1, 0, ctx->stream>>>(K->scal + 2, K->scal + 3, K->scal + 1);
         ctx->launches++;
       }
       CMB_CUDA(cudaGetLastError());
-      xdev = K->tmpz;
     }
     // phase of the first non-zero element (lanczos.hpp:806-813) and normalisation (:816)
     // global index of the first non-zero element (min over ranks); its owner contributes the value, which is
@@ -879,11 +903,16 @@ int cmb_krylov_ritz_vectors(cmb_krylov* K, cmb_dtype coef_dtype, const void* coe
     CMB_TRY(vec_pick_element(ctx, xdev, K->d_idx, K->row_begin, K->n_local, int(out_es), K->scal + 6));
     CMB_TRY(allreduce_sum_f64(ctx, K->scal + 6, out_es));
     const double* phase_src = K->scal + 6;  // (0,0) when the vector is identically zero: no phase change
-    CMB_TRY(vec_scale_phase(ctx, ccplx, xdev, K->scal + 1, phase_src, widen ? 2 * K->ld : K->ld));
+    CMB_TRY(vec_scale_phase(ctx, ccplx, xdev, K->scal + 1, phase_src, out_ld));
+    // device -> host on the copy stream: overlaps the assembly of the next vector
+    CMB_CUDA(cudaEventRecord(K->ev_x[b], ctx->stream));
+    CMB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, K->ev_x[b], 0));
     CMB_CUDA(cudaMemcpyAsync(static_cast<char*>(x_host) + size_t(e) * ldx * out_es * sizeof(double), xdev,
-                             sizeof(double) * K->n_local * out_es, cudaMemcpyDeviceToHost, ctx->stream));
+                             sizeof(double) * K->n_local * out_es, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CMB_CUDA(cudaEventRecord(K->ev_c[b], ctx->copy_stream));
   }
   CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  CMB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   return CMB_OK;
 }
 
