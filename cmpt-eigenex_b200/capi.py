@@ -89,6 +89,7 @@ def _declare(L):
         "cmb_lanczos_step": (i32, [vp, vp, dbl, i64, dbl, P(dbl), P(dbl), P(i32)]),
         "cmb_lanczos_run": (i32, [vp, vp, dbl, i64, dbl, i64, vp, vp, P(i64), P(i32)]),
         "cmb_lanczos_residual_norm": (i32, [vp, P(dbl)]),
+        "cmb_lanczos_thick_restart": (i32, [vp, P(dbl), i64, i64, i64]),
         "cmb_arnoldi_run": (i32, [vp, vp, vp, dbl, i64, vp, i64, vp, P(i64), P(i32)]),
         "cmb_arnoldi_step": (i32, [vp, vp, vp, dbl, vp, P(dbl), P(i32)]),
         "cmb_krylov_ritz_vectors": (i32, [vp, i32, vp, i64, i64, i64, vp, i64]),

@@ -633,6 +633,46 @@ int cmb_lanczos_residual_norm(cmb_krylov* K, double* out) {
   return CMB_OK;
 }
 
+// Thick restart (Wu & Simon 2000), additive.  State on entry: Krylov vectors u_0..u_m (nk = m+1), v = (A+shift) u_m,
+// alpha_m known.  The caller diagonalised the projected matrix of the first m vectors and passes the m x nkeep
+// coefficients of the Ritz vectors to keep.  The basis becomes [V_m coef, u_m] (nkeep + 1 vectors); v and alpha_m stay,
+// so the next Lanczos step (full reorthogonalisation) continues from u_m against the compressed basis.
+int cmb_lanczos_thick_restart(cmb_krylov* K, const double* coef, int64_t ldc, int64_t m, int64_t nkeep) {
+  CMB_REQUIRE(K && coef, "null argument");
+  CMB_REQUIRE(m >= 1 && m == K->nk - 1 && nkeep >= 1 && nkeep <= m && ldc >= m, "bad shape for a thick restart");
+  cmb_ctx* ctx = K->ctx;
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  const int nk = K->nk;
+  CMB_TRY(ensure_cols(K, K->ndefl + nk + int(nkeep)));  // scratch columns behind the basis
+  std::vector<Chunk> chunks;
+  contiguous_chunks(K, K->ndefl, K->ndefl + int(m), chunks);
+  const int es = K->es;
+  CMB_TRY(ensure_stage(K, size_t(nkeep) * size_t(m) * es + 8));
+  for (int64_t i = 0; i < nkeep; ++i) {
+    double* hs = K->h_stage + size_t(i) * size_t(m) * es;
+    for (int64_t r = 0; r < m; ++r) {
+      hs[r * es] = -coef[size_t(i) * ldc + r];
+      if (es == 2) hs[r * es + 1] = 0.0;
+    }
+    CMB_CUDA(cudaMemcpyAsync(K->h1, hs, sizeof(double) * m * es, cudaMemcpyHostToDevice, ctx->stream));
+    CMB_TRY(subtract_cols(K, chunks, K->h1, nullptr, K->col(K->ndefl + nk + int(i)), K->scal + 1, "ritz_assemble"));
+    K->bytes += (double(m) + 1.0) * double(K->n_local) * (K->cplx ? 16.0 : 8.0);
+  }
+  const size_t colbytes = sizeof(double) * size_t(K->ld);
+  for (int64_t i = 0; i < nkeep; ++i)
+    CMB_CUDA(cudaMemcpyAsync(K->col(K->ndefl + int(i)), K->col(K->ndefl + nk + int(i)), colbytes, cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+  if (nkeep != m) {
+    CMB_CUDA(cudaMemcpyAsync(K->col(K->ndefl + int(nkeep)), K->col(K->ndefl + int(m)), colbytes, cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+    CMB_CUDA(cudaMemcpyAsync(K->alpha_dev + size_t(nkeep) * 2, K->alpha_dev + size_t(m) * 2, sizeof(double) * 2,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  K->nk = int(nkeep) + 1;
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));  // the staging slices are reused by the next call
+  return CMB_OK;
+}
+
 int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double threshold, int64_t nsteps, void* hcols,
                     int64_t ldh, double* residues, int64_t* steps_done, int* status) {
   CMB_TRY(check_pair(K, op));

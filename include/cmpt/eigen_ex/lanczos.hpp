@@ -218,6 +218,7 @@ class LanczosBase {
   // computed data: the vectors live on the device; alpha/beta are mirrored on the host
   Index iterations_;
   Index nvectors_;
+  Index arrow_;  // size of the arrowhead block after a thick restart (0: tridiagonal)
   mutable std::vector<VectorType> lanczosvectors_;  // host cache of the device basis, filled on demand
   std::vector<RealScalar> alpha_;
   std::vector<RealScalar> beta_;
@@ -240,12 +241,15 @@ class LanczosBase {
   }
   const std::vector<RealScalar>& alpha() const { return alpha_; }
   const std::vector<RealScalar>& beta() const { return beta_; }
+  /// additive: > 0 after thickRestart(k): the projected matrix is then diag(alpha) with T(i,k) = T(k,i) = beta[i] for
+  /// i < k (arrowhead) and T(i,i+1) = T(i+1,i) = beta[i] for i >= k (tridiagonal tail); 0 = plain tridiagonal
+  Index arrowSize() const { return arrow_; }
   cmb_krylov* deviceState() const { return dev_.handle(); }
   /// algorithmic bytes moved by the Krylov steps so far
   double deviceBytes() const { return dev_.ready() ? cmb_krylov_bytes(dev_.handle()) : 0.0; }
 
  public:
-  LanczosBase() : iterations_(0), nvectors_(0) { setAllSettingsDefault(); }
+  LanczosBase() : iterations_(0), nvectors_(0), arrow_(0) { setAllSettingsDefault(); }
 
   /// default settings; does NOT clear computed data (lanczos.hpp:260-271)
   LanczosBase& setAllSettingsDefault() {
@@ -263,6 +267,7 @@ class LanczosBase {
   void clearLanczosSteps() {
     iterations_ = 0;
     nvectors_ = 0;
+    arrow_ = 0;
     lanczosvectors_.clear();
     alpha_.clear();
     beta_.clear();
@@ -313,6 +318,28 @@ class LanczosBase {
     nvectors_ += done;
     iterations_ += nbeta;
     return done;
+  }
+
+  /// additive: thick restart.  With Lanczos vectors u_0..u_m, keeps the k Ritz pairs
+  /// (theta[i], V_m coef(:,i)) of the projected matrix of u_0..u_{m-1} — coef is m x k column-major — plus u_m:
+  /// the basis becomes [y_1..y_k, u_m], alpha = [theta, alpha_m], beta[i] = couplings[i] (= last-row component of
+  /// coef(:,i) times the last beta, supplied by the caller).  Needs reorthogonalizeInterval() == 1.
+  void thickRestart(const std::vector<RealScalar>& coef, const std::vector<RealScalar>& theta,
+                    const std::vector<RealScalar>& couplings) {
+    const Index m = nvectors_ - 1, k = static_cast<Index>(theta.size());
+    if (m < 1 || k < 1 || k > m || static_cast<Index>(coef.size()) != m * k ||
+        static_cast<Index>(couplings.size()) != k)
+      throw LanczosException("thickRestart: bad shapes");
+    if (reorthogonalizeInterval_ != 1) throw LanczosException("thickRestart needs full reorthogonalisation");
+    std::vector<double> c(coef.begin(), coef.end());
+    detail::check(cmb_lanczos_thick_restart(dev_.handle(), c.data(), m, m, k), "cmb_lanczos_thick_restart");
+    const RealScalar alpha_m = alpha_[static_cast<std::size_t>(m)];
+    alpha_.assign(theta.begin(), theta.end());
+    alpha_.push_back(alpha_m);
+    beta_.assign(couplings.begin(), couplings.end());
+    nvectors_ = k + 1;
+    arrow_ = k;
+    lanczosvectors_.clear();
   }
 
  protected:

@@ -147,6 +147,12 @@ int cmb_lanczos_run(cmb_krylov* k, cmb_op* op, double shift, int64_t interval, d
  * produce, i.e. the factor of the Ritz residual bounds |beta_next * S(last,i)|.  Does not change the state. */
 int cmb_lanczos_residual_norm(cmb_krylov* k, double* out);
 
+/* Thick restart (additive; Wu & Simon 2000).  With Krylov vectors u_0..u_m on the device, replaces them by
+ * [V_m coef(:,0..nkeep), u_m]: coef is the m x nkeep (column-major, leading dimension ldc, real) matrix of Ritz
+ * coefficient vectors of the projected matrix of u_0..u_{m-1}.  v = (A+shift) u_m and alpha_m are kept, so the next
+ * cmb_lanczos_run step continues from u_m (full reorthogonalisation only). */
+int cmb_lanczos_thick_restart(cmb_krylov* k, const double* coef, int64_t ldc, int64_t m, int64_t nkeep);
+
 /* updateArnoldiSteps() (arnoldi.hpp:312-392).  hcol receives h(0..ncols-1, ncols-1) of the new column
  * (dtype elements); *residue the new residual norm.  shift points at one dtype element. */
 int cmb_arnoldi_step(cmb_krylov* k, cmb_op* op, const void* shift, double threshold, void* hcol,

@@ -82,3 +82,15 @@ def test_sample_triplets_on_ramp():
     low = float(re.search(r"device  : (\S+)", out).group(1))
     exact = float(re.search(r"exact lowest: (\S+)", out).group(1))
     assert exact - 1e-12 <= low < exact + 1e-5  # Ritz value from above; 120 steps do not converge it further
+
+
+@pytest.mark.gpu
+def test_sample_thick_restart_and_deflation():
+    # thick-restart Lanczos with a bounded basis (closed-form spectrum, explicit residuals) and
+    # the degenerate pair of the square Laplacian found through setOrthogonalizingVectors
+    out = _run("sample_thick_restart")
+    assert out.strip().endswith("PASS"), out
+    m = re.search(r"rect \d+x\d+: (\d+) restarts, (\d+) operator applications, (\d+)/6 converged", out)
+    assert int(m.group(1)) > 0 and int(m.group(3)) == 6
+    assert float(re.search(r"rect: max \|theta - exact\| = (\S+),", out).group(1)) < 1e-9
+    assert abs(float(re.search(r"<x_12 \| x_21> = (\S+)", out).group(1))) < 1e-8
