@@ -253,7 +253,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count() - launches0  # kernels of this library launched inside the timed region
     fams = {}
-    for fam in ("cgs_dot", "cgs_update_dot", "cgs_update_norm", "spmv_sell", "vec_dot", "nccl_allreduce", "nccl_halo", "halo_push",
+    for fam in ("cgs_dot", "cgs_update_dot", "cgs_update_norm", "spmv_sell", "vec_dot", "nccl_allreduce", "nccl_halo",
                 "halo_pack"):
         fams[fam] = ctx.profile_get(fam)
     ctx.profile(False)

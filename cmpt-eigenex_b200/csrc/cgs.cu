@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x, double* __restrict__ y,
            const double* __restrict__ hin, double* __restrict__ hout, double* __restrict__ partial,
            unsigned* __restrict__ ticket, const int* __restrict__ halt, int ncols, int cg, int ntiles, int stages,
-           MailPull pull, MailPush push) {
+           MailPull pull, MailPush push, int norm_trick) {
   using Cfg = CgsCfg<WC>;
   constexpr int T = Cfg::T, WR = Cfg::WR;
   constexpr int ES = CPLX ? 2 : 1;  // doubles per coefficient
@@ -202,7 +202,11 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
           }
         }
       }
-    } else if (gc == 0) {
+      if (MODE == 1 && norm_trick && gc == 0) {
+        nrm = fma(yv.x, yv.x, nrm);
+        nrm = fma(yv.y, yv.y, nrm);
+      }
+    } else if (gc == 0 && !norm_trick) {
       nrm = fma(yv.x, yv.x, nrm);
       nrm = fma(yv.y, yv.y, nrm);
     }
@@ -214,8 +218,26 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
     }
   }
 
+  // ===== UPDATE_NORM without a reduction of its own (norm_trick): beta^2 from the reduced coefficients =====
+  __shared__ double s_fin[kConsumerWarps * 32 + 8];
+  if (MODE == 2 && norm_trick) {
+    if (blockIdx.x != 0) return;
+    const int nh = ncols * ES;
+    for (int t = threadIdx.x; t <= nh; t += kConsumerWarps * 32)
+      s_fin[t] = (pull.P > 1) ? mail_sum(pull, t) : hin[t];
+    asm volatile("bar.sync 9, %0;" ::"r"(kConsumerWarps * 32) : "memory");
+    if (threadIdx.x == 0) {
+      double acc = 0.0;
+      for (int t = 0; t < nh; ++t) acc = fma(s_fin[t], s_fin[t], acc);
+      const double b2 = s_fin[nh] - acc;
+      hout[0] = b2 > 0.0 ? b2 : 0.0;
+    }
+    return;
+  }
+
   // ===== CTA-level reduction =====
   const int nred = (MODE <= 1) ? nc * ES : 1;  // values per CTA
+  __shared__ double s_nrm[kConsumerWarps];
   if (MODE <= 1) {
 #pragma unroll
     for (int j = 0; j < CG; ++j) {
@@ -229,17 +251,28 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
         }
       }
     }
+    if (MODE == 1 && norm_trick) {
+      const double sn = warp_sum(nrm);
+      if (lane == 0 && gc == 0) s_nrm[gr] = sn;
+    }
   } else {
     const double sn = warp_sum(nrm);
     if (lane == 0 && gc == 0) red[gr] = sn;
   }
   asm volatile("bar.sync 9, %0;" ::"r"(kConsumerWarps * 32) : "memory");
-  const int nout = (MODE <= 1) ? ncols * ES : 1;
+  const int nbase = (MODE <= 1) ? ncols * ES : 1;
+  const int nout = nbase + ((MODE == 1 && norm_trick) ? 1 : 0);  // values this launch reduces over the grid
   for (int t = threadIdx.x; t < nred; t += kConsumerWarps * 32) {
     double sacc = 0.0;
 #pragma unroll
     for (int g = 0; g < WR; ++g) sacc += (MODE <= 1) ? red[g * NCMAX * ES + t] : red[g];
-    if (t < nout) partial[size_t(blockIdx.x) * kPartialStride + t] = sacc;
+    if (t < nbase) partial[size_t(blockIdx.x) * kPartialStride + t] = sacc;
+  }
+  if (MODE == 1 && norm_trick && threadIdx.x == 0) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int g = 0; g < WR; ++g) sacc += s_nrm[g];
+    partial[size_t(blockIdx.x) * kPartialStride + nbase] = sacc;
   }
   // ===== last CTA sums the per-CTA partials in CTA order =====
   __threadfence();
@@ -254,7 +287,6 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
     // Sum the per-CTA partials in a fixed pattern (deterministic): G thread groups take interleaved CTAs with
     // four independent accumulators each (keeps ~4G loads in flight instead of one serial chain of gridDim.x
     // L2 round trips), then one thread per value adds the G group sums in order.
-    __shared__ double s_fin[kConsumerWarps * 32];
     const int tid = threadIdx.x, nb = int(gridDim.x);
     int G = (kConsumerWarps * 32) / nout;
     G = G < 1 ? 1 : (G > 16 ? 16 : G);
@@ -331,7 +363,7 @@ static int launch_cfg(cmb_ctx* ctx, const CgsPass& a, int cg) {
   {
     LaunchScope ls(ctx, a.family ? a.family : fam[MODE]);
     kern<<<grid, kThreads, smem, ctx->stream>>>(tm, a.x, a.y, a.hin, a.hout, ctx->d_partial, ctx->d_ticket, a.halt,
-                                                a.ncols, cg, ntiles, stages, a.pull, a.push);
+                                                a.ncols, cg, ntiles, stages, a.pull, a.push, a.norm_trick);
   }
   CMB_CUDA(cudaGetLastError());
   return CMB_OK;

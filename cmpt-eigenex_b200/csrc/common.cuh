@@ -99,8 +99,10 @@ struct HaloPush {                       // producer side (kernel argument)
   double* dst[kMaxPeers];               // where this rank's block starts in the peer's buffer 0
   long long stride[kMaxPeers];          // distance (doubles) between the peer's buffers 0 and 1
   unsigned long long* flag[kMaxPeers];  // this rank's flag in the peer's memory
-  unsigned long long* xseq = nullptr;   // local count of executed exchanges
+  unsigned long long* xseq = nullptr;   // local count of executed exchanges (advanced by the consuming kernel)
   unsigned* ticket = nullptr;
+  const int* idx = nullptr;             // local rows to send, grouped by peer (send_off)
+  int npush = 1;                        // CTAs of the consuming kernel that take part in the push
 };
 struct HaloPull {                       // consumer side (kernel argument)
   const double* base = nullptr;         // receive buffer 0 (or the NCCL receive buffer when flag == nullptr)

@@ -55,29 +55,47 @@ __device__ __forceinline__ void mail_publish(const MailPush& m, int q) {
   if (q < m.P) st_release_sys_u64(m.flag[q] + m.rank, m.seq);
 }
 
-// Consumer side of the peer-memory halo exchange: wait until every peer has published the exchange the preceding
-// push kernel of this rank counted in *xseq, then return the receive buffer of that parity.  Called by all threads
-// of the CTA.  The spin is bounded like mail_wait.
-__device__ __forceinline__ const double* halo_acquire(const HaloPull& h) {
-  if (!h.flag) return h.base;
-  __shared__ unsigned long long s_halo_seq;
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    const unsigned long long seq = *h.xseq;
-    if (lane < h.P && lane != h.rank) {
-      const long long t0 = clock64();
-      while (ld_acquire_sys_u64(h.flag + lane) < seq) {
-        if (clock64() - t0 > (1ll << 32)) {
-          *h.error = 1;
-          break;
-        }
+// ---- halo exchange through peer memory, fused into the operator kernel (halo.cu sets the arguments up) -------
+// Producer part, executed by the CTAs with blockIdx.x < hp.npush at the start of the kernel: the values the peers
+// need go straight into their receive buffers (NVLink stores); the pusher that finishes last raises this rank's
+// flag at every peer (one peer per thread).  Must be called by all threads of those CTAs.
+template <int ES>
+__device__ __forceinline__ void halo_push_part(const HaloPush& hp, const double* __restrict__ w, unsigned long long seq) {
+  const long long stride = (long long)hp.npush * blockDim.x;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int q = 0; q < hp.P; ++q) {
+    const long long a = hp.send_off[q], b = hp.send_off[q + 1];
+    if (b <= a) continue;
+    double* dst = hp.dst[q] + (seq & 1ull) * hp.stride[q];
+    for (long long i = a + t; i < b; i += stride) {
+      const long long s = hp.idx[i];
+#pragma unroll
+      for (int e = 0; e < ES; ++e) dst[(i - a) * ES + e] = w[s * ES + e];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int s_push_last;
+  if (threadIdx.x == 0) s_push_last = (atomicAdd(hp.ticket, 1u) == unsigned(hp.npush) - 1u);
+  __syncthreads();
+  if (s_push_last) {
+    if (int(threadIdx.x) < hp.P && int(threadIdx.x) != hp.rank) st_release_sys_u64(hp.flag[threadIdx.x], seq);
+    if (threadIdx.x == 0) *hp.ticket = 0u;
+  }
+}
+// Consumer part (whole warp): wait until every peer has published exchange `seq`.  Bounded like mail_wait.
+__device__ __forceinline__ void halo_wait_warp(const HaloPull& h, unsigned long long seq) {
+  const int lane = threadIdx.x & 31;
+  if (lane < h.P && lane != h.rank) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(h.flag + lane) < seq) {
+      if (clock64() - t0 > (1ll << 32)) {
+        *h.error = 1;
+        break;
       }
     }
-    __syncwarp();
-    if (lane == 0) s_halo_seq = seq;
   }
-  __syncthreads();
-  return h.base + (s_halo_seq & 1ull) * h.stride;
+  __syncwarp();
 }
 
 __device__ __forceinline__ bool step_prologue(const StepScalars& sc, double& inv) {
@@ -104,7 +122,7 @@ __device__ __forceinline__ bool step_prologue(const StepScalars& sc, double& inv
 // Block-level sum of `nval` (1 or 2) per-thread doubles, per-CTA partial, last-CTA deterministic final sum
 // written to out[0..nval).  Must be called by every thread of every CTA of the grid exactly once.
 template <int NVAL>
-__device__ __forceinline__ void grid_sum_finalize(double a0, double a1, double* partial, unsigned* ticket,
+__device__ __forceinline__ bool grid_sum_finalize(double a0, double a1, double* partial, unsigned* ticket,
                                                   double* out) {
   __shared__ double s_red[2][32];
   __shared__ int s_last;
@@ -145,6 +163,7 @@ __device__ __forceinline__ void grid_sum_finalize(double a0, double a1, double* 
       *ticket = 0u;
     }
   }
+  return s_last != 0;  // true in the CTA that finished last (every other CTA has left the kernel body by then)
 }
 
 }  // namespace cmb

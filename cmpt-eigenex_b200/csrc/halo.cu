@@ -107,41 +107,6 @@ __global__ void pack_kernel(const double* __restrict__ w, const int* __restrict_
   }
 }
 
-// Peer-memory variant of pack + send: the gathered values go straight into each peer's receive buffer (NVLink
-// stores), then the last CTA raises this rank's flag at every peer (also at those that get no data: the consumer
-// waits for all of them, which is what makes two receive buffers enough) and counts the exchange in *xseq.
-template <int ES>
-__global__ void __launch_bounds__(256)
-halo_push_kernel(const double* __restrict__ w, const int* __restrict__ idx, HaloPush hp, const int* __restrict__ halt) {
-  if (*halt) return;
-  const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(hp.xseq) + 1ull;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (int q = 0; q < hp.P; ++q) {
-    const long long a = hp.send_off[q], b = hp.send_off[q + 1];
-    if (b <= a) continue;
-    double* dst = hp.dst[q] + (seq & 1ull) * hp.stride[q];
-    for (long long i = a + t; i < b; i += stride) {
-      const long long s = idx[i];
-#pragma unroll
-      for (int e = 0; e < ES; ++e) dst[(i - a) * ES + e] = w[s * ES + e];
-    }
-  }
-  __threadfence_system();
-  __syncthreads();
-  __shared__ int s_last;
-  if (threadIdx.x == 0) s_last = (atomicAdd(hp.ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last) {
-    // one peer per thread: the release stores (and their NVLink round trips) overlap
-    if (threadIdx.x < hp.P && int(threadIdx.x) != hp.rank) st_release_sys_u64(hp.flag[threadIdx.x], seq);
-    if (threadIdx.x == 0) {
-      *hp.xseq = seq;
-      *hp.ticket = 0u;
-    }
-  }
-}
-
 HaloExchange::~HaloExchange() {
   if (p2p_ctx) {
     cudaStreamSynchronize(p2p_ctx->stream);
@@ -192,6 +157,8 @@ int HaloExchange::setup_p2p(cmb_ctx* ctx, const std::vector<double>& cnt) {
   push.rank = rank;
   push.xseq = xseq;
   push.ticket = ticket;
+  push.idx = d_send_idx;
+  push.npush = 1;  // set per launch (fused_push)
   for (int q = 0; q <= P; ++q) push.send_off[q] = send_off[q];
   for (int q = 0; q < P; ++q) {
     p2p_mapped[q] = mapped[q];
@@ -291,16 +258,7 @@ int HaloExchange::setup(cmb_ctx* ctx, int64_t n, int es_, const std::vector<int3
 }
 
 int HaloExchange::exchange(cmb_ctx* ctx, const double* w, const int* halt) {
-  if (p2p) {
-    LaunchScope ls(ctx, "halo_push");
-    const int grid = int(std::max<int64_t>(1, std::min<int64_t>((nsend + 255) / 256, int64_t(ctx->num_sms) * 4)));
-    if (es == 2)
-      halo_push_kernel<2><<<grid, 256, 0, ctx->stream>>>(w, d_send_idx, push, halt);
-    else
-      halo_push_kernel<1><<<grid, 256, 0, ctx->stream>>>(w, d_send_idx, push, halt);
-    CMB_CUDA(cudaGetLastError());
-    return CMB_OK;
-  }
+  if (p2p) return CMB_OK;  // the push is part of the consuming kernel (fused_push)
   if (nsend > 0) {
     LaunchScope ls(ctx, "halo_pack");
     const int grid = int(std::max<int64_t>(1, std::min<int64_t>((nsend + 255) / 256, int64_t(ctx->num_sms) * 8)));

@@ -1,5 +1,6 @@
 // halo.cuh — row partition + halo exchange interfaces (halo.cu).
 #pragma once
+#include <algorithm>
 #include <vector>
 
 #include "kernels.cuh"
@@ -29,6 +30,13 @@ struct HaloExchange {
   int setup(cmb_ctx* ctx, int64_t n_global, int es, const std::vector<int32_t>& halo_cols,
             const std::vector<int64_t>& per_owner);
   int exchange(cmb_ctx* ctx, const double* w, const int* halt);
+  // producer arguments for a consuming kernel launched with `grid` CTAs of 256 threads
+  HaloPush fused_push(int grid) const {
+    HaloPush h = push;
+    const int64_t want = (nsend + 255) / 256;
+    h.npush = int(std::max<int64_t>(1, std::min<int64_t>(want, grid)));
+    return h;
+  }
   // what the consuming kernel needs: which buffer to gather from and which flags to wait on
   HaloPull pull_args() const {
     if (p2p) return pull;

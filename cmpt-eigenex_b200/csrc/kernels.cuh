@@ -18,6 +18,10 @@ struct CgsPass {
   const char* family = nullptr; // profiling family override
   MailPull pull;                // P > 1: hin is the sum of the per-rank partials in the mailbox
   MailPush push;                // P > 1: the result goes to every peer's mailbox instead of hout
+  // Pythagorean norm (row-partitioned fast path): UPDATE_DOT with norm_trick also reduces ||y||^2 as entry ncols of
+  // hout; UPDATE_NORM with norm_trick then needs no reduction of its own: hout[0] = hin[ncols] - sum |hin_j|^2
+  // (= ||y - V hin||^2 for orthonormal V), computed by one CTA from the already reduced coefficients.
+  int norm_trick = 0;
 };
 enum { CGS_DOT = 0, CGS_UPDATE_DOT = 1, CGS_UPDATE_NORM = 2 };
 inline int cgs_max_cols(bool cplx) { return cplx ? 64 : 128; }

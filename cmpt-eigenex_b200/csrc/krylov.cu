@@ -158,16 +158,19 @@ static int gram_schmidt2_mailed(cmb_krylov* K, const Chunk& c, const double* x, 
   const unsigned long long s1 = p.push.seq;
   CMB_TRY(cgs_pass(ctx, K->cplx, CGS_DOT, p));
   // pass 2: h1 = sum of partials ; y = x - V h1 ; partial h2 -> mailboxes
+  // (also ||y||^2, so that the third pass needs no reduction of its own: ||y - V h2||^2 = ||y||^2 - |h2|^2)
   p.y = y;
   p.pull = mail_pull_of(ctx, s1, K->h1);
   p.push = mail_next_push(ctx);
+  p.norm_trick = 1;
   const unsigned long long s2 = p.push.seq;
   CMB_TRY(cgs_pass(ctx, K->cplx, CGS_UPDATE_DOT, p));
-  // pass 3: y -= V h2 ; partial ||y||^2 -> mailboxes
+  // pass 3: y -= V h2 ; ||y||^2 from the reduced h2 and ||y_before||^2 (same bits on every rank) -> K->scal[0]
   p.x = y;
   p.pull = mail_pull_of(ctx, s2, K->h2);
-  p.push = mail_next_push(ctx);
-  *nrm2_seq = p.push.seq;
+  p.push = MailPush();
+  p.hout = K->scal;
+  *nrm2_seq = 0;  // the norm is a plain device scalar: the operator apply needs no mailbox
   CMB_TRY(cgs_pass(ctx, K->cplx, CGS_UPDATE_NORM, p));
   return CMB_OK;
 }

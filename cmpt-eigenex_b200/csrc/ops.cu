@@ -20,20 +20,50 @@ namespace cmb {
 // ======================================================================================================
 // SELL-32
 // ======================================================================================================
-template <bool CPLX>
-__global__ void __launch_bounds__(256)
+// DIST: row-partitioned shard with the peer-memory halo fused in (a separate instantiation keeps the single-GPU
+// kernel free of that bookkeeping).  32 registers either way: the gathers are latency bound, occupancy is what counts.
+//
+// DIST kernels: the first hpush.npush CTAs only push this rank's boundary values into the peers' receive buffers
+// (halo_push_part).  The others walk the slices in `order`: first the n_interior slices that read no remote column,
+// then — after waiting for the peers' flags — the boundary slices.  The CTA that leaves last counts the exchange.
+struct SellDist {
+  unsigned long long seq;
+  int npush;
+  bool fused;
+};
+
+template <int ES>
+__device__ __forceinline__ bool sell_dist_prologue(const HaloPush& hpush, const HaloPull& hp, const double* w,
+                                                   double* partial, unsigned* ticket, double* alpha_slot, SellDist& d) {
+  d.fused = hp.flag != nullptr;
+  d.seq = 0;
+  d.npush = 0;
+  if (!d.fused) return true;
+  d.npush = hpush.npush;
+  d.seq = *reinterpret_cast<const volatile unsigned long long*>(hp.xseq) + 1ull;
+  if (int(blockIdx.x) < d.npush) {
+    halo_push_part<ES>(hpush, w, d.seq);
+    if (grid_sum_finalize<ES>(0.0, 0.0, partial, ticket, alpha_slot) && threadIdx.x == 0) *hpush.xseq = d.seq;
+    return false;  // pusher CTAs are done
+  }
+  return true;
+}
+
+template <bool CPLX, bool DIST>
+__global__ void __launch_bounds__(256, 8)
 spmv_sell_kernel(const long long* __restrict__ slice_ptr, const int* __restrict__ col, const double* __restrict__ val,
-                 long long nrows, long long nslices, const double* __restrict__ w, HaloPull hp,
-                 double* __restrict__ ucol, double* __restrict__ v, double shr, double shi, StepScalars sc,
-                 double* partial, unsigned* ticket) {
+                 long long nrows, int nslices, const double* __restrict__ w, HaloPush hpush, HaloPull hp,
+                 const int* __restrict__ order, int n_interior, double* __restrict__ ucol, double* __restrict__ v,
+                 double shr, double shi, StepScalars sc, double* partial, unsigned* ticket) {
   double inv;
   if (!step_prologue(sc, inv)) return;
-  const double* __restrict__ halo = halo_acquire(hp);
+  SellDist dist{0ull, 0, false};
+  if (DIST && !sell_dist_prologue<CPLX ? 2 : 1>(hpush, hp, w, partial, ticket, sc.alpha_slot, dist)) return;
   const int lane = threadIdx.x & 31;
-  const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int gwarp = (int(blockIdx.x) - dist.npush) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = (int(gridDim.x) - dist.npush) * (blockDim.x >> 5);
   double d0 = 0.0, d1 = 0.0;
-  for (long long slice = gwarp; slice < nslices; slice += nwarps) {
+  auto body = [&](long long slice, const double* halo) {
     const long long base = slice_ptr[slice];
     const int width = int((slice_ptr[slice + 1] - base) >> 5);
     const long long r = slice * 32 + lane;
@@ -81,27 +111,41 @@ spmv_sell_kernel(const long long* __restrict__ slice_ptr, const int* __restrict_
         d0 = fma(ui, y, d0);
       }
     }
+  };
+  if (!DIST) {
+    for (int gi = gwarp; gi < nslices; gi += nwarps) body(gi, nullptr);
+  } else if (!dist.fused) {  // NCCL fallback: the halo values are already in hp.base
+    for (int gi = gwarp; gi < nslices; gi += nwarps) body(gi, hp.base);
+  } else {
+    int gi = gwarp;
+    for (; gi < n_interior; gi += nwarps) body(order[gi], nullptr);  // no remote column in these slices
+    halo_wait_warp(hp, dist.seq);
+    const double* halo = hp.base + (dist.seq & 1ull) * hp.stride;
+    for (; gi < nslices; gi += nwarps) body(order[gi], halo);
   }
-  grid_sum_finalize<CPLX ? 2 : 1>(d0, d1, partial, ticket, sc.alpha_slot);
+  const bool last = grid_sum_finalize<CPLX ? 2 : 1>(d0, d1, partial, ticket, sc.alpha_slot);
+  if (DIST && dist.fused && last && threadIdx.x == 0) *hpush.xseq = dist.seq;  // this exchange is consumed
 }
 
 // Uniform-width variant (every slice has exactly W columns: stencils such as the 5-point Laplacian or the 7-point
 // convection-diffusion operator).  W is a compile-time constant, so all W index loads, W value loads and then all W
 // gathers of a row are issued back to back (one dependent phase instead of a runtime loop) and no slice pointer is
 // read.  Real scalars only; everything else goes through the generic kernel.
-template <int W>
-__global__ void __launch_bounds__(256)
-spmv_sell_uniform_kernel(const int* __restrict__ col, const double* __restrict__ val, long long nrows, long long nslices,
-                         const double* __restrict__ w, HaloPull hp, double* __restrict__ ucol,
-                         double* __restrict__ v, double shr, StepScalars sc, double* partial, unsigned* ticket) {
+template <int W, bool DIST>
+__global__ void __launch_bounds__(256, 8)
+spmv_sell_uniform_kernel(const int* __restrict__ col, const double* __restrict__ val, long long nrows, int nslices,
+                         const double* __restrict__ w, HaloPush hpush, HaloPull hp, const int* __restrict__ order,
+                         int n_interior, double* __restrict__ ucol, double* __restrict__ v, double shr,
+                         StepScalars sc, double* partial, unsigned* ticket) {
   double inv;
   if (!step_prologue(sc, inv)) return;
-  const double* __restrict__ halo = halo_acquire(hp);
+  SellDist dist{0ull, 0, false};
+  if (DIST && !sell_dist_prologue<1>(hpush, hp, w, partial, ticket, sc.alpha_slot, dist)) return;
   const int lane = threadIdx.x & 31;
-  const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int gwarp = (int(blockIdx.x) - dist.npush) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = (int(gridDim.x) - dist.npush) * (blockDim.x >> 5);
   double d0 = 0.0;
-  for (long long slice = gwarp; slice < nslices; slice += nwarps) {
+  auto body = [&](long long slice, const double* halo) {
     const long long base = slice * (W * 32) + lane;
     const long long r = slice * 32 + lane;
     int c[W];
@@ -111,7 +155,7 @@ spmv_sell_uniform_kernel(const int* __restrict__ col, const double* __restrict__
 #pragma unroll
     for (int k = 0; k < W; ++k) a[k] = __ldg(val + base + k * 32);
 #pragma unroll
-    for (int k = 0; k < W; ++k) xv[k] = (c[k] < nrows) ? w[c[k]] : halo[c[k] - nrows];
+    for (int k = 0; k < W; ++k) xv[k] = (!DIST || c[k] < nrows) ? w[c[k]] : halo[c[k] - nrows];
     double acc = 0.0;
 #pragma unroll
     for (int k = 0; k < W; ++k) acc = fma(a[k], xv[k], acc);
@@ -122,8 +166,32 @@ spmv_sell_uniform_kernel(const int* __restrict__ col, const double* __restrict__
       v[r] = y;
       d0 = fma(ui, y, d0);
     }
+  };
+  if (!DIST) {
+    for (int gi = gwarp; gi < nslices; gi += nwarps) body(gi, nullptr);
+  } else if (!dist.fused) {
+    for (int gi = gwarp; gi < nslices; gi += nwarps) body(gi, hp.base);
+  } else {
+    int gi = gwarp;
+    for (; gi < n_interior; gi += nwarps) body(order[gi], nullptr);
+    halo_wait_warp(hp, dist.seq);
+    const double* halo = hp.base + (dist.seq & 1ull) * hp.stride;
+    for (; gi < nslices; gi += nwarps) body(order[gi], halo);
   }
-  grid_sum_finalize<1>(d0, 0.0, partial, ticket, sc.alpha_slot);
+  const bool last = grid_sum_finalize<1>(d0, 0.0, partial, ticket, sc.alpha_slot);
+  if (DIST && dist.fused && last && threadIdx.x == 0) *hpush.xseq = dist.seq;
+}
+
+// flag[s] = 1 when slice s references a remote (halo) column, i.e. an index >= nrows
+__global__ void sell_halo_flag_kernel(const long long* __restrict__ slice_ptr, const int* __restrict__ col, long long nrows,
+                                      long long nslices, unsigned char* __restrict__ flag) {
+  const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gwarp >= nslices) return;
+  int any = 0;
+  for (long long i = slice_ptr[gwarp] + lane; i < slice_ptr[gwarp + 1]; i += 32) any |= (col[i] >= nrows);
+  any = __any_sync(0xffffffffu, any);
+  if (lane == 0) flag[gwarp] = (unsigned char)any;
 }
 
 __global__ void sell_width_kernel(const long long* __restrict__ rowptr, long long nrows, long long nslices,
@@ -176,29 +244,44 @@ struct SellOp : cmb_op {
   int* d_col = nullptr;
   double* d_val = nullptr;
   HaloExchange* halo = nullptr;  // row-partitioned shards only
+  int* d_order = nullptr;        // peer-memory halo: slices that touch no remote column first
+  long long n_interior = 0;
   long long padded_nnz = 0, nnz = 0;
   int uniform_width = 0;  // > 0: every slice has this width (fast path for real scalars)
   ~SellOp() override {
     pool_free(ctx, d_slice_ptr);
     pool_free(ctx, d_col);
     pool_free(ctx, d_val);
+    pool_free(ctx, d_order);
     delete halo;
   }
   int apply(const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) override {
-    HaloPull d_halo;
-    if (halo) {
-      // NVLink halo exchange of the un-normalised w (1/beta is applied inside the SpMV)
-      CMB_TRY(halo->exchange(ctx, w, sc.halt));
-      d_halo = halo->pull_args();
-    }
     long long blocks = (nslices + 7) / 8;
     int grid = int(std::min<long long>(blocks, (long long)ctx->num_sms * 8));
     if (grid < 1) grid = 1;
+    HaloPull d_halo;
+    HaloPush d_push;
+    if (halo) {
+      // NVLink halo exchange of the un-normalised w (1/beta is applied inside the SpMV): with peer memory the SpMV
+      // kernel gets extra leading CTAs that push; a pack kernel + ncclSend/ncclRecv group otherwise
+      CMB_TRY(halo->exchange(ctx, w, sc.halt));
+      d_halo = halo->pull_args();
+      if (halo->p2p) {
+        d_push = halo->fused_push(ctx->num_sms);
+        grid = std::max(1, std::min(grid, kMaxGrid - d_push.npush)) + d_push.npush;
+      }
+    }
     LaunchScope ls(ctx, "spmv_sell");
 #define CMB_SELL_UNIFORM(W)                                                                                        \
   case W:                                                                                                          \
-    spmv_sell_uniform_kernel<W><<<grid, 256, 0, ctx->stream>>>(d_col, d_val, n_local, nslices, w, d_halo, ucol, v, \
-                                                               shr, sc, ctx->d_partial, ctx->d_ticket + 1);        \
+    if (halo)                                                                                                      \
+      spmv_sell_uniform_kernel<W, true><<<grid, 256, 0, ctx->stream>>>(d_col, d_val, n_local, int(nslices), w, d_push,  \
+                                                                       d_halo, d_order, int(n_interior), ucol, v, shr,  \
+                                                                       sc, ctx->d_partial, ctx->d_ticket + 1);     \
+    else                                                                                                           \
+      spmv_sell_uniform_kernel<W, false><<<grid, 256, 0, ctx->stream>>>(d_col, d_val, n_local, int(nslices), w, d_push, \
+                                                                        d_halo, d_order, int(n_interior), ucol, v, shr, \
+                                                                        sc, ctx->d_partial, ctx->d_ticket + 1);    \
     CMB_CUDA(cudaGetLastError());                                                                                  \
     return CMB_OK;
     if (!cplx && shi == 0.0) {
@@ -217,12 +300,22 @@ struct SellOp : cmb_op {
       }
     }
 #undef CMB_SELL_UNIFORM
-    if (cplx)
-      spmv_sell_kernel<true><<<grid, 256, 0, ctx->stream>>>(d_slice_ptr, d_col, d_val, n_local, nslices, w, d_halo,
-                                                            ucol, v, shr, shi, sc, ctx->d_partial, ctx->d_ticket + 1);
-    else
-      spmv_sell_kernel<false><<<grid, 256, 0, ctx->stream>>>(d_slice_ptr, d_col, d_val, n_local, nslices, w, d_halo,
-                                                             ucol, v, shr, shi, sc, ctx->d_partial, ctx->d_ticket + 1);
+#define CMB_SELL_GENERIC(C, D)                                                                                    \
+  spmv_sell_kernel<C, D><<<grid, 256, 0, ctx->stream>>>(d_slice_ptr, d_col, d_val, n_local, int(nslices), w, d_push,    \
+                                                        d_halo, d_order, int(n_interior), ucol, v, shr, shi, sc,        \
+                                                        ctx->d_partial, ctx->d_ticket + 1)
+    if (cplx) {
+      if (halo)
+        CMB_SELL_GENERIC(true, true);
+      else
+        CMB_SELL_GENERIC(true, false);
+    } else {
+      if (halo)
+        CMB_SELL_GENERIC(false, true);
+      else
+        CMB_SELL_GENERIC(false, false);
+    }
+#undef CMB_SELL_GENERIC
     CMB_CUDA(cudaGetLastError());
     return CMB_OK;
   }
@@ -300,6 +393,38 @@ static int build_sell(SellOp* op, const int64_t* rowptr, const int32_t* col, con
   }();
   cleanup();
   return rc;
+}
+
+// Peer-memory halo: permutation of the slices with the ones that read no remote column first, so that the SpMV
+// kernel only has to wait for its peers when it reaches the boundary slices.
+static int build_slice_order(SellOp* op) {
+  cmb_ctx* ctx = op->ctx;
+  const long long ns = op->nslices;
+  if (ns == 0) return CMB_OK;
+  unsigned char* d_flag = nullptr;
+  CMB_TRY(pool_alloc(ctx, &d_flag, size_t(ns)));
+  const int grid = int((ns * 32 + 255) / 256);
+  sell_halo_flag_kernel<<<grid, 256, 0, ctx->stream>>>(op->d_slice_ptr, op->d_col, op->n_local, ns, d_flag);
+  std::vector<unsigned char> flag(static_cast<size_t>(ns));
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(flag.data(), d_flag, size_t(ns), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  pool_free(ctx, d_flag);
+  if (e != cudaSuccess) {
+    set_error("slice ordering failed: %s", cudaGetErrorString(e));
+    return CMB_ERR_CUDA;
+  }
+  std::vector<int> order;
+  order.reserve(static_cast<size_t>(ns));
+  for (long long s = 0; s < ns; ++s)
+    if (!flag[size_t(s)]) order.push_back(int(s));
+  op->n_interior = (long long)order.size();
+  for (long long s = 0; s < ns; ++s)
+    if (flag[size_t(s)]) order.push_back(int(s));
+  CMB_TRY(pool_alloc(ctx, &op->d_order, sizeof(int) * size_t(ns)));
+  CMB_CUDA(cudaMemcpyAsync(op->d_order, order.data(), sizeof(int) * size_t(ns), cudaMemcpyHostToDevice, ctx->stream));
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CMB_OK;
 }
 
 // ======================================================================================================
@@ -470,6 +595,7 @@ int cmb_op_csr_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t r
       rc = op->halo ? op->halo->setup(ctx, n_global, op->cplx ? 2 : 1, halo_cols, per_owner) : CMB_ERR_NOMEM;
     }
     if (rc == CMB_OK) rc = build_sell(op, rowptr, col_local.data(), val);
+    if (rc == CMB_OK && op->halo->p2p) rc = build_slice_order(op);
   } else {
     rc = build_sell(op, rowptr, col, val);
   }
