@@ -153,6 +153,65 @@ def gpu_main():
             assert np.all(np.abs(res - es.ritzResiduals()) < 1e-9)
             es.close()
         op.close()
+    # Krylov space exhausted on a row-partitioned operator: every rank must take the same halting decision on the
+    # device (beta^2 from the reduced coefficients) and the chain must stop with the reference's log lines
+    nb = 24
+    r0, r1 = dist.row_range(nb)
+    rp = np.zeros(nb + 1, np.int64)
+    cols, vals = [], []
+    for r in range(nb):
+        for c_, v_ in ((r - 1, -1.0), (r, 2.0 + 0.1 * r), (r + 1, -1.0)):
+            if 0 <= c_ < nb:
+                cols.append(c_)
+                vals.append(v_)
+        rp[r + 1] = len(cols)
+    cols, vals = np.array(cols, np.int32), np.array(vals)
+    full = (rp, cols, vals)
+    shard = (rp[r0:r1 + 1] - rp[r0], cols[rp[r0]:rp[r1]], vals[rp[r0]:rp[r1]])
+    x0 = syn.start_vector(nb, seed=11)
+    op = pkg.DeviceOperator.from_csr(ctx, *shard, n_global=nb, row_begin=r0)
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(op).setInitialVector(x0[r0:r1]).setMinIterations(40).setMaxIterations(60)
+    es.setMaxEigenvalues(4)
+    es.compute()
+    ref = rs.LanczosEigenSolver("d")
+    ref.set_matrix_multiplication(core.Operator.csr(*full))
+    ref.init, ref.min_iterations, ref.max_iterations, ref.max_eigenvalues = x0, 40, 60, 4
+    ref.compute()
+    assert es.log() == ref.log, (es.log(), ref.log)
+    assert any("full of Krylov subspace" in line for line in es.log())
+    assert es.alpha().size == nb
+    Ad = np.zeros((nb, nb))
+    for r in range(nb):
+        Ad[r, cols[rp[r]:rp[r + 1]]] = vals[rp[r]:rp[r + 1]]
+    assert np.abs(es.eigenvalues() - np.linalg.eigvalsh(Ad)[:4]).max() < 1e-12
+    # back-to-back applies without any reduction in between: the receive buffers alternate correctly
+    xs = x0[r0:r1].copy()
+    xf = x0.copy()
+    for _ in range(5):
+        xs = op.apply(xs)
+        xf = Ad @ xf
+    assert np.abs(xs - xf[r0:r1]).max() < 1e-10 * np.abs(xf).max()
+    es.close()
+    op.close()
+    # one-directional coupling (rank q reads from rank q+1 only): ranks that receive nothing still follow the protocol
+    nu = 64
+    r0, r1 = dist.row_range(nu)
+    Au = np.diag(1.0 + 0.05 * np.arange(nu)) + np.diag(0.3 * np.ones(nu - 20), 20)
+    rpu = np.zeros(r1 - r0 + 1, np.int64)
+    cu, vu = [], []
+    for r in range(r0, r1):
+        nzc = np.nonzero(Au[r])[0]
+        cu += nzc.tolist()
+        vu += Au[r, nzc].tolist()
+        rpu[r - r0 + 1] = len(cu)
+    op = pkg.DeviceOperator.from_csr(ctx, rpu, np.array(cu, np.int32), np.array(vu), n_global=nu, row_begin=r0)
+    xs, xf = syn.start_vector(nu, seed=3)[r0:r1].copy(), syn.start_vector(nu, seed=3)
+    for _ in range(6):
+        xs = op.apply(xs)
+        xf = Au @ xf
+    assert np.abs(xs - xf[r0:r1]).max() < 1e-12 * max(1.0, np.abs(xf).max())
+    op.close()
     # matrix-free Heisenberg ring, slabs exchanged over NVLink (cfg 5 at small L)
     Lm = 14
     n = 1 << Lm
