@@ -219,7 +219,7 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
   }
 
   // ===== UPDATE_NORM without a reduction of its own (norm_trick): beta^2 from the reduced coefficients =====
-  __shared__ double s_fin[kConsumerWarps * 32 + 8];
+  __shared__ double s_fin[2 * kConsumerWarps * 32 + 8];
   if (MODE == 2 && norm_trick) {
     if (blockIdx.x != 0) return;
     const int nh = ncols * ES;
@@ -284,30 +284,46 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
   asm volatile("bar.sync 9, %0;" ::"r"(kConsumerWarps * 32) : "memory");
   if (s_last) {
     __threadfence();
-    // Sum the per-CTA partials in a fixed pattern (deterministic): G thread groups take interleaved CTAs with
-    // four independent accumulators each (keeps ~4G loads in flight instead of one serial chain of gridDim.x
-    // L2 round trips), then one thread per value adds the G group sums in order.
+    // Sum the per-CTA partials in a fixed pattern (deterministic).  A thread takes a PAIR of neighbouring values (one
+    // 16-byte load per CTA row) and the interleaved CTAs of its group with eight independent accumulators: ~8 G loads
+    // in flight instead of one serial chain of gridDim.x L2 round trips.  Then one thread per value adds the G group
+    // sums in order.
     const int tid = threadIdx.x, nb = int(gridDim.x);
-    int G = (kConsumerWarps * 32) / nout;
+    const int npair = (nout + 1) >> 1;
+    int G = (kConsumerWarps * 32) / npair;
     G = G < 1 ? 1 : (G > 16 ? 16 : G);
-    if (tid < G * nout) {
-      const int vi = tid % nout, g = tid / nout;
-      const double* pp = partial + vi;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (tid < G * npair) {
+      const int vp = tid % npair, g = tid / npair;
+      const double2* pp = reinterpret_cast<const double2*>(partial) + vp;
+      constexpr int kRow = kPartialStride / 2;  // row length in double2
+      double2 acc[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = make_double2(0.0, 0.0);
       int b = g;
-      for (; b + 3 * G < nb; b += 4 * G) {
-        a0 += __ldcg(pp + size_t(b) * kPartialStride);
-        a1 += __ldcg(pp + size_t(b + G) * kPartialStride);
-        a2 += __ldcg(pp + size_t(b + 2 * G) * kPartialStride);
-        a3 += __ldcg(pp + size_t(b + 3 * G) * kPartialStride);
+      for (; b + 7 * G < nb; b += 8 * G) {
+        double2 ld[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ld[u] = __ldcg(pp + size_t(b + u * G) * kRow);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc[u].x += ld[u].x;
+          acc[u].y += ld[u].y;
+        }
       }
-      for (; b < nb; b += G) a0 += __ldcg(pp + size_t(b) * kPartialStride);
-      s_fin[tid] = (a0 + a1) + (a2 + a3);
+      for (; b < nb; b += G) {  // fewer than 8 rows left
+        const double2 l = __ldcg(pp + size_t(b) * kRow);
+        acc[0].x += l.x;
+        acc[0].y += l.y;
+      }
+      const double sx = ((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x)) + ((acc[4].x + acc[5].x) + (acc[6].x + acc[7].x));
+      const double sy = ((acc[0].y + acc[1].y) + (acc[2].y + acc[3].y)) + ((acc[4].y + acc[5].y) + (acc[6].y + acc[7].y));
+      s_fin[(g * npair + vp) * 2] = sx;
+      s_fin[(g * npair + vp) * 2 + 1] = sy;
     }
     asm volatile("bar.sync 9, %0;" ::"r"(kConsumerWarps * 32) : "memory");
     for (int t = tid; t < nout; t += kConsumerWarps * 32) {
       double sacc = 0.0;
-      for (int g = 0; g < G; ++g) sacc += s_fin[g * nout + t];
+      for (int g = 0; g < G; ++g) sacc += s_fin[g * npair * 2 + t];
       if (push.P > 1)
         mail_push_value(push, t, sacc);  // this rank's partial straight into every peer's mailbox (NVLink)
       else
