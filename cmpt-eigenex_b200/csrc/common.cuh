@@ -103,6 +103,7 @@ struct HaloPush {                       // producer side (kernel argument)
   unsigned* ticket = nullptr;
   const int* idx = nullptr;             // local rows to send, grouped by peer (send_off)
   int npush = 1;                        // CTAs of the consuming kernel that take part in the push
+  int all_push = 0;                     // every CTA pushes a share and then goes on to its rows (few interior slices)
 };
 struct HaloPull {                       // consumer side (kernel argument)
   const double* base = nullptr;         // receive buffer 0 (or the NCCL receive buffer when flag == nullptr)

@@ -83,19 +83,24 @@ __device__ __forceinline__ void halo_push_part(const HaloPush& hp, const double*
     if (threadIdx.x == 0) *hp.ticket = 0u;
   }
 }
-// Consumer part (whole warp): wait until every peer has published exchange `seq`.  Bounded like mail_wait.
-__device__ __forceinline__ void halo_wait_warp(const HaloPull& h, unsigned long long seq) {
-  const int lane = threadIdx.x & 31;
-  if (lane < h.P && lane != h.rank) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys_u64(h.flag + lane) < seq) {
-      if (clock64() - t0 > (1ll << 32)) {
-        *h.error = 1;
-        break;
+// Consumer part (all threads of the CTA): wait until every peer has published exchange `seq`.  One warp polls (with
+// a short back-off, so that thousands of waiting warps do not compete with the incoming NVLink writes for L2), the
+// others park on the CTA barrier.  Bounded like mail_wait.
+__device__ __forceinline__ void halo_wait_cta(const HaloPull& h, unsigned long long seq) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    if (lane < h.P && lane != h.rank) {
+      const long long t0 = clock64();
+      while (ld_acquire_sys_u64(h.flag + lane) < seq) {
+        __nanosleep(100);
+        if (clock64() - t0 > (1ll << 32)) {
+          *h.error = 1;
+          break;
+        }
       }
     }
   }
-  __syncwarp();
+  __syncthreads();
 }
 
 __device__ __forceinline__ bool step_prologue(const StepScalars& sc, double& inv) {

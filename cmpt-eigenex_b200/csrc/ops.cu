@@ -39,8 +39,12 @@ __device__ __forceinline__ bool sell_dist_prologue(const HaloPush& hpush, const 
   d.seq = 0;
   d.npush = 0;
   if (!d.fused) return true;
-  d.npush = hpush.npush;
   d.seq = *reinterpret_cast<const volatile unsigned long long*>(hp.xseq) + 1ull;
+  if (hpush.all_push) {  // nothing to overlap with: spread the push over the whole grid, then everybody computes
+    halo_push_part<ES>(hpush, w, d.seq);
+    return true;
+  }
+  d.npush = hpush.npush;
   if (int(blockIdx.x) < d.npush) {
     halo_push_part<ES>(hpush, w, d.seq);
     if (grid_sum_finalize<ES>(0.0, 0.0, partial, ticket, alpha_slot) && threadIdx.x == 0) *hpush.xseq = d.seq;
@@ -119,7 +123,7 @@ spmv_sell_kernel(const long long* __restrict__ slice_ptr, const int* __restrict_
   } else {
     int gi = gwarp;
     for (; gi < n_interior; gi += nwarps) body(order[gi], nullptr);  // no remote column in these slices
-    halo_wait_warp(hp, dist.seq);
+    halo_wait_cta(hp, dist.seq);
     const double* halo = hp.base + (dist.seq & 1ull) * hp.stride;
     for (; gi < nslices; gi += nwarps) body(order[gi], halo);
   }
@@ -174,7 +178,7 @@ spmv_sell_uniform_kernel(const int* __restrict__ col, const double* __restrict__
   } else {
     int gi = gwarp;
     for (; gi < n_interior; gi += nwarps) body(order[gi], nullptr);
-    halo_wait_warp(hp, dist.seq);
+    halo_wait_cta(hp, dist.seq);
     const double* halo = hp.base + (dist.seq & 1ull) * hp.stride;
     for (; gi < nslices; gi += nwarps) body(order[gi], halo);
   }
@@ -267,8 +271,15 @@ struct SellOp : cmb_op {
       CMB_TRY(halo->exchange(ctx, w, sc.halt));
       d_halo = halo->pull_args();
       if (halo->p2p) {
-        d_push = halo->fused_push(ctx->num_sms);
-        grid = std::max(1, std::min(grid, kMaxGrid - d_push.npush)) + d_push.npush;
+        if (2 * n_interior < nslices) {
+          // most slices read remote columns, so there is little to hide the exchange behind: all CTAs push first
+          d_push = halo->fused_push(grid);
+          d_push.npush = grid;
+          d_push.all_push = 1;
+        } else {
+          d_push = halo->fused_push(ctx->num_sms);
+          grid = std::max(1, std::min(grid, kMaxGrid - d_push.npush)) + d_push.npush;
+        }
       }
     }
     LaunchScope ls(ctx, "spmv_sell");
