@@ -556,12 +556,30 @@ def test_cfg2_full_size_properties(ctx):
 
 
 # ------------------------------------------------------------------------------------------------
+# matrix-free Heisenberg apply beyond one shared-memory tile: window passes (2 passes from L = 14 real / 13 complex,
+# 3 passes from L = 21 / 20), open and periodic chains
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,pbc,dtype", [(14, True, np.float64), (16, False, np.float64), (20, True, np.float64),
+                                         (21, True, np.float64), (22, False, np.float64), (23, True, np.float64),
+                                         (13, True, np.complex128), (17, False, np.complex128),
+                                         (20, True, np.complex128), (21, True, np.complex128)])
+def test_heisenberg_multi_pass_apply(ctx, L, pbc, dtype):
+    x = syn.start_vector(1 << L, seed=31, dtype=dtype)
+    op = pkg.DeviceOperator.heisenberg(ctx, L, 1.0, pbc, dtype=dtype)
+    y = op.apply(x)
+    yo = core.Operator.heisenberg(L, 1.0, pbc, prefix="z" if dtype == np.complex128 else "d").apply(x)
+    np.testing.assert_allclose(y, yo, atol=1e-14)
+    op.close()
+
+
+# ------------------------------------------------------------------------------------------------
 # row-partitioned matrix-free Heisenberg operator (cfg 5) with virtual ranks on one GPU
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("L,nranks,pbc,dtype", [(10, 2, True, np.float64), (10, 2, False, np.float64),
                                                 (11, 4, True, np.float64), (12, 8, True, np.float64),
                                                 (12, 8, False, np.complex128), (9, 4, True, np.complex128),
-                                                (13, 16, True, np.float64)])
+                                                (13, 16, True, np.float64), (17, 4, True, np.float64),
+                                                (23, 2, True, np.float64), (16, 4, False, np.complex128)])
 def test_heisenberg_partitioned_virtual_ranks(ctx, L, nranks, pbc, dtype):
     import ctypes as C
 
