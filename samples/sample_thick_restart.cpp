@@ -7,6 +7,8 @@
 // usage: sample_thick_restart [Nx Ny]
 #include <algorithm>
 #include <cmath>
+#include <complex>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -116,6 +118,32 @@ int main(int argc, char** argv) {
     std::printf("  <x_12 | x_21> = %.2e\n", dot);
     pass = pass && std::abs(vals[0] - exact[0]) < 1e-9 && std::abs(vals[1] - exact[1]) < 1e-9 &&
            std::abs(vals[2] - exact[2]) < 1e-9 && std::abs(dot) < 1e-8;
+  }
+  {
+    // complex Scalar: the Hermitian chain of the reference's sample_lanczos2.cpp (spectrum 2 cos(k pi/(n+1))), four
+    // lowest pairs with a basis of 24 vectors
+    using C = std::complex<double>;
+    const int n = 200;
+    std::vector<std::int64_t> rowptr(n + 1, 0);
+    std::vector<std::int32_t> col;
+    std::vector<C> val;
+    for (int i = 0; i < n; ++i) {
+      if (i > 0) col.push_back(i - 1), val.push_back(C(0.0, +1.0));
+      if (i < n - 1) col.push_back(i + 1), val.push_back(C(0.0, -1.0));
+      rowptr[i + 1] = static_cast<std::int64_t>(col.size());
+    }
+    Vector<C> x0(n);
+    for (int i = 0; i < n; ++i) x0[i] = C(std::cos(0.37 * i) + 0.2, std::sin(0.11 * i * i));
+    ThickRestartLanczos<C> tr;
+    tr.setMatrixMultiplication(DeviceOperator<C>::fromCSR(n, rowptr.data(), col.data(), val.data()));
+    tr.setInitialVector(x0).setWanted(4).setMaxBasis(24).setTolerance(1e-11).setMaxRestarts(500);
+    tr.compute();
+    const double pi = std::acos(-1.0);
+    double dmax = 0;
+    for (int k = 0; k < 4; ++k) dmax = std::max(dmax, std::abs(tr.eigenvalues()[k] - 2.0 * std::cos((n - k) * pi / (n + 1))));
+    std::printf("complex chain n=%d: %ld restarts, %ld/4 converged, max |theta - exact| = %.2e\n", n, long(tr.restarts()),
+                long(tr.converged()), dmax);
+    pass = pass && tr.converged() == 4 && dmax < 1e-9;
   }
   std::printf("%s\n", pass ? "PASS" : "FAIL");
   return pass ? 0 : 1;
