@@ -24,6 +24,14 @@ def test_samples_are_built():
         assert os.path.exists(os.path.join(BIN, n))
 
 
+def test_vector_map_algebra_host_only():
+    # VectorMap (sums, products, scalar multiples, composition, size checks) — pure host code
+    exe = os.path.join(ROOT, "tests", "cpp", "bin", "test_vector_map")
+    assert os.path.exists(exe), "host tests are built by __graft_entry__.build()"
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0 and p.stdout.strip() == "PASS", p.stdout + p.stderr
+
+
 @pytest.mark.gpu
 def test_sample_lanczos1_legacy_callback():
     out = _run("sample_lanczos1")
@@ -94,3 +102,11 @@ def test_sample_thick_restart_and_deflation():
     assert int(m.group(1)) > 0 and int(m.group(3)) == 6
     assert float(re.search(r"rect: max \|theta - exact\| = (\S+),", out).group(1)) < 1e-9
     assert abs(float(re.search(r"<x_12 \| x_21> = (\S+)", out).group(1))) < 1e-8
+
+
+@pytest.mark.gpu
+def test_sample_vector_map_feeds_the_solver():
+    # VectorMap sum of two device operators through the callback path == the assembled operator on the device
+    out = _run("sample_vector_map")
+    assert out.strip().endswith("PASS"), out
+    assert float(re.search(r"max \|vector map - assembled\| = (\S+)", out).group(1)) < 1e-10
