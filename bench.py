@@ -285,7 +285,7 @@ def run_ours(args):
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[dom]
             traffic = tr["ratio"] * per_launch_bytes  # measured dram/algorithmic ratio x this run's bytes per launch
-            traffic_src = "ncu --set full capture (profiles/r1b_prof_step_raw.txt): dram bytes / algorithmic bytes = %.4f" % tr["ratio"]
+            traffic_src = "ncu --set full capture (profiles/r1d_prof_step4_raw.txt): dram bytes / algorithmic bytes = %.4f" % tr["ratio"]
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
