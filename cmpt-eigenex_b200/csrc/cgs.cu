@@ -131,6 +131,13 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
   }
   double nrm = 0.0;
 
+  // Columns j >= cg of this warp's share do not exist: their v stays zero (set once here, the loads below are
+  // predicated) and their coefficients are zero, so the arithmetic of the tile loop runs unconditionally over all CG
+  // slots — no per-column select or branch in the hot loop.
+  double2 v[CG];
+#pragma unroll
+  for (int j = 0; j < CG; ++j) v[j] = make_double2(0.0, 0.0);
+
   int it = 0, s = 0;
   uint32_t ph = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -138,12 +145,9 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
     const double* vs = stage_base + size_t(s) * stage_doubles;
     double2 xv = make_double2(0.0, 0.0);
     if (x) xv = *reinterpret_cast<const double2*>(vs + nc * T + row);
-    double2 v[CG];
 #pragma unroll
-    for (int j = 0; j < CG; ++j) {
-      v[j] = make_double2(0.0, 0.0);
+    for (int j = 0; j < CG; ++j)
       if (j < cg) v[j] = *reinterpret_cast<const double2*>(vs + vofs + j * Cfg::BOXR);
-    }
 
     double2 yv = xv;
     if (MODE >= 1) {
@@ -151,17 +155,15 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
       double2 p = make_double2(0.0, 0.0), p2 = make_double2(0.0, 0.0);
 #pragma unroll
       for (int j = 0; j < CG; ++j) {
-        if (j < cg) {
-          double2& q = (j & 1) ? p2 : p;
-          if (CPLX) {
-            q.x = fma(v[j].x, hr[j], q.x);
-            q.x = fma(-v[j].y, hi[j], q.x);
-            q.y = fma(v[j].x, hi[j], q.y);
-            q.y = fma(v[j].y, hr[j], q.y);
-          } else {
-            q.x = fma(v[j].x, hr[j], q.x);
-            q.y = fma(v[j].y, hr[j], q.y);
-          }
+        double2& q = (j & 1) ? p2 : p;
+        if (CPLX) {
+          q.x = fma(v[j].x, hr[j], q.x);
+          q.x = fma(-v[j].y, hi[j], q.x);
+          q.y = fma(v[j].x, hi[j], q.y);
+          q.y = fma(v[j].y, hr[j], q.y);
+        } else {
+          q.x = fma(v[j].x, hr[j], q.x);
+          q.y = fma(v[j].y, hr[j], q.y);
         }
       }
       p.x += p2.x;
@@ -190,16 +192,14 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
     if (MODE <= 1) {
 #pragma unroll
       for (int j = 0; j < CG; ++j) {
-        if (j < cg) {
-          if (CPLX) {  // conj(v) * y
-            ar[j] = fma(v[j].x, yv.x, ar[j]);
-            ar[j] = fma(v[j].y, yv.y, ar[j]);
-            ai[j] = fma(v[j].x, yv.y, ai[j]);
-            ai[j] = fma(-v[j].y, yv.x, ai[j]);
-          } else {
-            ar[j] = fma(v[j].x, yv.x, ar[j]);
-            ar[j] = fma(v[j].y, yv.y, ar[j]);
-          }
+        if (CPLX) {  // conj(v) * y
+          ar[j] = fma(v[j].x, yv.x, ar[j]);
+          ar[j] = fma(v[j].y, yv.y, ar[j]);
+          ai[j] = fma(v[j].x, yv.y, ai[j]);
+          ai[j] = fma(-v[j].y, yv.x, ai[j]);
+        } else {
+          ar[j] = fma(v[j].x, yv.x, ar[j]);
+          ar[j] = fma(v[j].y, yv.y, ar[j]);
         }
       }
       if (MODE == 1 && norm_trick && gc == 0) {
