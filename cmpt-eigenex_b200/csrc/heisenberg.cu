@@ -595,11 +595,11 @@ struct HeisenbergOp : cmb_op {
       const int grid = int(std::min<long long>(ntiles, (long long)ctx->num_sms));
 #define CMB_HEIS_LAUNCH(C, M, R)                                                                                     \
   do {                                                                                                               \
-    static bool attr = false;                                                                                        \
-    if (!attr) {                                                                                                     \
+    static bool attr[64] = {};  /* function attributes are per device */                                            \
+    if (!attr[ctx->device & 63]) {                                                                                   \
       CMB_CUDA(cudaFuncSetAttribute(heis_apply_kernel<C, M, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                     kHeisSmem));                                                                     \
-      attr = true;                                                                                                   \
+      attr[ctx->device & 63] = true;                                                                                 \
     }                                                                                                                \
     heis_apply_kernel<C, M, R><<<grid, kHeisThreads, kHeisSmem, ctx->stream>>>(a, ps, tm, w, ucol, v, shr, shi, sc,  \
                                                                                ctx->d_partial, ctx->d_ticket + 1);   \
