@@ -250,6 +250,7 @@ struct SellOp : cmb_op {
   HaloExchange* halo = nullptr;  // row-partitioned shards only
   int* d_order = nullptr;        // peer-memory halo: slices that touch no remote column first
   long long n_interior = 0;
+  int resident_ctas = 0;         // CTAs of the SpMV kernel that fit on the GPU at once (queried on first use)
   long long padded_nnz = 0, nnz = 0;
   int uniform_width = 0;  // > 0: every slice has this width (fast path for real scalars)
   ~SellOp() override {
@@ -272,7 +273,15 @@ struct SellOp : cmb_op {
       d_halo = halo->pull_args();
       if (halo->p2p) {
         if (2 * n_interior < nslices) {
-          // most slices read remote columns, so there is little to hide the exchange behind: all CTAs push first
+          // most slices read remote columns, so there is little to hide the exchange behind: all CTAs push first.
+          // Every CTA then waits for the peers, so the whole grid must be resident at once (a CTA that could not
+          // start before others finish would never push): cap the grid by the measured occupancy.
+          if (resident_ctas == 0) {
+            int per_sm = 0;
+            CMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_sell_kernel<true, true>, 256, 0));
+            resident_ctas = std::max(1, per_sm) * ctx->num_sms;
+          }
+          grid = std::min(grid, resident_ctas);
           d_push = halo->fused_push(grid);
           d_push.npush = grid;
           d_push.all_push = 1;
