@@ -786,6 +786,27 @@ int cmb_op_heisenberg_create(cmb_ctx* ctx, cmb_dtype dtype, int L, double J, int
   return CMB_OK;
 }
 
+int cmb_heisenberg_plan(int L, int pbc, int nranks, int rank, int* kind, int* partner, int* needed, int* offset_half,
+                        int* length_half) {
+  if (!kind || !partner || !needed || !offset_half || !length_half) return CMB_ERR_INVALID;
+  if (L < 2 || nranks < 1 || (nranks & (nranks - 1)) != 0 || rank < 0 || rank >= nranks) return CMB_ERR_INVALID;
+  HeisPlan pl;
+  pl.build(L, pbc != 0, nranks, rank);
+  if (pl.Ll < 2 || int(pl.remote.size()) > 8) return CMB_ERR_INVALID;
+  int off = 0;
+  for (size_t k = 0; k < pl.remote.size(); ++k) {
+    const HeisRemote& r = pl.remote[k];
+    const int len = !r.needed ? 0 : (r.kind == 3 ? 2 : 1);
+    kind[k] = r.kind;
+    partner[k] = r.partner;
+    needed[k] = r.needed ? 1 : 0;
+    offset_half[k] = off;
+    length_half[k] = len;
+    off += len;
+  }
+  return int(pl.remote.size());
+}
+
 // Diagnostic / test entry: the distributed operator with P = 2^p VIRTUAL ranks on one GPU.  Every virtual rank
 // runs the same kernel and the same packing as a real rank; the NCCL exchange is replaced by device copies
 // between the virtual ranks' slabs.  x and y are full host vectors of 2^L elements.

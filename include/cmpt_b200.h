@@ -100,6 +100,12 @@ int cmb_op_heisenberg_create(cmb_ctx* ctx, cmb_dtype dtype, int L, double J, int
  * kernels and packing as real ranks, the NVLink exchange replaced by device copies); x, y: full 2^L host vectors */
 int cmb_debug_heisenberg_virtual(cmb_ctx* ctx, cmb_dtype dtype, int L, double J, int pbc, int nranks, const void* x,
                                  void* y);
+/* host-only: the exchange plan of rank `rank` of `nranks` for the matrix-free Heisenberg chain.  Entry k of the
+ * outputs (capacity >= 8) describes remote bond k: kind (2 straddle, 3 rank-rank, 4 periodic wrap), partner rank,
+ * whether a slab travels, its offset in this rank's receive buffer and its length, both in units of the local slab
+ * length / 2.  Returns the number of remote bonds (0 for a single rank), negative on error.  No GPU needed. */
+int cmb_heisenberg_plan(int L, int pbc, int nranks, int rank, int* kind, int* partner, int* needed, int* offset_half,
+                        int* length_half);
 /* legacy host callback with the reference's signature plus a user pointer: out = A*in on LOCAL host
  * slabs (single-rank contexts only).  Costs one D2H + one H2D of an n-vector per Krylov step. */
 typedef void (*cmb_matmul_fn)(const void* in, void* out, void* user);

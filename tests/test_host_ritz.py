@@ -103,3 +103,49 @@ def test_no_silent_cpu_fallback_without_gpu():
         pkg.Context(0)
     assert e.value.code == capi.CMB_ERR_NO_DEVICE
     assert b"no CPU fallback" in capi.lib().cmb_last_error()
+
+
+@pytest.mark.parametrize("L,pbc,nranks", [(10, True, 2), (12, True, 4), (12, False, 4), (30, True, 8), (20, True, 16),
+                                          (9, False, 1)])
+def test_heisenberg_exchange_plan_is_consistent_between_partners(L, pbc, nranks):
+    """Host-only: the slab exchange of the matrix-free Heisenberg chain is pairwise and symmetric (what lets a rank
+    compute where its slab lands in the partner's receive buffer, csrc/heisenberg.cu setup_p2p), and it covers exactly
+    the bonds that cross the rank bits."""
+    import ctypes as C
+
+    lib = capi.lib()
+
+    def plan(rank):
+        arr = [(C.c_int32 * 8)() for _ in range(5)]
+        nrem = lib.cmb_heisenberg_plan(L, int(pbc), nranks, rank, *arr)
+        assert nrem >= 0
+        return [tuple(int(a[k]) for a in arr) for k in range(nrem)]
+
+    p = nranks.bit_length() - 1
+    plans = [plan(r) for r in range(nranks)]
+    if nranks == 1:
+        assert plans[0] == []
+        return
+    nb = L if (pbc and L > 2) else L - 1
+    crossing = p + (1 if nb == L else 0)  # bonds (Ll-1,Ll) .. (L-2,L-1) and the periodic wrap bond
+    for r, pl in enumerate(plans):
+        assert len(pl) == crossing
+        off = 0
+        for k, (kind, partner, needed, offset, length) in enumerate(pl):
+            assert 0 <= partner < nranks and partner != r
+            assert offset == off
+            off += length
+            # the partner lists the same bond at the same position, points back at me, and agrees on the size
+            kind2, partner2, needed2, _, length2 = plans[partner][k]
+            assert (kind2, partner2, needed2, length2) == (kind, r, needed, length)
+            if kind == 2:      # straddle bond: partner differs in rank bit 0, half slab
+                assert partner == r ^ 1 and needed == 1 and length == 1
+            elif kind == 3:    # rank-rank bond b: full slab iff my two rank bits differ
+                b = k - 1
+                differ = ((r >> b) ^ (r >> (b + 1))) & 1
+                assert partner == r ^ (3 << b) and needed == differ and length == 2 * differ
+            else:              # periodic wrap: partner differs in the top rank bit, packed half slab
+                assert kind == 4 and partner == r ^ (1 << (p - 1)) and needed == 1 and length == 1
+    # the heaviest ranks of cfg 5 (L = 30 on 8 GPUs) receive three slabs' worth per apply
+    if (L, nranks) == (30, 8):
+        assert max(sum(e[4] for e in pl) for pl in plans) == 6 and min(sum(e[4] for e in pl) for pl in plans) == 2
