@@ -7,6 +7,7 @@
 
 #include "cmpt/eigen_ex/arnoldi.hpp"
 #include "cmpt/eigen_ex/lanczos.hpp"
+#include "cmpt/eigen_ex/detail/symmetric_eigen.hpp"
 #include "cmpt_b200_solver.h"
 #include "common.cuh"
 
@@ -539,6 +540,17 @@ int cmbs_host_tridiagonal_eigen(int64_t n, const double* alpha, const double* be
     std::copy(ww.begin(), ww.end(), w);
     if (z) std::copy(zz.begin(), zz.end(), z);
     S_REQ(ok, "tridiagonal QR did not converge");
+    return CMB_OK;
+  });
+}
+int cmbs_host_symmetric_eigen(int64_t n, const double* a, double* w, double* z) {
+  S_REQ(n >= 0 && (n == 0 || (a && w && z)), "bad argument");
+  return guarded([&]() -> int {
+    std::vector<double> aa(a, a + size_t(n) * size_t(n)), ww, zz;
+    const bool ok = detail::symmetric_eigensystem<double>(int(n), aa, ww, zz);
+    std::copy(ww.begin(), ww.end(), w);
+    std::copy(zz.begin(), zz.end(), z);
+    S_REQ(ok, "Jacobi iteration did not converge");
     return CMB_OK;
   });
 }

@@ -455,6 +455,17 @@ def host_tridiagonal_eigen(alpha, beta, vectors=True):
     return (w, z) if vectors else w
 
 
+def host_symmetric_eigen(a):
+    """The product's host Jacobi solver for small dense symmetric matrices (detail/symmetric_eigen.hpp): the projected
+    matrix of the thick-restart driver; no GPU needed."""
+    af = np.asfortranarray(a, dtype=np.float64)
+    n = af.shape[0]
+    w = np.empty(n)
+    z = np.empty((n, n), order="F")
+    check(lib().cmbs_host_symmetric_eigen(n, ptr(af), ptr(w), ptr(z)))
+    return w, z
+
+
 def host_hessenberg_eigen(h, vectors=True):
     """The product's host Hessenberg solver (detail/hessenberg_eigen.hpp); no GPU needed."""
     hc = np.asfortranarray(h, dtype=np.complex128)

@@ -78,6 +78,9 @@ int cmbs_exp_solve_with_taylor(cmbs_solver* s, double x_re, double x_im, double 
 /* host-side Ritz solvers, exposed for testing against LAPACK (no GPU needed) */
 int cmbs_host_tridiagonal_eigen(int64_t n, const double* alpha, const double* beta, double* w, double* z /*nullable*/);
 int cmbs_host_hessenberg_eigen(int64_t n, const void* h_complex, void* w_complex, void* v_complex /*nullable*/);
+/* dense real symmetric n x n (column-major), cyclic Jacobi (detail/symmetric_eigen.hpp): the projected matrix of the
+ * thick-restart driver.  w ascending, z column-major eigenvectors. */
+int cmbs_host_symmetric_eigen(int64_t n, const double* a, double* w, double* z);
 
 /* pinned host memory for staging inputs/results at full PCIe rate */
 int cmb_host_alloc(size_t bytes, void** out);

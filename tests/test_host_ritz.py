@@ -149,3 +149,32 @@ def test_heisenberg_exchange_plan_is_consistent_between_partners(L, pbc, nranks)
     # the heaviest ranks of cfg 5 (L = 30 on 8 GPUs) receive three slabs' worth per apply
     if (L, nranks) == (30, 8):
         assert max(sum(e[4] for e in pl) for pl in plans) == 6 and min(sum(e[4] for e in pl) for pl in plans) == 2
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 24, 61])
+def test_symmetric_jacobi_matches_lapack(n):
+    rng = np.random.default_rng(100 + n)
+    a = rng.normal(size=(n, n))
+    a = (a + a.T) / 2
+    w, z = pkg.host_symmetric_eigen(a)
+    np.testing.assert_allclose(w, np.linalg.eigvalsh(a), atol=1e-13 * max(1.0, np.abs(a).max()) * n)
+    assert np.abs(z.T @ z - np.eye(n)).max() < 1e-13
+    assert np.abs(a @ z - z * w).max() < 1e-12 * max(1.0, np.abs(a).max()) * n
+
+
+def test_symmetric_jacobi_on_thick_restart_arrowhead():
+    """The projected matrix after a thick restart: diag(theta) with an arrow at row/column k, tridiagonal tail."""
+    k, m = 6, 20
+    rng = np.random.default_rng(5)
+    t = np.diag(np.sort(rng.uniform(0, 1, m)))
+    t[:k, k] = t[k, :k] = 1e-3 * rng.normal(size=k)
+    for i in range(k, m - 1):
+        t[i, i + 1] = t[i + 1, i] = rng.uniform(0.1, 0.5)
+    w, z = pkg.host_symmetric_eigen(t)
+    np.testing.assert_allclose(w, np.linalg.eigvalsh(t), atol=1e-14)
+    assert np.abs(t @ z - z * w).max() < 1e-14
+    # degenerate and tiny couplings do not stall the sweeps
+    t2 = np.diag([1.0, 1.0, 1.0, 2.0])
+    t2[0, 3] = t2[3, 0] = 1e-200
+    w2, _ = pkg.host_symmetric_eigen(t2)
+    np.testing.assert_allclose(w2, [1, 1, 1, 2], atol=1e-15)
