@@ -732,7 +732,14 @@ int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double thresho
     std::vector<Chunk> chunks;
     const int c = K->ndefl + k + 1;
     contiguous_chunks(K, 0, c, chunks);
-    rc = gram_schmidt2(K, chunks, K->v, K->w, K->scal);
+    if (ctx->mail_ok && chunks.size() == 1) {
+      // row-partitioned fast path: the coefficient reductions go through the peer-memory mailboxes (reduced h1, h2
+      // are written back to K->h1 / K->h2, ||w||^2 to K->scal[0]) — no collective kernel inside the chain
+      unsigned long long unused_seq = 0;
+      rc = gram_schmidt2_mailed(K, chunks[0], K->v, K->w, &unused_seq);
+    } else {
+      rc = gram_schmidt2(K, chunks, K->v, K->w, K->scal);
+    }
     if (rc != CMB_OK) break;
     double* slot = hist + size_t(s) * (2 * hstride + 1);
     cudaMemcpyAsync(slot, K->h1, sizeof(double) * c * es, cudaMemcpyDeviceToDevice, ctx->stream);
@@ -758,6 +765,14 @@ int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double thresho
   }
   pool_free(ctx, hist);
   CMB_TRY(rc);
+  if (ctx->mail_ok) {
+    int mail_err = 0;
+    CMB_CUDA(cudaMemcpy(&mail_err, ctx->d_mail_error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (mail_err) {
+      set_error("a peer rank never published its Gram-Schmidt partials or halo values (wait timed out)");
+      return CMB_ERR_NCCL;
+    }
+  }
   // steps are valid until a residue <= threshold appears (that step is still valid; the next one was refused)
   double* hs = K->h_stage;
   int64_t done = 0;
