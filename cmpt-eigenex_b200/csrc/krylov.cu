@@ -159,18 +159,27 @@ static int gram_schmidt2_mailed(cmb_krylov* K, const Chunk& c, const double* x, 
   CMB_TRY(cgs_pass(ctx, K->cplx, CGS_DOT, p));
   // pass 2: h1 = sum of partials ; y = x - V h1 ; partial h2 -> mailboxes
   // (also ||y||^2, so that the third pass needs no reduction of its own: ||y - V h2||^2 = ||y||^2 - |h2|^2)
+  // The identity needs orthonormal columns: the Krylov vectors are (to rounding), user-supplied deflation vectors
+  // need not be, so with deflation vectors the norm keeps its own reduction.
+  const bool trick = (K->ndefl == 0);
   p.y = y;
   p.pull = mail_pull_of(ctx, s1, K->h1);
   p.push = mail_next_push(ctx);
-  p.norm_trick = 1;
+  p.norm_trick = trick ? 1 : 0;
   const unsigned long long s2 = p.push.seq;
   CMB_TRY(cgs_pass(ctx, K->cplx, CGS_UPDATE_DOT, p));
-  // pass 3: y -= V h2 ; ||y||^2 from the reduced h2 and ||y_before||^2 (same bits on every rank) -> K->scal[0]
   p.x = y;
   p.pull = mail_pull_of(ctx, s2, K->h2);
-  p.push = MailPush();
-  p.hout = K->scal;
-  *nrm2_seq = 0;  // the norm is a plain device scalar: the operator apply needs no mailbox
+  if (trick) {
+    // pass 3: y -= V h2 ; ||y||^2 from the reduced h2 and ||y_before||^2 (same bits on every rank) -> K->scal[0]
+    p.push = MailPush();
+    p.hout = K->scal;
+    *nrm2_seq = 0;  // the norm is a plain device scalar: the operator apply needs no mailbox
+  } else {
+    // pass 3: y -= V h2 ; partial ||y||^2 -> mailboxes, summed in the prologue of the operator apply
+    p.push = mail_next_push(ctx);
+    *nrm2_seq = p.push.seq;
+  }
   CMB_TRY(cgs_pass(ctx, K->cplx, CGS_UPDATE_NORM, p));
   return CMB_OK;
 }
@@ -732,11 +741,11 @@ int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double thresho
     std::vector<Chunk> chunks;
     const int c = K->ndefl + k + 1;
     contiguous_chunks(K, 0, c, chunks);
-    if (ctx->mail_ok && chunks.size() == 1) {
+    if (ctx->mail_ok && chunks.size() == 1 && K->ndefl == 0) {
       // row-partitioned fast path: the coefficient reductions go through the peer-memory mailboxes (reduced h1, h2
       // are written back to K->h1 / K->h2, ||w||^2 to K->scal[0]) — no collective kernel inside the chain
-      unsigned long long unused_seq = 0;
-      rc = gram_schmidt2_mailed(K, chunks[0], K->v, K->w, &unused_seq);
+      unsigned long long norm_seq = 0;  // stays 0 without deflation vectors: the norm is in K->scal[0]
+      rc = gram_schmidt2_mailed(K, chunks[0], K->v, K->w, &norm_seq);
     } else {
       rc = gram_schmidt2(K, chunks, K->v, K->w, K->scal);
     }

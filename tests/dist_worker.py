@@ -194,6 +194,51 @@ def gpu_main():
     assert np.abs(xs - xf[r0:r1]).max() < 1e-10 * np.abs(xf).max()
     es.close()
     op.close()
+    # deflation vectors on a row-partitioned operator (they keep the norm's own reduction, see gram_schmidt2_mailed):
+    # two exact eigenvectors of the 2D Laplacian are projected out, Lanczos and Arnoldi must agree with the oracle
+    N = 16
+    n = N * N
+    full = syn.laplacian2d_csr(N)
+    r0, r1 = dist.row_range(n)
+    shard = syn.laplacian2d_csr(N, r0, r1)
+    ii, jj = np.meshgrid(np.arange(1, N + 1), np.arange(1, N + 1), indexing="ij")
+    defl = []
+    for (p_, q_) in ((1, 1), (1, 2)):
+        e = (np.sin(p_ * np.pi * ii / (N + 1)) * np.sin(q_ * np.pi * jj / (N + 1))).reshape(-1)
+        defl.append(e / np.linalg.norm(e))
+    x0 = syn.start_vector(n, seed=13)
+    op = pkg.DeviceOperator.from_csr(ctx, *shard, n_global=n, row_begin=r0)
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(op).setInitialVector(x0[r0:r1]).setOrthogonalizingVectors([d[r0:r1] for d in defl])
+    es.setMinIterations(50).setMaxIterations(50).setMaxEigenvalues(2)
+    es.compute()
+    ref = rs.LanczosEigenSolver("d")
+    ref.set_matrix_multiplication(core.Operator.csr(*full))
+    ref.init, ref.ortho = x0, defl
+    ref.min_iterations = ref.max_iterations = 50
+    ref.max_eigenvalues = 2
+    ref.compute()
+    ra, rb = ref.alpha_beta()
+    assert np.abs(es.alpha() - ra).max() < 1e-11 and np.abs(es.beta() - rb).max() < 1e-11
+    lam = np.sort((4 - 2 * np.cos(ii * np.pi / (N + 1)) - 2 * np.cos(jj * np.pi / (N + 1))).reshape(-1))
+    # lam[0] is gone; the level lam[1] = lam[2] is doubly degenerate and only one copy was deflated
+    assert es.eigenvalues()[0] > lam[1] - 1e-9 and es.eigenvalues()[0] > lam[0] + 1e-3
+    Xd = gather_rows(es.eigenvectors(), n, td)
+    assert max(abs(d @ Xd[:, 0]) for d in defl) < 1e-10
+    es.close()
+    ea = pkg.ArnoldiEigenSolver(np.float64)
+    ea.setMatrixMultiplication(op).setInitialVector(x0[r0:r1]).setOrthogonalizingVectors([d[r0:r1] for d in defl])
+    ea.setMinIterations(20).setMaxIterations(20).setMaxEigenvalues(1)
+    ea.compute()
+    refa = rs.ArnoldiEigenSolver("d")
+    refa.set_matrix_multiplication(core.Operator.csr(*full))
+    refa.init, refa.ortho = x0, defl
+    refa.min_iterations = refa.max_iterations = 20
+    refa.max_eigenvalues = 1
+    refa.compute()
+    assert np.abs(ea.hessenbergMatrix()[:, :8] - refa.hessenberg[:, :8]).max() < 1e-10
+    ea.close()
+    op.close()
     # one-directional coupling (rank q reads from rank q+1 only): ranks that receive nothing still follow the protocol
     nu = 64
     r0, r1 = dist.row_range(nu)
