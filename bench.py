@@ -290,6 +290,8 @@ def run_ours(args):
             pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "peak_note": "the measured peak is a copy (half reads, half writes); the CGS passes read c+1 vectors per "
+                             "vector written, so frac can exceed 1 — ncu's DRAM peak on this part is about 8.19 TB/s",
                 "bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_s * 1e3,
                 "families": {k: {"ms": fams[k][0], "launches": fams[k][1],
                                  "GBps": (alg[k] * args.steps / (fams[k][0] * 1e-3) / 1e9) if (k in alg and fams[k][0] > 0) else None}
