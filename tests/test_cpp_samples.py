@@ -24,6 +24,23 @@ def test_samples_are_built():
         assert os.path.exists(os.path.join(BIN, n))
 
 
+def test_headers_compile_in_eigen_mode_against_api_stub():
+    """The image has no Eigen, so the headers' `CMPT_EIGENEX_HAVE_EIGEN` branch would never be compiled.  A stub
+    Eigen/Core with Eigen 3's signatures (tests/cpp/eigen_stub; nothing beyond what Eigen offers) lets the compiler
+    check that branch: every sample must at least parse and type-check with Eigen-style vectors and matrices."""
+    inc = ["-I" + os.path.join(ROOT, "tests", "cpp", "eigen_stub"), "-I" + os.path.join(ROOT, "include")]
+    srcs = sorted(f for f in os.listdir(os.path.join(ROOT, "samples")) if f.endswith(".cpp"))
+    assert len(srcs) >= 7
+    for f in srcs:
+        p = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", *inc, os.path.join(ROOT, "samples", f)],
+                           capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, f + "\n" + p.stderr[-3000:]
+    # the branch really was taken
+    p = subprocess.run(["g++", "-std=c++17", "-E", *inc, os.path.join(ROOT, "samples", "sample_lanczos1.cpp")],
+                       capture_output=True, text=True, timeout=300)
+    assert "stub_detail" in p.stdout
+
+
 def test_vector_map_algebra_host_only():
     # SURVEY.md §8(f) rank 4: VectorMap (sums, products, scalar multiples, composition, size checks) — pure host code
     exe = os.path.join(ROOT, "tests", "cpp", "bin", "test_vector_map")
