@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcmpt_b200.so")
 
 CMB_F64, CMB_C64 = 0, 1
-CMBS_LANCZOS, CMBS_ARNOLDI = 0, 1
+CMBS_LANCZOS, CMBS_ARNOLDI, CMBS_THICK_RESTART = 0, 1, 2
 CMB_OK = 0
 CMB_ERR_NO_DEVICE = -6
 STEP_OK, STEP_BREAKDOWN, STEP_NOSTART, STEP_FULL = 0, 1, 2, 4

@@ -7,6 +7,7 @@
 
 #include "cmpt/eigen_ex/arnoldi.hpp"
 #include "cmpt/eigen_ex/lanczos.hpp"
+#include "cmpt/eigen_ex/thick_restart.hpp"
 #include "cmpt/eigen_ex/detail/symmetric_eigen.hpp"
 #include "cmpt_b200_solver.h"
 #include "common.cuh"
@@ -279,6 +280,106 @@ struct ArnoldiS : Common<ArnoldiEigenSolver<Scalar>> {
   double bytes() override { return es.arnoldiBase().deviceBytes(); }
 };
 
+// ThickRestartLanczos<Scalar> (additive solver, thick_restart.hpp): the subset of the interface that applies to it.
+template <class Scalar>
+struct ThickS : cmbs_solver {
+  using Solver = ThickRestartLanczos<Scalar>;
+  using Index = typename Solver::Index;
+  Solver es;
+  [[noreturn]] static void no(const char* what) {
+    throw LanczosException(std::string(what) + " is not available for the thick-restart solver");
+  }
+  void set_operator(cmb_op* op) override { es.setMatrixMultiplication(DeviceOperator<Scalar>::borrow(op)); }
+  void set_callback(int64_t n, cmb_matmul_fn fn, void* user) override {
+    es.setMatrixMultiplication([fn, user](const Scalar* in, Scalar* out) { fn(in, out, user); }, Index(n));
+  }
+  bool set_int(const std::string& k, int64_t v) override {
+    if (k == "wanted") es.setWanted(v);
+    else if (k == "maxBasis") es.setMaxBasis(v);
+    else if (k == "keep") es.setKeep(v);
+    else if (k == "maxRestarts") es.setMaxRestarts(v);
+    else if (k == "computeEigenvectorsOn") es.setComputeEigenvectorsOn(v != 0);
+    else return false;
+    return true;
+  }
+  bool set_real(const std::string& k, double v) override {
+    if (k == "tolerance") es.setTolerance(v);
+    else if (k == "threshold") es.setThreshold(v);
+    else if (k == "eigenvalueShift") es.setEigenvalueShift(v);
+    else return false;
+    return true;
+  }
+  bool set_complex(const std::string&, double, double) override { return false; }
+  bool get_int(const std::string& k, int64_t* v) override {
+    if (k == "wanted") *v = es.wanted();
+    else if (k == "maxBasis") *v = es.maxBasis();
+    else if (k == "keep") *v = es.keep();
+    else if (k == "maxRestarts") *v = es.maxRestarts();
+    else if (k == "restarts") *v = es.restarts();
+    else if (k == "operatorApplications" || k == "iterations") *v = es.operatorApplications();
+    else if (k == "converged") *v = es.converged();
+    else if (k == "neigenvalues") *v = es.eigenvalues().size();
+    else if (k == "nlog") *v = int64_t(es.log().size());
+    else if (k == "nvectors") *v = es.lanczosBase().lanczosvectorsSize();
+    else if (k == "matrixHeight") *v = es.lanczosBase().matrixHeight();
+    else if (k == "localHeight") *v = es.localHeight();
+    else if (k == "hasWARN" || k == "hasERROR") {
+      const std::string head = (k == "hasWARN") ? Solver::headWARN() : std::string("ERROR     ");
+      int64_t c = 0;
+      for (const auto& l : es.log()) c += (l.find(head) == 0);
+      *v = c;
+    } else return false;
+    return true;
+  }
+  bool get_real(const std::string& k, double* v) override {
+    if (k == "tolerance") *v = es.tolerance();
+    else return false;
+    return true;
+  }
+  void set_indices(const int64_t*, int64_t) override { no("indicesForConvergence"); }
+  void set_initial(const void* v, int64_t n) override {
+    if (n == 0) {
+      es.setInitialVector();
+      return;
+    }
+    typename Solver::VectorType x(n);
+    memcpy(x.data(), v, sizeof(Scalar) * size_t(n));
+    es.setInitialVector(x);
+  }
+  void set_ortho(int64_t nvec, const void* vecs, int64_t ld) override {
+    std::vector<typename Solver::VectorType> o;
+    const Scalar* p = static_cast<const Scalar*>(vecs);
+    const Index n = es.localHeight();
+    for (int64_t j = 0; j < nvec; ++j) {
+      typename Solver::VectorType x(n);
+      memcpy(x.data(), p + size_t(j) * ld, sizeof(Scalar) * size_t(n));
+      o.push_back(std::move(x));
+    }
+    es.setOrthogonalizingVectors(o);
+  }
+  void compute() override { es.compute(); }
+  void continue_compute() override { no("continueToCompute"); }
+  void clear() override { es = Solver(); }
+  void clear_computed() override { no("clearComputedData"); }
+  void eigenvalues(void* out) override {
+    double* o = static_cast<double*>(out);
+    for (Index i = 0; i < Index(es.eigenvalues().size()); ++i) o[i] = es.eigenvalues()[i];
+  }
+  void eigenvectors_ptr(const void** p, int64_t* r, int64_t* c) override {
+    *p = es.eigenvectors().data();
+    *r = es.eigenvectors().rows();
+    *c = es.eigenvectors().cols();
+  }
+  void residuals(double* out) override {
+    for (Index i = 0; i < Index(es.residuals().size()); ++i) out[i] = es.residuals()[i];
+  }
+  void small_vectors(void*, int64_t*, int64_t*) override { no("the projected eigenvectors"); }
+  void basis_vector(int64_t, void*) override { no("basis vectors"); }
+  const std::vector<std::string>& log() override { return es.log(); }
+  void conv_log(int64_t, void*, int64_t* n) override { *n = 0; }
+  double bytes() override { return es.deviceBytes(); }
+};
+
 template <class F>
 int guarded(F&& f) {
   try {
@@ -313,6 +414,8 @@ int cmbs_create(int kind, cmb_dtype dtype, cmbs_solver** out) {
     else if (kind == CMBS_LANCZOS && dtype == CMB_C64) s = new LanczosS<std::complex<double>>();
     else if (kind == CMBS_ARNOLDI && dtype == CMB_F64) s = new ArnoldiS<double>();
     else if (kind == CMBS_ARNOLDI && dtype == CMB_C64) s = new ArnoldiS<std::complex<double>>();
+    else if (kind == CMBS_THICK_RESTART && dtype == CMB_F64) s = new ThickS<double>();
+    else if (kind == CMBS_THICK_RESTART && dtype == CMB_C64) s = new ThickS<std::complex<double>>();
     S_REQ(s, "unknown solver kind / dtype");
     s->kind = kind;
     s->dtype = dtype;

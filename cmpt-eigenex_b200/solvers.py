@@ -397,6 +397,46 @@ class LanczosEigenSolver(_Solver):
         return out
 
 
+class ThickRestartLanczos(_Solver):
+    """cmpt::EigenEx::ThickRestartLanczos<Scalar> (include/cmpt/eigen_ex/thick_restart.hpp; additive): the lowest
+    `wanted` eigenpairs with at most `maxBasis` Lanczos vectors on the device."""
+
+    kind = capi.CMBS_THICK_RESTART
+
+    def _vec_dtype(self):
+        return self.dtype
+
+    def setWanted(self, v):
+        return self._seti("wanted", v)
+
+    def setMaxBasis(self, v):
+        return self._seti("maxBasis", v)
+
+    def setKeep(self, v):
+        return self._seti("keep", v)
+
+    def setMaxRestarts(self, v):
+        return self._seti("maxRestarts", v)
+
+    def eigenvalues(self):
+        out = np.empty(self._geti("neigenvalues"))
+        if out.size:
+            check(lib().cmbs_get_eigenvalues(self.h, ptr(out)))
+        return out
+
+    def residuals(self):
+        return self.ritzResiduals()
+
+    def restarts(self):
+        return self._geti("restarts")
+
+    def operatorApplications(self):
+        return self._geti("operatorApplications")
+
+    def converged(self):
+        return self._geti("converged")
+
+
 class ArnoldiEigenSolver(_Solver):
     """cmpt::EigenEx::ArnoldiEigenSolver<Scalar> (arnoldi.hpp:444-1027) on the GPU."""
 

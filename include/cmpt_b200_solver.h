@@ -5,7 +5,7 @@
  * language (the Python tests and bench.py use ctypes) drives the same classes through this binding, which
  * adds nothing of its own: each function forwards to the member of the same name.
  *
- * kind: CMBS_LANCZOS or CMBS_ARNOLDI; dtype: CMB_F64 or CMB_C64 (Scalar = double / std::complex<double>).
+ * kind: CMBS_LANCZOS, CMBS_ARNOLDI or CMBS_THICK_RESTART (integer settings wanted / maxBasis / keep / maxRestarts); dtype: CMB_F64 or CMB_C64 (Scalar = double / std::complex<double>).
  * Vectors are contiguous arrays of dtype elements; matrices are column-major.  Lanczos eigenvalues are double,
  * Arnoldi eigenvalues/eigenvectors are complex (interleaved re,im) for both dtypes.
  */
@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 typedef struct cmbs_solver cmbs_solver;
-enum { CMBS_LANCZOS = 0, CMBS_ARNOLDI = 1 };
+enum { CMBS_LANCZOS = 0, CMBS_ARNOLDI = 1, CMBS_THICK_RESTART = 2 /* additive: ThickRestartLanczos */ };
 
 int cmbs_create(int kind, cmb_dtype dtype, cmbs_solver** out);
 int cmbs_destroy(cmbs_solver* s);

@@ -76,3 +76,52 @@ def test_thick_restart_structure_and_convergence():
     capi.check(lib.cmb_krylov_destroy(kh))
     op.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_thick_restart_solver_binding(dtype):
+    """ThickRestartLanczos through the solver binding: lowest pairs of a rectangular 2D Laplacian (real) and of the
+    Hermitian chain (complex) with a basis that could never hold an unrestarted run."""
+    ctx = pkg.Context(0)
+    if dtype == np.float64:
+        nx, ny = 60, 47
+        n = nx * ny
+        ii, jj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+        rows, cols, vals = [], [], []
+        for di, dj, v in ((0, 0, 4.0), (1, 0, -1.0), (-1, 0, -1.0), (0, 1, -1.0), (0, -1, -1.0)):
+            ok = (ii + di >= 0) & (ii + di < nx) & (jj + dj >= 0) & (jj + dj < ny)
+            rows.append((ii * ny + jj)[ok])
+            cols.append(((ii + di) * ny + jj + dj)[ok])
+            vals.append(np.full(ok.sum(), v))
+        import scipy.sparse as sp
+
+        A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+        A.sort_indices()
+        rp, c, v = A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data
+        ex = np.sort((4 - 2 * np.cos(np.arange(1, nx + 1)[:, None] * np.pi / (nx + 1))
+                      - 2 * np.cos(np.arange(1, ny + 1)[None, :] * np.pi / (ny + 1))).reshape(-1))
+    else:
+        n = 200
+        rp, c, v = syn.hermitian_chain_csr(n)
+        ex = np.sort(2 * np.cos(np.arange(1, n + 1) * np.pi / (n + 1)))
+    op = pkg.DeviceOperator.from_csr(ctx, rp, c, v)
+    tr = pkg.ThickRestartLanczos(dtype)
+    tr.setMatrixMultiplication(op).setInitialVector(syn.start_vector(n, seed=3, dtype=dtype))
+    tr.setWanted(4).setMaxBasis(24).setTolerance(1e-11).setMaxRestarts(500)
+    tr.compute()
+    assert tr.converged() == 4 and tr.restarts() > 0
+    assert tr.nvectors() <= 24
+    np.testing.assert_allclose(tr.eigenvalues(), ex[:4], atol=1e-9)
+    X = tr.eigenvectors()
+    assert X.shape == (n, 4)
+    import scipy.sparse as sp
+
+    A = sp.csr_matrix((v, c, rp), shape=(n, n))
+    res = np.linalg.norm(A @ X - X * tr.eigenvalues(), axis=0)
+    assert res.max() < 1e-8 and np.all(np.abs(res - tr.residuals()) < 1e-8)
+    assert any("thick-restart lanczos converged" in line for line in tr.log())
+    with pytest.raises(capi.CmbError):
+        tr.continueToCompute()
+    tr.close()
+    op.close()
+    ctx.close()
