@@ -125,3 +125,21 @@ def test_thick_restart_solver_binding(dtype):
     tr.close()
     op.close()
     ctx.close()
+
+
+def test_thick_restart_two_lowest_states_of_the_heisenberg_ring():
+    """SURVEY.md Appendix E known answers at scale: ground state and first excited level of the L = 20 ring
+    (matrix-free operator, 2^20 states) with at most 20 Lanczos vectors on the device."""
+    L = 20
+    ctx = pkg.Context(0)
+    op = pkg.DeviceOperator.heisenberg(ctx, L)
+    tr = pkg.ThickRestartLanczos(np.float64)
+    tr.setMatrixMultiplication(op).setInitialVector(syn.start_vector(1 << L, seed=7))
+    tr.setWanted(2).setMaxBasis(20).setTolerance(1e-9).setMaxRestarts(200).setComputeEigenvectorsOn(False)
+    tr.compute()
+    assert tr.converged() == 2 and tr.nvectors() <= 20
+    e = tr.eigenvalues()
+    assert abs(e[0] - (-8.904386529876)) < 1e-9 and abs(e[1] - (-8.686440986187)) < 1e-8
+    tr.close()
+    op.close()
+    ctx.close()
