@@ -41,6 +41,22 @@ def test_headers_compile_in_eigen_mode_against_api_stub():
     assert "stub_detail" in p.stdout
 
 
+def test_host_headers_against_the_oracle_streams():
+    """Host-only: LanczosBase::makeRandomVector (std::mt19937 + normal_distribution, lanczos.hpp:124-135,
+    random.hpp:89-101) must reproduce the stream the oracle restates, for real and complex Scalar; the binary also
+    self-checks the util.hpp shuffles and the TripletsMatrix container."""
+    from oracle import core
+
+    exe = os.path.join(ROOT, "tests", "cpp", "bin", "test_host_headers")
+    assert os.path.exists(exe), "host tests are built by __graft_entry__.build()"
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0 and p.stdout.strip().endswith("PASS"), p.stdout + p.stderr
+    lines = {ln.split()[0]: [float(t) for t in ln.split()[1:]] for ln in p.stdout.splitlines() if ln.startswith("random_")}
+    np.testing.assert_allclose(lines["random_d"], core.seeded_vector(1, 7, "d"), rtol=0, atol=1e-16)
+    z = np.array(lines["random_z"]).reshape(-1, 2)
+    np.testing.assert_allclose(z[:, 0] + 1j * z[:, 1], core.seeded_vector(1, 5, "z"), rtol=0, atol=1e-16)
+
+
 def test_vector_map_algebra_host_only():
     # SURVEY.md §8(f) rank 4: VectorMap (sums, products, scalar multiples, composition, size checks) — pure host code
     exe = os.path.join(ROOT, "tests", "cpp", "bin", "test_vector_map")
