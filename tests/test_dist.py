@@ -55,6 +55,24 @@ def test_world_size_2_gloo_cpu():
     assert p.returncode == 0 and "DIST_CPU_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
 
 
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """bench.py --impl reference launched like the driver does for N > 1: rank 0 alone runs the CPU oracle on a bounded
+    sample and prints ONE JSON line, the other rank exits 0 without output (small grid here to keep the suite fast)."""
+    import json
+
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29633", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "0", "--grid", "96", "--cpu-sample-m", "6"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ))
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["metric"] == "krylov_iterations_per_sec"
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
 @pytest.mark.gpu
 def test_two_ranks_on_two_gpus_match_oracle():
     n = C.c_int(0)
