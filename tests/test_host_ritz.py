@@ -105,6 +105,26 @@ def test_no_silent_cpu_fallback_without_gpu():
     assert b"no CPU fallback" in capi.lib().cmb_last_error()
 
 
+def test_bench_and_smoke_fail_loudly_without_gpu():
+    """The product path must not fall back to the oracle: without a GPU bench.py's own arm and smoke() exit non-zero
+    with the library's "no CPU fallback" error (the oracle is only the checker / the reference arm)."""
+    import os
+    import subprocess
+    import sys
+
+    n = ctypes.c_int(-1)
+    capi.check(capi.lib().cmb_device_count(ctypes.byref(n)))
+    if n.value > 0:
+        pytest.skip("a GPU is visible")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0", "--grid", "64"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode != 0 and "no CPU fallback" in p.stderr and not any(ln.startswith("{") for ln in p.stdout.splitlines())
+    p = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, capture_output=True,
+                       text=True, timeout=300)
+    assert p.returncode != 0 and "no CPU fallback" in p.stderr
+
+
 @pytest.mark.parametrize("L,pbc,nranks", [(10, True, 2), (12, True, 4), (12, False, 4), (30, True, 8), (20, True, 16),
                                           (9, False, 1)])
 def test_heisenberg_exchange_plan_is_consistent_between_partners(L, pbc, nranks):
