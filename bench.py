@@ -1,28 +1,37 @@
 #!/usr/bin/env python
-"""bench.py — Krylov iterations/s of the Lanczos hot path (BASELINE.json metric) on N B200s.
+"""bench.py — Krylov iterations/s of the Lanczos / Arnoldi hot path (BASELINE.json metric) on N B200s.
 
-Workload (config.workload): BASELINE cfg 2 — Lanczos with full reorthogonalisation on the 2D 5-point
-Laplacian, 4096 x 4096 grid (16.8M rows, 83.9M non-zeros, CSR -> SELL-32 on the device), m = 100
-(reference semantics: setMinIterations(m); setMaxIterations(m) => 101 vectors, 101 operator applies),
-lowest 5 eigenpairs, explicit start vector (splitmix64 seed 7).  At N > 1 the same problem is
-row-partitioned over the ranks (strong scaling).
+Default workload (config.workload): BASELINE cfg 2 — Lanczos with full reorthogonalisation on the 2D 5-point
+Laplacian, 4096 x 4096 grid (16.8M rows, 83.9M non-zeros, CSR -> SELL on the device), m = 100 (reference
+semantics: setMinIterations(m); setMaxIterations(m) => 101 vectors, 101 operator applies), lowest 5 eigenpairs,
+explicit start vector (splitmix64 seed 7).  At N > 1 the same problem is row-partitioned over the ranks (strong
+scaling).  `--config {1,3,4,5}` selects the other BASELINE configs with the same contract:
+  1  dense symmetric n=2000, Lanczos m=100 (L2-resident, launch-latency bound)
+  3  3D convection-diffusion 256^3 CSR, Arnoldi m=50 per restart cycle, 5 largest eigenvalues
+  4  Heisenberg ring L=24 as explicit CSR, Lanczos m=100 (row-sharded for N > 1)
+  5  matrix-free Heisenberg ring, Lanczos m=40; L = 30 on 8 GPUs, L = 27 + log2(N) otherwise (weak scaling: one
+     GPU holds 2^27 states x 43 vectors = 46 GB, the per-GPU share of the L=30 run)
 
 One "step" = one full solve (compute()).
-  value : m * steps / device time of the Krylov loops (operator already in HBM; start-vector upload
-          and the host Ritz solves are inside the timed region), CUDA events on the library's stream,
-          max over ranks.
-  e2e   : the same metric through the solver API with HOST buffers: CSR arrays and start vector in
-          pinned host memory -> operator build (H2D + SELL conversion) -> compute() with the 5 Ritz
-          vectors -> eigenvalues/eigenvectors back on the host.  Wall clock around synchronised calls.
-  roofline : the dominant kernel family (CGS2 passes), algorithmic bytes per launch / mean launch
-          duration from CUDA events recorded around every launch inside the timed region.
-  cpu_baseline / --impl reference : the CPU oracle (restatement of the reference's algorithm:
-          single-pass MGS as separate dot/axpy sweeps, tridiagonal solve every trip; the reference
-          itself cannot be built here, Eigen3 is absent) on the box's host cores, on a bounded sample
-          of the same workload (same matrix and start vector, the first m_sample iterations).
+  value : m * steps / device time of the Krylov loops (operator already in HBM; start-vector upload and the host
+          Ritz solves are inside the timed region), CUDA events on the library's stream, max over ranks.
+  e2e   : the same metric through the solver API with HOST buffers: operator arrays and start vector in pinned host
+          memory -> operator build (H2D + SELL conversion) -> compute() with the Ritz vectors -> eigenvalues /
+          eigenvectors back on the host.  Wall clock around synchronised calls.
+  roofline : the dominant kernel family, algorithmic bytes per launch / mean launch duration from CUDA events
+          recorded around every launch inside the timed region.
+  parity : alpha/beta/Ritz values of the timed solve against the reference ITSELF — the full-size recording
+          tests/golden/ref_full_cfg<N>.npz made with oracle/_ref (the unmodified reference classes) — and, at
+          N = 1, against the live cpu_baseline run.  The process exits non-zero when a difference exceeds 1e-10.
+  cpu_baseline / --impl reference : the reference's own CPU implementation (oracle/_ref/libref.so: the unmodified
+          lanczos.hpp / arnoldi.hpp compiled against the stand-in Eigen of oracle/eigen_shim, all host threads) on
+          the same workload.  --impl reference times full-m solves (as many of the requested steps as fit the time
+          budget; at least one); when not even one full solve fits, a shorter solve is timed and scaled by the
+          step-cost model, and the line says "extrapolated": true.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -36,6 +45,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "krylov_iterations_per_sec"
 UNIT = "it/s"
+PARITY_TOL = 1e-10
 
 
 def parse_args():
@@ -44,10 +54,15 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--grid", type=int, default=4096, help="N of the N x N Laplacian grid")
-    ap.add_argument("--m", type=int, default=100, help="Lanczos iterations per solve")
-    ap.add_argument("--nev", type=int, default=5)
-    ap.add_argument("--cpu-sample-m", type=int, default=20, help="iterations of the bounded CPU sample")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--grid", type=int, default=None, help="grid edge (cfg 2: 4096, cfg 3: 256) / n (cfg 1) / L (cfg 4, 5)")
+    ap.add_argument("--krylov-m", dest="m", type=int, default=None, help="Krylov iterations per solve")
+    ap.add_argument("--nev", type=int, default=None)
+    ap.add_argument("--scalar", default="real", choices=["real", "complex"], help="cfg 3 Scalar of the GPU arm")
+    ap.add_argument("--cpu-budget", type=float, default=float(os.environ.get("BENCH_CPU_BUDGET", 40)),
+                    help="seconds of reference CPU work in the cpu_baseline leg of the GPU arm")
+    ap.add_argument("--ref-budget", type=float, default=float(os.environ.get("BENCH_REF_BUDGET", 200)),
+                    help="seconds of timed reference CPU work in --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -115,65 +130,293 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def workload_name(args):
-    return "cfg2: Lanczos full-reorth, 2D 5-pt Laplacian %dx%d CSR (n=%d), m=%d, lowest %d" % (
-        args.grid, args.grid, args.grid * args.grid, args.m, args.nev)
+# -------------------------------------------------------------------------------------------------
+# workloads (BASELINE.json configs)
+# -------------------------------------------------------------------------------------------------
+class Workload:
+    """One BASELINE config: what the operator is, how it is built per rank, which solver runs on it."""
+
+    def __init__(self, args, world):
+        from cmpt_eigenex_b200 import synthetic as syn
+
+        self.syn = syn
+        self.cfg = args.config
+        self.world = world
+        self.kind = "arnoldi" if self.cfg == 3 else "lanczos"
+        self.complex = self.cfg == 3 and args.scalar == "complex"
+        self.dtype = np.complex128 if self.complex else np.float64
+        self.s = 16.0 if self.complex else 8.0
+        if self.cfg == 1:
+            self.size = args.grid or 2000
+            self.n, self.m, self.nev = self.size, args.m or 100, args.nev or 5
+            self.family = "gemv_dense"
+            self.name = "cfg1: Lanczos full-reorth, dense symmetric n=%d, m=%d, lowest %d" % (self.n, self.m, self.nev)
+        elif self.cfg == 2:
+            self.size = args.grid or 4096
+            self.n, self.m, self.nev = self.size ** 2, args.m or 100, args.nev or 5
+            self.family = "spmv_sell"
+            self.name = "cfg2: Lanczos full-reorth, 2D 5-pt Laplacian %dx%d CSR (n=%d), m=%d, lowest %d" % (
+                self.size, self.size, self.n, self.m, self.nev)
+        elif self.cfg == 3:
+            self.size = args.grid or 256
+            self.n, self.m, self.nev = self.size ** 3, args.m or 50, args.nev or 5
+            self.family = "spmv_sell"
+            self.name = "cfg3: Arnoldi m=%d per restart cycle, 3D convection-diffusion %d^3 CSR (n=%d), %d largest |lambda|" % (
+                self.m, self.size, self.n, self.nev)
+        elif self.cfg == 4:
+            self.size = args.grid or 24
+            self.n, self.m, self.nev = 1 << self.size, args.m or 100, args.nev or 5
+            self.family = "spmv_sell"
+            self.name = "cfg4: Lanczos full-reorth, Heisenberg ring L=%d explicit CSR (n=%d), m=%d" % (self.size, self.n, self.m)
+        else:
+            self.size = args.grid or (30 if world == 8 else 27 + int(math.log2(world)))
+            self.n, self.m, self.nev = 1 << self.size, args.m or 40, args.nev or 1
+            self.family = "heisenberg_mf"
+            self.name = "cfg5: Lanczos full-reorth, matrix-free Heisenberg ring L=%d (n=2^%d), m=%d" % (self.size, self.size, self.m)
+        self.scaling = "weak" if (self.cfg == 5 and args.grid is None) else "strong"
+        if self.cfg == 1 and world > 1:
+            raise SystemExit("cfg 1 (dense n=2000) does not shard: run it with --gpus 1")
+
+    def config(self):
+        """Identical in the GPU arm and the reference arm."""
+        return {"workload": self.name, "cfg": self.cfg, "m": self.m, "n": self.n, "nev": self.nev,
+                "start_vector": "splitmix64 seed 7, uniform(-1,1), normalised",
+                "l2": "L2 flushed (256 MiB memset) between timed solves; working set far exceeds the 126 MB L2"
+                if self.cfg != 1 else "L2 flushed between timed solves (32 MB matrix: L2-resident by design, SURVEY.md 8(d) cfg 1)"}
+
+    # ---- host inputs of one rank ----
+    def row_range(self, rank):
+        return (rank * self.n) // self.world, ((rank + 1) * self.n) // self.world
+
+    def host_operator_arrays(self, r0, r1):
+        syn = self.syn
+        if self.cfg == 1:
+            return {"dense": syn.dense_symmetric(self.n, seed=1)}
+        if self.cfg == 2:
+            rp, c, v = syn.laplacian2d_csr(self.size, r0, r1)
+        elif self.cfg == 3:
+            rp, c, v = syn.convdiff3d_csr(self.size, r0=r0, r1=r1)
+        elif self.cfg == 4:
+            rp, c, v = syn.heisenberg_csr(self.size, r0=r0, r1=r1)
+        else:
+            return {}
+        return {"rowptr": rp, "col": c, "val": v.astype(self.dtype)}
+
+    def start_slab(self, r0, r1, all_sum):
+        """local slab of the normalised global start vector x_i = 2u(7,i)-1 (norm over all ranks)"""
+        x = np.empty(r1 - r0)
+        chunk = 1 << 22
+        for s in range(r0, r1, chunk):
+            cnt = min(chunk, r1 - s)
+            x[s - r0: s - r0 + cnt] = 2.0 * self.syn.uniform01(7, s, cnt) - 1.0
+        nrm2 = all_sum(float(x @ x))
+        return (x / np.sqrt(nrm2)).astype(self.dtype)
+
+    def make_operator(self, pkg, ctx, arrays, r0):
+        if self.cfg == 1:
+            return pkg.DeviceOperator.from_dense(ctx, arrays["dense"])
+        if self.cfg == 5:
+            return pkg.DeviceOperator.heisenberg(ctx, self.size, 1.0, True, dtype=self.dtype)
+        return pkg.DeviceOperator.from_csr(ctx, arrays["rowptr"], arrays["col"], arrays["val"], n_global=self.n, row_begin=r0)
+
+    def make_solver(self, pkg, op, x0, vectors):
+        es = (pkg.ArnoldiEigenSolver if self.kind == "arnoldi" else pkg.LanczosEigenSolver)(self.dtype)
+        if op is not None:
+            es.setMatrixMultiplication(op)
+        es.setInitialVector(x0)
+        es.setMinIterations(self.m).setMaxIterations(self.m).setMaxEigenvalues(self.nev)
+        es.setIndicesForConvergence(list(range(self.nev))).setComputeEigenvectorsOn(vectors).setReserveSize(self.m + 1)
+        return es
+
+    # ---- reference (CPU) side: rank 0 only, full problem ----
+    def checker_operator(self, core):
+        syn = self.syn
+        if self.cfg == 1:
+            return core.Operator.dense(syn.dense_symmetric(self.n, seed=1))
+        if self.cfg == 5:
+            return core.Operator.heisenberg(self.size, 1.0, True, "d")
+        rp, c, v = {2: lambda: syn.laplacian2d_csr(self.size), 3: lambda: syn.convdiff3d_csr(self.size),
+                    4: lambda: syn.heisenberg_csr(self.size)}[self.cfg]()
+        # the reference's ArnoldiEigenSolver only compiles for complex Scalar (arnoldi.hpp:857,864)
+        return core.Operator.csr(rp, c, v.astype(complex) if self.cfg == 3 else v)
+
+    def reference_solver(self, ref, op, m, vectors=False):
+        x0 = self.syn.start_vector(self.n, seed=7)
+        if self.kind == "arnoldi":
+            es = ref.ArnoldiEigenSolver("z")
+            x0 = x0.astype(complex)
+        else:
+            es = ref.LanczosEigenSolver("d")
+        es.set_matrix_multiplication(op)
+        es.init = x0
+        es.min_iterations = es.max_iterations = m
+        es.max_eigenvalues = self.nev
+        es.indices_for_convergence = list(range(self.nev))
+        es.compute_eigenvectors_on = vectors
+        return es
+
+    def reference_cost(self, m, op_units):
+        """Memory passes (in units of one vector) of the reference's algorithm for an m-iteration solve: one MGS sweep of
+        dot (2 reads) + axpy (2 reads, 1 write) per basis column, the recurrence, the norm and the scaling, the
+        operator apply and the alpha dot (lanczos.hpp:399-452 / arnoldi.hpp:361-385).  Used only to scale a shorter
+        timed solve when a full one does not fit the time budget."""
+        if self.kind == "lanczos":
+            return sum(5 * c + 12 + op_units for c in range(1, m + 1)) + op_units + 4
+        return sum(5 * c + 6 + op_units for c in range(1, m + 1))
+
+    def fixture(self):
+        """Full-size recording of the reference itself (tests/golden/make_ref_fullsize.py), if this is a BASELINE size."""
+        defaults = {1: 2000, 2: 4096, 3: 256, 4: 24}
+        name = None
+        if self.cfg in defaults and self.size == defaults[self.cfg] and self.m == {1: 100, 2: 100, 3: 50, 4: 100}[self.cfg]:
+            name = "ref_full_cfg%d.npz" % self.cfg
+        if self.cfg == 5 and self.size == 24 and self.m == 40:
+            name = "ref_full_cfg5_L24.npz"
+        if name is None:
+            return None, None
+        path = os.path.join(ROOT, "tests", "golden", name)
+        if not os.path.exists(path):
+            return None, None
+        return np.load(path), "tests/golden/" + name
+
+    def algorithmic_bytes(self, nloc, op_bytes):
+        """Per-solve algorithmic bytes of each kernel family on one rank."""
+        m, s = self.m, self.s
+        cols = range(1, m + 1)
+        napply = m + 1 if self.kind == "lanczos" else m
+        return {"cgs_dot": sum((c + 1) for c in cols) * nloc * s,
+                "cgs_update_dot": sum((c + 2) for c in cols) * nloc * s,
+                "cgs_update_norm": sum((c + 2) for c in cols) * nloc * s,
+                self.family: napply * op_bytes}
 
 
 # -------------------------------------------------------------------------------------------------
-# CPU oracle legs
+# reference (CPU) legs — the only place bench.py touches oracle/
 # -------------------------------------------------------------------------------------------------
-def oracle_sample(args, rp, c, v, x0, m_sample, steps, warmup):
-    """Times the CPU oracle on the first m_sample Lanczos iterations of the workload."""
-    from oracle import core
-    from oracle import reference_solvers as rs
+def reference_timing(wl, budget, steps, label):
+    """Times oracle/_ref (the unmodified reference classes) on the workload.  Returns the cpu_baseline object plus
+    the last solver (for parity) and the number of iterations it ran."""
+    from oracle import core, ref
 
     threads = os.cpu_count() or 1
-    core.set_num_threads(threads)
-    opr = core.Operator.csr(rp, c, v)
-    times = []
-    for i in range(warmup + steps):
-        ref = rs.LanczosEigenSolver("d")
-        ref.set_matrix_multiplication(opr)
-        ref.init = x0
-        ref.min_iterations = ref.max_iterations = m_sample
-        ref.max_eigenvalues = args.nev
-        ref.indices_for_convergence = list(range(args.nev))
-        ref.compute_eigenvectors_on = False
+    core.set_num_threads(threads)  # the operator routine behind the MatMulFunction
+    ref.set_num_threads(threads)   # the stand-in Eigen's vector kernels
+    op = wl.checker_operator(core)
+    n = wl.n
+    sref = 16.0 if wl.kind == "arnoldi" else 8.0
+    op_units = 2.0 + (0.0 if wl.cfg == 5 else 1.5 * (op_nnz(wl) / n))
+    # calibration solve: a few iterations (also warms the allocator and the page cache)
+    m_cal = min(6, wl.m)
+    es = wl.reference_solver(ref, op, m_cal)
+    t0 = time.perf_counter()
+    es.compute()
+    t_cal = time.perf_counter() - t0
+    full_pred = t_cal * wl.reference_cost(wl.m, op_units) / wl.reference_cost(m_cal, op_units)
+    times, extrapolated = [], False
+    if full_pred <= budget or budget <= 0:
+        n_timed = max(1, min(steps, int(budget / max(full_pred, 1e-9)))) if budget > 0 else steps
+        m_run = wl.m
+        for _ in range(n_timed):
+            es = wl.reference_solver(ref, op, m_run)
+            t0 = time.perf_counter()
+            es.compute()
+            times.append(time.perf_counter() - t0)
+        value = wl.m * len(times) / sum(times)
+        ms_per_step = 1e3 * sum(times) / len(times)
+        sample = "%d full solve(s) of the workload (m=%d, n=%d)" % (len(times), wl.m, n)
+    else:
+        extrapolated = True
+        m_run = m_cal
+        while m_run < wl.m and t_cal * wl.reference_cost(m_run + 1, op_units) / wl.reference_cost(m_cal, op_units) <= budget:
+            m_run += 1
+        es = wl.reference_solver(ref, op, m_run)
         t0 = time.perf_counter()
-        ref.compute()
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    total = sum(times)
-    return {"value": m_sample * len(times) / total, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "same matrix/start vector, first %d of %d Lanczos iterations (single-pass MGS as the reference, "
-                      "eigenvectors off), %d timed solve(s), OpenMP over all host threads" % (m_sample, args.m, len(times)),
-            "ms_per_step": 1e3 * total / len(times)}
+        es.compute()
+        t_run = time.perf_counter() - t0
+        t_full = t_run * wl.reference_cost(wl.m, op_units) / wl.reference_cost(m_run, op_units)
+        value = wl.m / t_full
+        ms_per_step = 1e3 * t_full
+        sample = ("first %d of %d iterations of one solve timed (%.1f s), scaled to the full solve by the step-cost model "
+                  "sum_c (5c + const) (EXTRAPOLATED: a full solve was predicted at %.0f s, budget %.0f s)" % (
+                      m_run, wl.m, t_run, full_pred, budget))
+    sample += "; same operator, same start vector, eigenvectors off; reference's single-pass MGS; %s" % label
+    if wl.kind == "arnoldi":
+        sample += "; complex<double> Scalar (the reference's ArnoldiEigenSolver does not compile for real Scalar)"
+    cb = {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
+          "extrapolated": extrapolated, "ms_per_step": ms_per_step, "iterations_run": int(m_run),
+          "what": "oracle/_ref/libref.so = /root/reference lanczos.hpp/arnoldi.hpp unmodified, compiled against oracle/eigen_shim "
+                  "(OpenMP vector kernels), operator = OpenMP host routine of oracle/krylov_oracle.cpp"}
+    del sref
+    return cb, es, m_run
+
+
+def op_nnz(wl):
+    if wl.cfg == 1:
+        return wl.n * wl.n
+    if wl.cfg == 2:
+        return 5 * wl.n - 4 * wl.size
+    if wl.cfg == 3:
+        return 7 * wl.n - 6 * wl.size ** 2
+    if wl.cfg == 4:
+        return wl.n * (1 + wl.size // 2)
+    return 0
+
+
+def parity_against(got, want, label, count=None):
+    """got/want: dicts with alpha/beta (Lanczos) or hessenberg (Arnoldi) and eigenvalues."""
+    out = {"against": label}
+    worst = 0.0
+    scale = 1.0
+    if "alpha" in want and "alpha" in got:
+        k = min(len(got["alpha"]), len(want["alpha"])) if count is None else min(count + 1, len(got["alpha"]), len(want["alpha"]))
+        kb = min(len(got["beta"]), len(want["beta"])) if count is None else min(count, len(got["beta"]), len(want["beta"]))
+        scale = max(1.0, float(np.abs(want["alpha"][:k]).max()))
+        out["max_abs_diff_alpha"] = float(np.abs(got["alpha"][:k] - want["alpha"][:k]).max())
+        out["max_abs_diff_beta"] = float(np.abs(got["beta"][:kb] - want["beta"][:kb]).max()) if kb else 0.0
+        out["iterations_compared"] = int(kb)
+        worst = max(out["max_abs_diff_alpha"], out["max_abs_diff_beta"]) / scale
+    if "hessenberg" in want and "hessenberg" in got:
+        H, Hr = np.asarray(got["hessenberg"]), np.asarray(want["hessenberg"])
+        k = min(8, H.shape[0], Hr.shape[0])
+        scale = max(1.0, float(np.abs(Hr).max()))
+        out["max_abs_diff_hessenberg_leading8"] = float(np.abs(H[:k, :k] - Hr[:k, :k]).max())
+        out["max_abs_diff_hessenberg_all"] = float(np.abs(H[:Hr.shape[0], :Hr.shape[1]] - Hr[:H.shape[0], :H.shape[1]]).max())
+        worst = out["max_abs_diff_hessenberg_leading8"] / scale
+    if count is None and "eigenvalues" in want and len(want["eigenvalues"]) == len(got["eigenvalues"]):
+        ev, rev = np.asarray(got["eigenvalues"]), np.asarray(want["eigenvalues"])
+        if "hessenberg" in want:
+            # unconverged trailing Ritz values of a non-normal H are ill-conditioned: the gate is the leading one
+            rel = np.abs(ev[:1] - rev[:1]) / np.abs(rev[:1])
+            out["max_rel_diff_all_eigenvalues"] = float((np.abs(ev - rev) / np.abs(rev)).max())
+        else:
+            rel = np.abs(ev - rev) / np.maximum(np.abs(rev), 1e-3 * scale)
+        out["max_rel_diff_eigenvalues"] = float(rel.max())
+        worst = max(worst, out["max_rel_diff_eigenvalues"])
+    out["worst"] = worst
+    out["tol"] = PARITY_TOL
+    out["ok"] = bool(worst <= PARITY_TOL)
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from cmpt_eigenex_b200 import synthetic as syn
-
-    N = args.grid
-    rp, c, v = syn.laplacian2d_csr(N)
-    x0 = syn.start_vector(N * N, seed=7)
-    # bound the whole run to a few minutes: shrink the per-step sample when many steps are requested
-    m_sample = args.cpu_sample_m
-    nrun = args.steps + args.warmup
-    while m_sample > 4 and nrun * (m_sample ** 2) > 6 * 20 ** 2:
-        m_sample -= 2
-    cb = oracle_sample(args, rp, c, v, x0, m_sample, args.steps, args.warmup)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = Workload(args, world)
+    if wl.cfg == 5 and wl.size > 26:
+        print(json.dumps({"metric": METRIC, "impl": "reference", "unit": UNIT, "n_gpus": args.gpus, "config": wl.config(),
+                          "unavailable": "2^%d states x %d vectors = %.0f GB of basis does not fit host memory; see --grid 24" % (
+                              wl.size, wl.m + 3, (wl.m + 3) * 8.0 * wl.n / 1e9)}), flush=True)
+        return
+    cb, es, m_run = reference_timing(wl, args.ref_budget, max(1, args.steps), "warm-up = one %d-iteration calibration solve" % min(6, wl.m))
     line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "note": "CPU oracle port of the reference algorithm; the "
-                       "reference itself needs Eigen3, which is not installed"},
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "scaling": wl.scaling, "vs_baseline": None, "dtype": "c128" if wl.kind == "arnoldi" else "f64", "data": "synthetic",
+            "config": wl.config(),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated", "what")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "detail": {"lowest_eigenvalues": [complex(x).real for x in np.asarray(es.eigenvalues)[:5]], "iterations_run": m_run}}
     print(json.dumps(line), flush=True)
 
 
@@ -183,7 +426,6 @@ def run_reference(args):
 def run_ours(args):
     import cmpt_eigenex_b200 as pkg
     from cmpt_eigenex_b200 import capi
-    from cmpt_eigenex_b200 import synthetic as syn
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -196,20 +438,6 @@ def run_ours(args):
         ctx = pkg.Context(0)
         dist = None
 
-    N, m, nev = args.grid, args.m, args.nev
-    n = N * N
-    r0, r1 = (rank * n) // world, ((rank + 1) * n) // world
-    nloc = r1 - r0
-    rp, c, v = syn.laplacian2d_csr(N, r0, r1)
-    nnz_local = int(rp[-1])
-    # inputs staged in pinned host memory (what the e2e region copies from)
-    prp, pc, pv = capi.PinnedBuffer(rp.shape, np.int64), capi.PinnedBuffer(c.shape, np.int32), capi.PinnedBuffer(v.shape, np.float64)
-    prp.array[:], pc.array[:], pv.array[:] = rp, c, v
-    x0_full = syn.start_vector(n, seed=7)
-    px = capi.PinnedBuffer((nloc,), np.float64)
-    px.array[:] = x0_full[r0:r1]
-    del rp, c, v
-
     def barrier():
         if dist is not None:
             dist.barrier()
@@ -217,18 +445,28 @@ def run_ours(args):
     def max_over_ranks(x):
         return dist.all_max(x) if dist is not None else x
 
-    def make_solver(op, vectors):
-        es = pkg.LanczosEigenSolver(np.float64)
-        if op is not None:
-            es.setMatrixMultiplication(op)
-        es.setInitialVector(px.array)
-        es.setMinIterations(m).setMaxIterations(m).setMaxEigenvalues(nev)
-        es.setIndicesForConvergence(list(range(nev))).setComputeEigenvectorsOn(vectors).setReserveSize(m + 1)
-        return es
+    def sum_over_ranks(x):
+        return dist.all_sum(x) if dist is not None else x
+
+    wl = Workload(args, world)
+    m, nev = wl.m, wl.nev
+    r0, r1 = wl.row_range(rank)
+    nloc = r1 - r0
+    # inputs staged in pinned host memory (what the e2e region copies from)
+    arrays = wl.host_operator_arrays(r0, r1)
+    pinned = {}
+    for k, a in arrays.items():
+        pb = capi.PinnedBuffer(a.shape, a.dtype)
+        pb.array[...] = a
+        pinned[k] = pb
+    host = {k: pb.array for k, pb in pinned.items()}
+    del arrays
+    px = capi.PinnedBuffer((nloc,), wl.dtype)
+    px.array[:] = wl.start_slab(r0, r1, sum_over_ranks)
 
     # ---- device-resident leg: operator in HBM, Krylov loop timed with CUDA events ----
-    op = pkg.DeviceOperator.from_csr(ctx, prp.array, pc.array, pv.array, n_global=n, row_begin=r0)
-    es = make_solver(op, vectors=False)
+    op = wl.make_operator(pkg, ctx, host, r0)
+    es = wl.make_solver(pkg, op, px.array, vectors=False)
     for _ in range(args.warmup):
         es.compute()
     ctx.sync()
@@ -252,28 +490,28 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count() - launches0  # kernels of this library launched inside the timed region
-    fams = {}
-    for fam in ("cgs_dot", "cgs_update_dot", "cgs_update_norm", "spmv_sell", "vec_dot", "nccl_allreduce", "nccl_halo",
-                "halo_pack"):
-        fams[fam] = ctx.profile_get(fam)
+    fam_names = ("cgs_dot", "cgs_update_dot", "cgs_update_norm", "spmv_sell", "heisenberg_mf", "gemv_dense", "vec_dot",
+                 "nccl_allreduce", "nccl_halo", "halo_pack")
+    fams = {fam: ctx.profile_get(fam) for fam in fam_names}
     ctx.profile(False)
     dev_ms = max_over_ranks(dev_ms)
     if os.environ.get("BENCH_DEBUG") and rank == 0:
         print("device-leg: dev %.1f ms, host wall %.1f ms per solve; families %s" % (
-            dev_ms / args.steps, host_ms / args.steps, {k: (round(v[0] / args.steps, 2), v[1] // args.steps) for k, v in fams.items()}),
-            file=sys.stderr, flush=True)
+            dev_ms / args.steps, host_ms / args.steps,
+            {k: (round(v[0] / args.steps, 2), v[1] // args.steps) for k, v in fams.items() if v[1]}), file=sys.stderr, flush=True)
     value = m * args.steps / (dev_ms * 1e-3)
-    eig = es.eigenvalues()
-    step_bytes = es.deviceBytes()  # algorithmic bytes of one solve on this rank
+    got = {"eigenvalues": es.eigenvalues()}
+    if wl.kind == "lanczos":
+        got["alpha"], got["beta"] = es.alpha(), es.beta()
+    else:
+        got["hessenberg"] = es.hessenbergMatrix()
+    step_bytes = sum_over_ranks(es.deviceBytes())  # algorithmic bytes of one solve over all ranks
+    residuals = es.ritzResiduals()
     es.close()
 
     # ---- roofline of the dominant kernel family ----
     peak, peak_src = load_peaks()
-    s = 8.0
-    alg = {"cgs_dot": sum((cc + 1) for cc in range(1, m + 1)) * nloc * s,
-           "cgs_update_dot": sum((cc + 2) for cc in range(1, m + 1)) * nloc * s,
-           "cgs_update_norm": sum((cc + 2) for cc in range(1, m + 1)) * nloc * s,
-           "spmv_sell": (m + 1) * op.bytes}
+    alg = wl.algorithmic_bytes(nloc, op.bytes)
     dom = max(alg, key=lambda k: fams[k][0])
     dom_ms, dom_n = fams[dom]
     roof = None
@@ -283,9 +521,9 @@ def run_ours(args):
         ach = per_launch_bytes / per_launch_s / 1e9
         traffic, traffic_src = None, None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[dom]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[dom]
             traffic = tr["ratio"] * per_launch_bytes  # measured dram/algorithmic ratio x this run's bytes per launch
-            traffic_src = "ncu --set full capture (profiles/r1d_prof_step4_raw.txt): dram bytes / algorithmic bytes = %.4f" % tr["ratio"]
+            traffic_src = "%s: dram bytes / algorithmic bytes = %.4f" % (tr["source"], tr["ratio"])
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -295,27 +533,27 @@ def run_ours(args):
                 "bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_s * 1e3,
                 "families": {k: {"ms": fams[k][0], "launches": fams[k][1],
                                  "GBps": (alg[k] * args.steps / (fams[k][0] * 1e-3) / 1e9) if (k in alg and fams[k][0] > 0) else None}
-                             for k in fams}}
+                             for k in fams if fams[k][1]}}
     overall_gbs = step_bytes * args.steps / (dev_ms * 1e-3) / 1e9
 
     # ---- end-to-end leg: host buffers in, host results out ----
     e2e = None
     if not args.no_e2e:
         op.close()
-        es2 = make_solver(None, vectors=True)
-        h2d = prp.array.nbytes + pc.array.nbytes + pv.array.nbytes + px.array.nbytes
-        d2h = nev * nloc * 8 + nev * 8
+        es2 = wl.make_solver(pkg, None, px.array, vectors=True)
+        h2d = sum(a.nbytes for a in host.values()) + px.array.nbytes
+        d2h = nev * nloc * int(16 if wl.kind == "arnoldi" else wl.s) + nev * 16
         times = []
         for i in range(args.warmup + args.steps):
             ctx.sync()
             barrier()
             t0 = time.perf_counter()
-            op2 = pkg.DeviceOperator.from_csr(ctx, prp.array, pc.array, pv.array, n_global=n, row_begin=r0)
+            op2 = wl.make_operator(pkg, ctx, host, r0)
             es2.setMatrixMultiplication(op2).setInitialVector(px.array)
             es2.compute()
             ev = es2.eigenvalues()
             X = es2.eigenvectors(copy=False)
-            chk = float(X[0, 0]) + float(ev[0])  # touch the host results
+            chk = complex(X[0, 0]) + complex(ev[0])  # touch the host results
             op2.close()
             ctx.sync()
             dt = time.perf_counter() - t0
@@ -328,35 +566,57 @@ def run_ours(args):
         tot = max_over_ranks(sum(times))
         e2e = {"value": m * len(times) / tot, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * tot / len(times),
-               "what": "pinned host CSR + start vector -> SELL build -> compute() with %d Ritz vectors -> host" % nev}
+               "what": "pinned host operator arrays + start vector -> device operator build -> compute() with %d Ritz vectors -> host" % nev}
         es2.close()
 
-    # ---- CPU baseline (rank 0, N = 1 only) ----
+    # ---- parity: against the reference's own full-size recording, and (N = 1) against the live cpu_baseline run ----
+    parity = []
+    fx, fx_name = wl.fixture()
+    if fx is not None and rank == 0:
+        want = {k: fx[k] for k in fx.files}
+        if wl.kind == "arnoldi" and not wl.complex:
+            want = dict(want, hessenberg=np.real(want["hessenberg"]))  # real operator, real start vector: H is real
+        parity.append(parity_against(got, want, fx_name + " (the reference itself, full size)"))
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cb = oracle_sample(args, prp.array, pc.array, pv.array, x0_full, args.cpu_sample_m, 1, 0)
-        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if world == 1 and not args.no_cpu_baseline and not (wl.cfg == 5 and wl.size > 26):
+        cb, res, m_run = reference_timing(wl, args.cpu_budget, 1, "no warm-up beyond one %d-iteration calibration solve" % min(6, m))
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated", "what")}
+        live = {"eigenvalues": res.eigenvalues}
+        if wl.kind == "lanczos":
+            live["alpha"], live["beta"] = res.alpha_beta()
+        else:
+            live["hessenberg"] = res.hessenberg
+        parity.append(parity_against(got, live, "live cpu_baseline run of oracle/_ref (first %d iterations)" % m_run,
+                                     count=None if m_run == m else m_run))
 
+    rc = 0
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args), "partition": "rows/%d" % world,
-                           "timing": "CUDA events on the library stream; L2 flushed (256 MiB memset) between timed solves; "
-                                     "basis (13.6 GB) and matrix (1.3 GB) far exceed the 126 MB L2",
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
+                "dtype": "c128" if wl.complex else "f64", "data": "synthetic", "config": wl.config(),
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "parity": parity,
+                "detail": {"partition": "rows/%d" % world, "timing": "CUDA events on the library stream, max over ranks",
                            "algorithmic_GBps": overall_gbs, "bytes_per_solve": step_bytes,
-                           "lowest_eigenvalues": [float(x) for x in eig]},
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                           "lowest_eigenvalues": [complex(x).real for x in got["eigenvalues"]],
+                           "ritz_residuals": [float(x) for x in residuals]}}
         print(json.dumps(line), flush=True)
+        bad = [p for p in parity if not p["ok"]]
+        if bad:
+            print("PARITY FAILURE: %s" % json.dumps(bad), file=sys.stderr, flush=True)
+            rc = 3
+    barrier()
+    ctx.close()
+    return rc
 
 
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
-        run_ours(args)
+        return 0
+    return run_ours(args)
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())

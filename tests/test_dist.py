@@ -56,21 +56,45 @@ def test_world_size_2_gloo_cpu():
 
 
 def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
-    """bench.py --impl reference launched like the driver does for N > 1: rank 0 alone runs the CPU oracle on a bounded
-    sample and prints ONE JSON line, the other rank exits 0 without output (small grid here to keep the suite fast)."""
+    """bench.py --impl reference launched like the driver does for N > 1: rank 0 alone runs the reference's own CPU
+    implementation (oracle/_ref) on the workload and prints ONE JSON line, the other rank exits 0 without output
+    (small grid here to keep the suite fast)."""
     import json
 
+    from oracle import ref
+
+    if not ref.available():
+        pytest.skip("oracle/_ref/libref.so absent and no reference tree to build it from")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29633", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
-           "--steps", "1", "--warmup", "0", "--grid", "96", "--cpu-sample-m", "6"]
+           "--steps", "2", "--warmup", "0", "--grid", "96", "--krylov-m", "30"]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ))
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["metric"] == "krylov_iterations_per_sec"
-    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["extrapolated"] is False and "2 full solve(s)" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["m"] == 30 and d["config"]["n"] == 96 * 96
+
+
+def test_reference_arm_extrapolates_only_when_a_full_solve_does_not_fit():
+    """With a tiny time budget the reference arm times a shorter solve, scales it with the step-cost model and says so."""
+    import json
+
+    from oracle import ref
+
+    if not ref.available():
+        pytest.skip("oracle/_ref/libref.so absent and no reference tree to build it from")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--grid", "128",
+           "--krylov-m", "60", "--ref-budget", "1e-6"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ))
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    d = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["cpu_baseline"]["extrapolated"] is True and "EXTRAPOLATED" in d["cpu_baseline"]["sample"]
+    assert d["value"] > 0
 
 
 @pytest.mark.gpu
