@@ -381,13 +381,19 @@ def parity_against(got, want, label, count=None):
         scale = max(1.0, float(np.abs(Hr).max()))
         out["max_abs_diff_hessenberg_leading8"] = float(np.abs(H[:k, :k] - Hr[:k, :k]).max())
         out["max_abs_diff_hessenberg_all"] = float(np.abs(H[:Hr.shape[0], :Hr.shape[1]] - Hr[:H.shape[0], :H.shape[1]]).max())
-        worst = out["max_abs_diff_hessenberg_leading8"] / scale
+        # the gate is the projected matrix itself: leading block to the tolerance, the rest to 100x (rounding differences
+        # grow along the Arnoldi recurrence of a non-normal operator)
+        worst = max(out["max_abs_diff_hessenberg_leading8"], 1e-2 * out["max_abs_diff_hessenberg_all"]) / scale
     if count is None and "eigenvalues" in want and len(want["eigenvalues"]) == len(got["eigenvalues"]):
         ev, rev = np.asarray(got["eigenvalues"]), np.asarray(want["eigenvalues"])
         if "hessenberg" in want:
-            # unconverged trailing Ritz values of a non-normal H are ill-conditioned: the gate is the leading one
-            rel = np.abs(ev[:1] - rev[:1]) / np.abs(rev[:1])
+            # Ritz values of a non-normal H that have not converged are ill-conditioned functions of H (two runs of the
+            # reference with different summation order differ in them too): only converged ones are gated
+            res = np.asarray(got.get("ritz_residuals", np.full(len(ev), np.inf)))
+            conv = res < 1e-8 * scale
+            out["converged_ritz_values"] = int(conv.sum())
             out["max_rel_diff_all_eigenvalues"] = float((np.abs(ev - rev) / np.abs(rev)).max())
+            rel = np.abs(ev[conv] - rev[conv]) / np.abs(rev[conv]) if conv.any() else np.zeros(1)
         else:
             rel = np.abs(ev - rev) / np.maximum(np.abs(rev), 1e-3 * scale)
         out["max_rel_diff_eigenvalues"] = float(rel.max())
@@ -507,6 +513,7 @@ def run_ours(args):
         got["hessenberg"] = es.hessenbergMatrix()
     step_bytes = sum_over_ranks(es.deviceBytes())  # algorithmic bytes of one solve over all ranks
     residuals = es.ritzResiduals()
+    got["ritz_residuals"] = residuals
     es.close()
 
     # ---- roofline of the dominant kernel family ----

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x, double* __restrict__ y,
            const double* __restrict__ hin, double* __restrict__ hout, double* __restrict__ partial,
            unsigned* __restrict__ ticket, const int* __restrict__ halt, int ncols, int cg, int ntiles, int stages,
-           MailPull pull, MailPush push, int norm_trick) {
+           MailPull pull, MailPush push, int norm_trick, int* retry, int retry_tag, double norm_guard) {
   using Cfg = CgsCfg<WC>;
   constexpr int T = Cfg::T, WR = Cfg::WR;
   constexpr int ES = CPLX ? 2 : 1;  // doubles per coefficient
@@ -231,6 +231,13 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
       for (int t = 0; t < nh; ++t) acc = fma(s_fin[t], s_fin[t], acc);
       const double b2 = s_fin[nh] - acc;
       hout[0] = b2 > 0.0 ? b2 : 0.0;
+      // cancellation guard (same bits on every rank, so all ranks halt together): the host reduces the norm
+      // explicitly and resumes the chain.  A vanishing ||y||^2 is a genuine breakdown, not a cancellation.
+      if (retry && s_fin[nh] > 0.0 && !(b2 > norm_guard * s_fin[nh])) {
+        retry[0] = 1;
+        retry[1] = retry_tag;
+        *const_cast<int*>(halt) = 1;
+      }
     }
     return;
   }
@@ -379,7 +386,8 @@ static int launch_cfg(cmb_ctx* ctx, const CgsPass& a, int cg) {
   {
     LaunchScope ls(ctx, a.family ? a.family : fam[MODE]);
     kern<<<grid, kThreads, smem, ctx->stream>>>(tm, a.x, a.y, a.hin, a.hout, ctx->d_partial, ctx->d_ticket, a.halt,
-                                                a.ncols, cg, ntiles, stages, a.pull, a.push, a.norm_trick);
+                                                a.ncols, cg, ntiles, stages, a.pull, a.push, a.norm_trick, a.retry, a.retry_tag,
+                                                a.norm_guard);
   }
   CMB_CUDA(cudaGetLastError());
   return CMB_OK;

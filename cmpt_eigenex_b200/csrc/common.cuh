@@ -88,6 +88,8 @@ struct MailPull {                 // consumer side (kernel argument)
   const unsigned long long* flag = nullptr;
   double* writeback = nullptr;            // optional plain copy of the reduced values (for the host)
   int* error = nullptr;                   // set to 1 when a peer never arrives (bounded spin)
+  int* halt = nullptr;                    // sticky halt flag of the chain: raised together with *error
+  long long timeout = 1ll << 36;          // spin bound in SM clocks (cmb_ctx::spin_timeout)
 };
 
 // Halo exchange through peer memory (halo.cu): the owner of the rows stores the values a peer needs straight into
@@ -112,7 +114,11 @@ struct HaloPull {                       // consumer side (kernel argument)
   const unsigned long long* xseq = nullptr;
   int P = 1, rank = 0;
   int* error = nullptr;
+  int* halt = nullptr;                  // sticky halt flag of the chain: raised together with *error
+  long long timeout = 1ll << 36;        // spin bound in SM clocks (cmb_ctx::spin_timeout)
 };
+
+struct VGroup;  // virtual ranks on one device (vgroup.cu)
 
 }  // namespace cmb
 
@@ -137,6 +143,13 @@ struct cmb_ctx {
   unsigned long long* mail_flag[cmb::kMaxPeers] = {};  // [rank]: base of that rank's flag array
   unsigned long long mail_seq = 0;                     // sequence number of the last push (same on all ranks)
   int* d_mail_error = nullptr;
+  // Bound of the in-kernel waits for a peer (mailbox, halo flags) in SM clocks: ~30 s by default, CMPT_B200_SPIN_TIMEOUT_S
+  // or cmb_ctx_set_spin_timeout() change it.  A kernel replayed by a profiler or stopped in a debugger can exceed any
+  // bound: multi-rank runs are not compatible with replaying tools.
+  long long spin_timeout = 60000000000ll;
+  double norm_guard = 1e-8;        // guard ratio of the Pythagorean norm (CgsPass::norm_guard; CMPT_B200_NORM_GUARD)
+  bool dead = false;               // a peer wait timed out: the sequence numbers of the ranks no longer agree
+  cmb::VGroup* vgroup = nullptr;   // virtual rank (vgroup.cu): collectives are host-thread rendezvous, not NCCL
   // L2 flush buffer
   void* d_flush = nullptr;
   size_t flush_bytes = 0;
@@ -174,6 +187,22 @@ MailPull mail_pull_of(cmb_ctx* ctx, unsigned long long seq, double* writeback);
 // collective CUDA-IPC mapping of one cudaMalloc'ed buffer per rank (all-or-nothing; ctx.cu)
 bool ipc_share(cmb_ctx* ctx, void* base, void** mapped);
 void ipc_unshare(cmb_ctx* ctx, void** mapped);
+// all ranks wait for each other (stream synchronised first); no-op on a single rank
+int rank_barrier(cmb_ctx* ctx);
+// all-to-all of int32 device lists: the piece [send_off[q], send_off[q+1]) of d_send goes to rank q, the piece rank q
+// destined to this rank lands at d_recv + recv_off[q]
+int alltoallv_i32(cmb_ctx* ctx, const int32_t* d_send, const int64_t* send_off, int32_t* d_recv, const int64_t* recv_off);
+// Reports (and clears) a timed-out peer wait of the kernels launched so far; the stream must be synchronised.
+int check_peer_wait(cmb_ctx* ctx);
+// virtual ranks (vgroup.cu)
+int vgroup_allreduce_f64(cmb_ctx* c, double* p, size_t count);
+int vgroup_allreduce_min_u64(cmb_ctx* c, unsigned long long* p, size_t count);
+bool vgroup_share(cmb_ctx* c, void* base, void** mapped);
+int vgroup_barrier(cmb_ctx* c);
+int vgroup_alltoallv_i32(cmb_ctx* c, const int32_t* d_send, const int64_t* send_off, int32_t* d_recv, const int64_t* recv_off);
+int vgroup_attach(VGroup* g, cmb_ctx* c, int rank);
+int vgroup_size(const VGroup* g);
+int vgroup_device(const VGroup* g);
 
 // driver entry point for tensor-map encoding (no link-time libcuda dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

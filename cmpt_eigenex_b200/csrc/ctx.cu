@@ -7,9 +7,14 @@
 
 #include <vector>
 
+#include <algorithm>
+
+#include "cmpt_b200_debug.h"
 #include "common.cuh"
 
 namespace cmb {
+
+VGroup* vgroup_of(cmb_vgroup* vg);  // vgroup.cu
 
 static thread_local char g_err[1024] = "";
 
@@ -113,6 +118,7 @@ int resolve_profile(cmb_ctx* ctx) {
 
 int allreduce_sum_f64(cmb_ctx* ctx, double* p, size_t count) {
   if (ctx->nranks == 1) return CMB_OK;
+  if (ctx->vgroup) return vgroup_allreduce_f64(ctx, p, count);
   LaunchScope ls(ctx, "nccl_allreduce");
   int r = ctx->nccl->AllReduce(p, p, count, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
   if (r != 0) {
@@ -124,6 +130,7 @@ int allreduce_sum_f64(cmb_ctx* ctx, double* p, size_t count) {
 
 int allreduce_min_u64(cmb_ctx* ctx, unsigned long long* p, size_t count) {
   if (ctx->nranks == 1) return CMB_OK;
+  if (ctx->vgroup) return vgroup_allreduce_min_u64(ctx, p, count);
   int r = ctx->nccl->AllReduce(p, p, count, kNcclUint64, kNcclMin, ctx->nccl_comm, ctx->stream);
   if (r != 0) {
     set_error("ncclAllReduce(min) failed: %s", ctx->nccl->GetErrorString ? ctx->nccl->GetErrorString(r) : "?");
@@ -162,7 +169,60 @@ MailPull mail_pull_of(cmb_ctx* ctx, unsigned long long seq, double* writeback) {
   m.flag = ctx->mail_flag[ctx->rank] + slot * ctx->nranks;
   m.writeback = writeback;
   m.error = ctx->d_mail_error;
+  m.timeout = ctx->spin_timeout;
   return m;
+}
+
+int rank_barrier(cmb_ctx* ctx) {
+  if (ctx->nranks == 1) return CMB_OK;
+  if (ctx->vgroup) return vgroup_barrier(ctx);
+  CMB_TRY(allreduce_sum_f64(ctx, ctx->d_partial, 1));  // scratch word; its value is never read
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CMB_OK;
+}
+
+int alltoallv_i32(cmb_ctx* ctx, const int32_t* d_send, const int64_t* send_off, int32_t* d_recv, const int64_t* recv_off) {
+  if (ctx->nranks == 1) return CMB_OK;
+  if (ctx->vgroup) return vgroup_alltoallv_i32(ctx, d_send, send_off, d_recv, recv_off);
+  auto chk = [&](int r, const char* what) {
+    if (r != 0) {
+      set_error("%s failed: %s", what, ctx->nccl->GetErrorString ? ctx->nccl->GetErrorString(r) : "?");
+      return int(CMB_ERR_NCCL);
+    }
+    return int(CMB_OK);
+  };
+  int rc = chk(ctx->nccl->GroupStart(), "ncclGroupStart");
+  for (int q = 0; q < ctx->nranks && rc == CMB_OK; ++q) {
+    if (q == ctx->rank) continue;
+    if (send_off[q + 1] > send_off[q])
+      rc = chk(ctx->nccl->Send(d_send + send_off[q], size_t(send_off[q + 1] - send_off[q]), kNcclInt32, q, ctx->nccl_comm,
+                               ctx->stream), "ncclSend");
+    if (rc == CMB_OK && recv_off[q + 1] > recv_off[q])
+      rc = chk(ctx->nccl->Recv(d_recv + recv_off[q], size_t(recv_off[q + 1] - recv_off[q]), kNcclInt32, q, ctx->nccl_comm,
+                               ctx->stream), "ncclRecv");
+  }
+  if (rc == CMB_OK) rc = chk(ctx->nccl->GroupEnd(), "ncclGroupEnd");
+  else ctx->nccl->GroupEnd();
+  return rc;
+}
+
+int check_peer_wait(cmb_ctx* ctx) {
+  if (ctx->dead) {
+    set_error("this context is unusable: an earlier wait for a peer rank timed out and the ranks' sequence numbers no "
+              "longer agree; destroy the contexts of all ranks and create new ones");
+    return CMB_ERR_NCCL;
+  }
+  if (!ctx->mail_ok) return CMB_OK;
+  int err = 0;
+  CMB_CUDA(cudaMemcpy(&err, ctx->d_mail_error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (!err) return CMB_OK;
+  // the flag is cleared so that the message appears once; the context stays marked dead (see above)
+  CMB_CUDA(cudaMemset(ctx->d_mail_error, 0, sizeof(int)));
+  ctx->dead = true;
+  set_error("a peer rank never published its Gram-Schmidt partials or halo values: the in-kernel wait timed out after "
+            "%.1f s (CMPT_B200_SPIN_TIMEOUT_S / cmb_ctx_set_spin_timeout change the limit; replaying profilers and "
+            "debuggers are not compatible with multi-rank runs)", double(ctx->spin_timeout) / 1.9e9);
+  return CMB_ERR_NCCL;
 }
 
 // Collective: every rank passes the base of a cudaMalloc'ed buffer; CUDA IPC handles travel through NCCL (allgather
@@ -170,6 +230,7 @@ MailPull mail_pull_of(cmb_ctx* ctx, unsigned long long seq, double* writeback) {
 // true on every rank or false on every rank (then nothing stays mapped).
 bool ipc_share(cmb_ctx* c, void* base, void** mapped) {
   const int P = c->nranks;
+  if (c->vgroup) return vgroup_share(c, base, mapped);
   for (int q = 0; q < P; ++q) mapped[q] = nullptr;
   if (P < 2 || P > kMaxPeers || !c->nccl || !c->nccl->AllGather) return false;
   cudaIpcMemHandle_t mine;
@@ -227,7 +288,7 @@ bool ipc_share(cmb_ctx* c, void* base, void** mapped) {
 
 void ipc_unshare(cmb_ctx* c, void** mapped) {
   for (int q = 0; q < c->nranks; ++q) {
-    if (q != c->rank && mapped[q]) cudaIpcCloseMemHandle(mapped[q]);
+    if (q != c->rank && mapped[q] && !c->vgroup) cudaIpcCloseMemHandle(mapped[q]);
     mapped[q] = nullptr;
   }
   cudaGetLastError();
@@ -236,7 +297,7 @@ void ipc_unshare(cmb_ctx* c, void** mapped) {
 // Allocate this rank's mailbox and map the peers' mailboxes.  Failure is not fatal: the context then keeps using
 // NCCL allreduce for the coefficients.
 static int mail_setup(cmb_ctx* c) {
-  if (c->nranks < 2 || c->nranks > kMaxPeers || !c->nccl->AllGather) return CMB_OK;
+  if (c->nranks < 2 || c->nranks > kMaxPeers || (!c->vgroup && !c->nccl->AllGather)) return CMB_OK;
   if (getenv("CMPT_B200_NO_MAILBOX")) return CMB_OK;
   const int P = c->nranks;
   const size_t bytes = mail_data_doubles(P) * sizeof(double) + size_t(kMailSlots) * P * sizeof(unsigned long long);
@@ -266,7 +327,7 @@ static int mail_setup(cmb_ctx* c) {
 static void mail_teardown(cmb_ctx* c) {
   if (!c->mail_ok) return;
   for (int q = 0; q < c->nranks; ++q)
-    if (q != c->rank && c->mail_data[q]) cudaIpcCloseMemHandle(c->mail_data[q]);
+    if (q != c->rank && c->mail_data[q] && !c->vgroup) cudaIpcCloseMemHandle(c->mail_data[q]);
   cudaFree(c->mail_data[c->rank]);
   cudaFree(c->d_mail_error);
   c->mail_ok = false;
@@ -289,6 +350,12 @@ static int ctx_init_common(cmb_ctx* c, int device) {
     return CMB_ERR_UNSUPPORTED;
   }
   c->num_sms = prop.multiProcessorCount;
+  {
+    double seconds = 30.0;
+    if (const char* t = getenv("CMPT_B200_SPIN_TIMEOUT_S")) seconds = std::max(0.1, atof(t));
+    c->spin_timeout = (long long)(seconds * double(prop.clockRate) * 1e3);
+    if (const char* g = getenv("CMPT_B200_NORM_GUARD")) c->norm_guard = atof(g);
+  }
   {
     // keep freed pool memory cached: operator (re)builds then never reach cudaMalloc/cudaFree
     cudaMemPool_t pool = nullptr;
@@ -407,11 +474,10 @@ int cmb_ctx_destroy(cmb_ctx* c) {
     // unmap the peers' mailboxes, wait until everybody has done so, then free the own one
     for (int q = 0; q < c->nranks; ++q)
       if (q != c->rank && c->mail_data[q]) {
-        cudaIpcCloseMemHandle(c->mail_data[q]);
+        if (!c->vgroup) cudaIpcCloseMemHandle(c->mail_data[q]);
         c->mail_data[q] = nullptr;
       }
-    allreduce_sum_f64(c, c->d_partial, 1);
-    cudaStreamSynchronize(c->stream);
+    rank_barrier(c);
     mail_teardown(c);
   }
   if (c->nccl_comm && c->nccl) c->nccl->CommDestroy(c->nccl_comm);
@@ -428,6 +494,38 @@ int cmb_ctx_destroy(cmb_ctx* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
+  return CMB_OK;
+}
+
+// Virtual rank `rank` of the group (declared in cmpt_b200_debug.h).  Collective: call it from nranks host threads.
+int cmb_ctx_create_virtual(cmb_vgroup* vg, int rank, cmb_ctx** out) {
+  CMB_REQUIRE(vg && out, "null argument");
+  *out = nullptr;
+  VGroup* g = vgroup_of(vg);
+  CMB_REQUIRE(rank >= 0 && rank < vgroup_size(g), "bad virtual rank");
+  cmb_ctx* c = new (std::nothrow) cmb_ctx();
+  if (!c) return CMB_ERR_NOMEM;
+  int r = ctx_init_common(c, vgroup_device(g));
+  if (r == CMB_OK) r = vgroup_attach(g, c, rank);
+  if (r != CMB_OK) {
+    delete c;
+    return r;
+  }
+  if (c->nranks > 1) mail_setup(c);
+  if (c->nranks > 1 && !c->mail_ok) {
+    set_error("virtual rank %d: the peer-memory mailboxes could not be set up", rank);
+    cmb_ctx_destroy(c);
+    return CMB_ERR_NCCL;
+  }
+  *out = c;
+  return CMB_OK;
+}
+
+int cmb_ctx_set_spin_timeout(cmb_ctx* c, double seconds) {
+  CMB_REQUIRE(c && seconds > 0.0, "bad argument");
+  cudaDeviceProp prop;
+  CMB_CUDA(cudaGetDeviceProperties(&prop, c->device));
+  c->spin_timeout = (long long)(seconds * double(prop.clockRate) * 1e3);
   return CMB_OK;
 }
 

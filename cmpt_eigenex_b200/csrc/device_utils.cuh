@@ -25,14 +25,16 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsign
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // Wait (whole warp) until every rank has published sequence number m.seq in this rank's mailbox.  The spin is
-// bounded (~2 s): a missing peer raises m.error instead of hanging the GPU.
+// bounded (m.timeout SM clocks, ~30 s by default): a missing peer raises m.error and the sticky halt flag, so that no
+// later launch of the chain consumes stale data, instead of hanging the GPU.
 __device__ __forceinline__ void mail_wait(const MailPull& m) {
   const int lane = threadIdx.x & 31;
   if (lane < m.P) {
     const long long t0 = clock64();
     while (ld_acquire_sys_u64(m.flag + lane) < m.seq) {
-      if (clock64() - t0 > (1ll << 32)) {
+      if (clock64() - t0 > m.timeout) {
         *m.error = 1;
+        if (m.halt) *m.halt = 1;
         break;
       }
     }
@@ -93,8 +95,9 @@ __device__ __forceinline__ void halo_wait_cta(const HaloPull& h, unsigned long l
       const long long t0 = clock64();
       while (ld_acquire_sys_u64(h.flag + lane) < seq) {
         __nanosleep(100);
-        if (clock64() - t0 > (1ll << 32)) {
+        if (clock64() - t0 > h.timeout) {
           *h.error = 1;
+          if (h.halt) *h.halt = 1;
           break;
         }
       }

@@ -107,10 +107,13 @@ __global__ void pack_kernel(const double* __restrict__ w, const int* __restrict_
   }
 }
 
+// Collective on multi-rank contexts: a peer may still have this rank's receive buffer mapped (or be pushing into it),
+// so every rank first unmaps, then all ranks meet, and only then the exported buffer is freed.
 HaloExchange::~HaloExchange() {
   if (p2p_ctx) {
     cudaStreamSynchronize(p2p_ctx->stream);
     ipc_unshare(p2p_ctx, p2p_mapped);
+    rank_barrier(p2p_ctx);
     cudaFree(push.xseq);
     cudaFree(push.ticket);
     cudaFree(p2p_base);
@@ -178,6 +181,7 @@ int HaloExchange::setup_p2p(cmb_ctx* ctx, const std::vector<double>& cnt) {
   pull.P = P;
   pull.rank = rank;
   pull.error = ctx->d_mail_error;
+  pull.timeout = ctx->spin_timeout;
   return CMB_OK;
 }
 
@@ -215,18 +219,8 @@ int HaloExchange::setup(cmb_ctx* ctx, int64_t n, int es_, const std::vector<int3
   CMB_CUDA(cudaMalloc(&d_need, sizeof(int32_t) * std::max<int64_t>(nrecv, 1)));
   CMB_CUDA(cudaMalloc(&d_send_idx, sizeof(int32_t) * std::max<int64_t>(nsend, 1)));
   CMB_CUDA(cudaMemcpyAsync(d_need, halo_cols.data(), sizeof(int32_t) * nrecv, cudaMemcpyHostToDevice, ctx->stream));
-  rc = nccl_check(ctx, ctx->nccl->GroupStart(), "ncclGroupStart");
-  for (int q = 0; q < P && rc == CMB_OK; ++q) {
-    if (q == rank) continue;
-    if (recv_off[q + 1] > recv_off[q])
-      rc = nccl_check(ctx, ctx->nccl->Send(d_need + recv_off[q], size_t(recv_off[q + 1] - recv_off[q]), kNcclInt32, q,
-                                           ctx->nccl_comm, ctx->stream), "ncclSend");
-    if (rc == CMB_OK && send_off[q + 1] > send_off[q])
-      rc = nccl_check(ctx, ctx->nccl->Recv(d_send_idx + send_off[q], size_t(send_off[q + 1] - send_off[q]), kNcclInt32, q,
-                                           ctx->nccl_comm, ctx->stream), "ncclRecv");
-  }
-  if (rc == CMB_OK) rc = nccl_check(ctx, ctx->nccl->GroupEnd(), "ncclGroupEnd");
-  else ctx->nccl->GroupEnd();
+  // what I need from q goes to q; what q needs from me arrives in d_send_idx
+  rc = alltoallv_i32(ctx, d_need, recv_off.data(), d_send_idx, send_off.data());
   std::vector<int32_t> sidx(std::max<int64_t>(nsend, 1));
   if (rc == CMB_OK) {
     cudaError_t e = cudaMemcpyAsync(sidx.data(), d_send_idx, sizeof(int32_t) * nsend, cudaMemcpyDeviceToHost, ctx->stream);
@@ -259,6 +253,10 @@ int HaloExchange::setup(cmb_ctx* ctx, int64_t n, int es_, const std::vector<int3
 
 int HaloExchange::exchange(cmb_ctx* ctx, const double* w, const int* halt) {
   if (p2p) return CMB_OK;  // the push is part of the consuming kernel (fused_push)
+  if (ctx->vgroup) {
+    set_error("virtual ranks exchange halos through peer memory only (CMPT_B200_NO_P2P_HALO is not supported there)");
+    return CMB_ERR_UNSUPPORTED;
+  }
   if (nsend > 0) {
     LaunchScope ls(ctx, "halo_pack");
     const int grid = int(std::max<int64_t>(1, std::min<int64_t>((nsend + 255) / 256, int64_t(ctx->num_sms) * 8)));

@@ -19,6 +19,7 @@
 #include <type_traits>
 #include <vector>
 
+#include "cmpt_b200_debug.h"
 #include "device_utils.cuh"
 #include "op.cuh"
 
@@ -67,6 +68,7 @@ struct HeisArgs {
   unsigned long long seq;
   unsigned flag_mask;
   int* error;
+  long long timeout;  // spin bound of the flag wait in SM clocks (cmb_ctx::spin_timeout)
 };
 
 // Two neighbouring tile elements (t0 even, t0 + 1): the unit of work of one thread.  For every bond that does not
@@ -138,8 +140,9 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
     if ((a.flag_mask >> threadIdx.x) & 1u) {
       const long long t0 = clock64();
       while (ld_acquire_sys_u64(a.flag + threadIdx.x) < a.seq) {
-        if (clock64() - t0 > (1ll << 32)) {  // bounded (~2 s): a missing partner raises the error flag
+        if (clock64() - t0 > a.timeout) {  // bounded: a missing partner raises the error flag and halts the chain
           *a.error = 1;
+          *sc.halt = 1;
           break;
         }
       }
@@ -420,6 +423,7 @@ struct HeisenbergOp : cmb_op {
       }
       if (ev_ready) cudaEventDestroy(ev_ready);
       ipc_unshare(ctx, p2p_mapped);
+      rank_barrier(ctx);  // collective: nobody frees an exported buffer a peer may still write to
       cudaFree(p2p_base);
       cudaFreeHost(h_seq);
     }
@@ -650,6 +654,10 @@ struct HeisenbergOp : cmb_op {
       for (auto& r : plan.remote) has_wrap |= (r.kind == 4);
       if (has_wrap) CMB_TRY(pack_wrap(w, 1 - rt, d_pack, sc.halt));
       if (p2p) return apply_p2p(a, w, ucol, v, shr, shi, sc);
+      if (ctx->vgroup) {
+        set_error("virtual ranks exchange slabs through peer memory only");
+        return CMB_ERR_UNSUPPORTED;
+      }
       auto chk = [&](int r, const char* what) -> int {
         if (r != 0) {
           set_error("%s failed: %s", what, ctx->nccl->GetErrorString ? ctx->nccl->GetErrorString(r) : "?");
@@ -739,6 +747,7 @@ struct HeisenbergOp : cmb_op {
     a.seq = x;
     a.flag_mask = mask;
     a.error = ctx->d_mail_error;
+    a.timeout = ctx->spin_timeout;
     CMB_TRY(launch(a, w, ucol, v, shr, shi, sc));
     // whoever overwrites w or the pack buffer next must come after the copies that read them
     for (size_t k = 0; k < plan.remote.size(); ++k)

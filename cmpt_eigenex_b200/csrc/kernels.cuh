@@ -22,6 +22,13 @@ struct CgsPass {
   // hout; UPDATE_NORM with norm_trick then needs no reduction of its own: hout[0] = hin[ncols] - sum |hin_j|^2
   // (= ||y - V hin||^2 for orthonormal V), computed by one CTA from the already reduced coefficients.
   int norm_trick = 0;
+  // Guard of the Pythagorean norm: when beta^2 <= norm_guard * ||y||^2 (cancellation: the relative error of beta^2 is
+  // eps ||y||^2 / beta^2) the UPDATE_NORM launch raises the sticky halt flag and records retry[0] = 1, retry[1] =
+  // retry_tag; the host then reduces the norm explicitly and resumes the chain (krylov.cu).  The decision is taken from
+  // values that are bit-identical on every rank.
+  int* retry = nullptr;
+  int retry_tag = 0;
+  double norm_guard = 1e-8;
 };
 enum { CGS_DOT = 0, CGS_UPDATE_DOT = 1, CGS_UPDATE_NORM = 2 };
 inline int cgs_max_cols(bool cplx) { return cplx ? 64 : 128; }

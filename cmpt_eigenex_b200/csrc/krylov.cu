@@ -16,6 +16,7 @@
 
 #include <algorithm>
 
+#include "cmpt_b200_debug.h"
 #include "op.cuh"
 
 using namespace cmb;
@@ -48,6 +49,7 @@ struct cmb_krylov {
   size_t h_stage_elems = 0;
   bool started = false;
   unsigned long long nrm2_seq = 0;  // non-zero: ||w||^2 is the mailbox reduction with this sequence number
+  bool resume_norm_ready = false;   // w is orthogonalised and scal[0] holds its explicitly reduced norm (guard retry)
   double residue = 0.0;  // Arnoldi: last residual norm (host copy)
   double bytes = 0.0;
   double *tmp1 = nullptr, *tmp2 = nullptr, *tmpz = nullptr;
@@ -144,7 +146,7 @@ static int total_cols(const std::vector<Chunk>& ch) {
 // so no collective kernel runs in between.  *nrm2_seq receives the sequence number under which ||y||^2 will be
 // found by the consumer (the operator apply).
 static int gram_schmidt2_mailed(cmb_krylov* K, const Chunk& c, const double* x, double* y,
-                                unsigned long long* nrm2_seq) {
+                                unsigned long long* nrm2_seq, int retry_tag) {
   cmb_ctx* ctx = K->ctx;
   CgsPass p;
   p.ld = K->ld;
@@ -164,16 +166,21 @@ static int gram_schmidt2_mailed(cmb_krylov* K, const Chunk& c, const double* x, 
   const bool trick = (K->ndefl == 0);
   p.y = y;
   p.pull = mail_pull_of(ctx, s1, K->h1);
+  p.pull.halt = K->halt;
   p.push = mail_next_push(ctx);
   p.norm_trick = trick ? 1 : 0;
   const unsigned long long s2 = p.push.seq;
   CMB_TRY(cgs_pass(ctx, K->cplx, CGS_UPDATE_DOT, p));
   p.x = y;
   p.pull = mail_pull_of(ctx, s2, K->h2);
+  p.pull.halt = K->halt;
   if (trick) {
     // pass 3: y -= V h2 ; ||y||^2 from the reduced h2 and ||y_before||^2 (same bits on every rank) -> K->scal[0]
     p.push = MailPush();
     p.hout = K->scal;
+    p.retry = K->halt + 1;  // cancellation guard: halt[1] = 1, halt[2] = retry_tag, and the chain halts
+    p.retry_tag = retry_tag;
+    p.norm_guard = ctx->norm_guard;
     *nrm2_seq = 0;  // the norm is a plain device scalar: the operator apply needs no mailbox
   } else {
     // pass 3: y -= V h2 ; partial ||y||^2 -> mailboxes, summed in the prologue of the operator apply
@@ -291,7 +298,7 @@ static int check_pair(const cmb_krylov* K, const cmb_op* op) {
 }
 
 // Enqueue the orthogonalisation part of Lanczos step k (k = index of the newest Krylov vector).
-static int enqueue_lanczos_orth(cmb_krylov* K, int64_t interval) {
+static int enqueue_lanczos_orth(cmb_krylov* K, int64_t interval, int retry_tag) {
   const int k = K->nk - 1;
   std::vector<Chunk> chunks;
   if (interval == 1) {
@@ -300,7 +307,7 @@ static int enqueue_lanczos_orth(cmb_krylov* K, int64_t interval) {
     contiguous_chunks(K, 0, K->ndefl + k + 1, chunks);
     K->nrm2_seq = 0;
     if (K->ctx->mail_ok && chunks.size() == 1)
-      return gram_schmidt2_mailed(K, chunks[0], K->v, K->w, &K->nrm2_seq);
+      return gram_schmidt2_mailed(K, chunks[0], K->v, K->w, &K->nrm2_seq, retry_tag);
     return gram_schmidt2(K, chunks, K->v, K->w, K->scal);
   }
   K->nrm2_seq = 0;
@@ -489,6 +496,7 @@ int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, d
   CMB_REQUIRE(alpha && beta && steps_done && status && nsteps >= 0, "bad argument");
   cmb_ctx* ctx = K->ctx;
   CMB_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->dead) return check_peer_wait(ctx);
   *steps_done = 0;
   *status = CMB_STEP_OK;
   if (nsteps == 0) return CMB_OK;
@@ -516,12 +524,22 @@ int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, d
     CMB_TRY(ensure_cols(K, K->ndefl + k + 2));
     const int nk_save = K->nk;
     K->nk = k + 1;  // enqueue_lanczos_orth works on the state "k+1 vectors"
-    int rc = enqueue_lanczos_orth(K, interval);
+    int rc = CMB_OK;
+    if (K->resume_norm_ready) {
+      // resumed after the Pythagorean guard: w is orthogonalised already, scal[0] holds the explicit norm
+      K->resume_norm_ready = false;
+      K->nrm2_seq = 0;
+    } else {
+      rc = enqueue_lanczos_orth(K, interval, enq);
+    }
     const int c = orth_cols_count(K, interval);
     K->nk = nk_save;
     CMB_TRY(rc);
     sc.threshold = threshold;
-    if (K->nrm2_seq) sc.nrm2_pull = mail_pull_of(ctx, K->nrm2_seq, K->scal);  // ||w||^2 sits in the mailbox
+    if (K->nrm2_seq) {
+      sc.nrm2_pull = mail_pull_of(ctx, K->nrm2_seq, K->scal);  // ||w||^2 sits in the mailbox
+      sc.nrm2_pull.halt = K->halt;
+    }
     sc.beta_slot = K->beta_dev + k;
     sc.alpha_slot = K->alpha_dev + size_t(k + 1) * 2;
     CMB_TRY(op->apply(K->w, K->col(K->ndefl + k + 1), K->v, shift, 0.0, sc));
@@ -544,28 +562,43 @@ int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, d
   CMB_CUDA(cudaMemcpyAsync(hs + 2 * na + nb, K->halt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CMB_CUDA(cudaStreamSynchronize(ctx->stream));
   const int halted = *reinterpret_cast<int*>(hs + 2 * na + nb);
-  if (ctx->mail_ok) {
-    int mail_err = 0;
-    CMB_CUDA(cudaMemcpy(&mail_err, ctx->d_mail_error, sizeof(int), cudaMemcpyDeviceToHost));
-    if (mail_err) {
-      set_error("a peer rank never published its Gram-Schmidt partials (mailbox wait timed out)");
-      return CMB_ERR_NCCL;
-    }
-  }
+  CMB_TRY(check_peer_wait(ctx));
   int ok_steps = enq;
+  bool guard_retry = false;
   if (halted) {
-    ok_steps = 0;
-    while (ok_steps < enq && hs[2 * na + ok_steps] > threshold) ++ok_steps;
-    *status = CMB_STEP_BREAKDOWN;
-    CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int), ctx->stream));
+    int flags[3] = {0, 0, 0};
+    CMB_CUDA(cudaMemcpy(flags, K->halt, sizeof(flags), cudaMemcpyDeviceToHost));
+    guard_retry = flags[1] != 0;
+    CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int) * 4, ctx->stream));
+    if (guard_retry) {
+      ok_steps = flags[2];  // steps of this chain completed before the guarded one
+    } else {
+      ok_steps = 0;
+      while (ok_steps < enq && hs[2 * na + ok_steps] > threshold) ++ok_steps;
+      *status = CMB_STEP_BREAKDOWN;
+    }
   }
   int ai = 0;
   if (did_first) alpha[ai++] = hs[0];
   for (int s = 0; s < ok_steps; ++s) alpha[ai++] = hs[2 * ((did_first ? 1 : 0) + s)];
-  const int nb_out = halted ? ok_steps + 1 : ok_steps;  // the breaking beta is kept (lanczos.hpp:433-436)
+  const int nb_out = (halted && !guard_retry) ? ok_steps + 1 : ok_steps;  // the breaking beta is kept (lanczos.hpp:433-436)
   for (int s = 0; s < nb_out && s < enq; ++s) beta[s] = hs[2 * na + s];
   K->nk = (did_first ? 1 : nk0) + ok_steps;
   *steps_done = (did_first ? 1 : 0) + ok_steps;
+  if (guard_retry) {
+    // The Pythagorean beta^2 = ||w1||^2 - |h2|^2 of step ok_steps lost its digits to cancellation.  w itself is fine
+    // (the third pass has written it): reduce ||w||^2 explicitly and resume the chain with the remaining steps.
+    CMB_TRY(vec_dot(ctx, K->cplx, K->w, K->w, K->ld, K->scal + 2, K->halt));
+    CMB_CUDA(cudaMemcpyAsync(K->scal, K->scal + 2, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CMB_TRY(allreduce_sum_f64(ctx, K->scal, 1));
+    K->resume_norm_ready = true;
+    const int64_t done_here = *steps_done;
+    int64_t more = 0;
+    int rc2 = cmb_lanczos_run(K, op, shift, interval, threshold, nsteps - done_here, alpha + ai, beta + nb_out, &more, status);
+    K->resume_norm_ready = false;
+    CMB_TRY(rc2);
+    *steps_done = done_here + more;
+  }
   return CMB_OK;
 }
 
@@ -691,6 +724,7 @@ int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double thresho
   CMB_REQUIRE(hcols && residues && steps_done && status && nsteps >= 0, "bad argument");
   cmb_ctx* ctx = K->ctx;
   CMB_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->dead) return check_peer_wait(ctx);
   double shr = 0.0, shi = 0.0;
   if (shift) {
     shr = static_cast<const double*>(shift)[0];
@@ -745,7 +779,7 @@ int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double thresho
       // row-partitioned fast path: the coefficient reductions go through the peer-memory mailboxes (reduced h1, h2
       // are written back to K->h1 / K->h2, ||w||^2 to K->scal[0]) — no collective kernel inside the chain
       unsigned long long norm_seq = 0;  // stays 0 without deflation vectors: the norm is in K->scal[0]
-      rc = gram_schmidt2_mailed(K, chunks[0], K->v, K->w, &norm_seq);
+      rc = gram_schmidt2_mailed(K, chunks[0], K->v, K->w, &norm_seq, int(s));
     } else {
       rc = gram_schmidt2(K, chunks, K->v, K->w, K->scal);
     }
@@ -774,13 +808,12 @@ int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double thresho
   }
   pool_free(ctx, hist);
   CMB_TRY(rc);
-  if (ctx->mail_ok) {
-    int mail_err = 0;
-    CMB_CUDA(cudaMemcpy(&mail_err, ctx->d_mail_error, sizeof(int), cudaMemcpyDeviceToHost));
-    if (mail_err) {
-      set_error("a peer rank never published its Gram-Schmidt partials or halo values (wait timed out)");
-      return CMB_ERR_NCCL;
-    }
+  CMB_TRY(check_peer_wait(ctx));
+  int guard_step = -1;
+  if (halted) {
+    int flags[3] = {0, 0, 0};
+    CMB_CUDA(cudaMemcpy(flags, K->halt, sizeof(flags), cudaMemcpyDeviceToHost));
+    if (flags[1]) guard_step = flags[2];
   }
   // steps are valid until a residue <= threshold appears (that step is still valid; the next one was refused)
   double* hs = K->h_stage;
@@ -792,11 +825,31 @@ int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double thresho
     for (int i = 0; i < (k + 1) * es; ++i) hout[i] = slot[K->ndefl * es + i] + slot[hstride + K->ndefl * es + i];
     residues[s] = sqrt(slot[2 * hstride]);
     ++done;
+    if (int(s) == guard_step) break;  // the Pythagorean residue of this step is unreliable: replaced below
     if (residues[s] <= threshold) break;
+  }
+  if (halted) CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int) * 4, ctx->stream));
+  if (guard_step >= 0) {
+    // cancellation in ||w1||^2 - |h2|^2: w is orthogonalised, reduce its norm explicitly and go on with the chain
+    CMB_TRY(vec_dot(ctx, K->cplx, K->w, K->w, K->ld, K->scal + 2, K->halt));
+    CMB_CUDA(cudaMemcpyAsync(K->scal, K->scal + 2, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CMB_TRY(allreduce_sum_f64(ctx, K->scal, 1));
+    CMB_CUDA(cudaMemcpyAsync(K->h_stage, K->scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    residues[done - 1] = sqrt(K->h_stage[0]);
+    K->residue = residues[done - 1];
+    K->nk = k0 + int(done);
+    *steps_done = done;
+    if (done < nsteps) {
+      int64_t more = 0;
+      CMB_TRY(cmb_arnoldi_run(K, op, shift, threshold, nsteps - done, static_cast<double*>(hcols) + size_t(done) * ldh * es, ldh,
+                              residues + done, &more, status));
+      *steps_done = done + more;
+    }
+    return CMB_OK;
   }
   if (halted) {
     *status = CMB_STEP_BREAKDOWN;
-    CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int), ctx->stream));
     if (done < nsteps) {
       // the chain stopped on the device: w and ||w||^2 still describe the last valid step
       CMB_CUDA(cudaMemcpyAsync(K->scal, hs + size_t(done - 1) * (2 * hstride + 1) + 2 * hstride, sizeof(double),

@@ -198,13 +198,17 @@ __global__ void sell_halo_flag_kernel(const long long* __restrict__ slice_ptr, c
   if (lane == 0) flag[gwarp] = (unsigned char)any;
 }
 
+// bad[0] is raised when the CSR arrays are inconsistent (decreasing rowptr, row longer than 2^31, column index outside
+// [0, ncols)): the build then fails with CMB_ERR_INVALID instead of leaving an operator that reads out of bounds.
 __global__ void sell_width_kernel(const long long* __restrict__ rowptr, long long nrows, long long nslices,
-                                  int* __restrict__ width) {
+                                  int* __restrict__ width, int* __restrict__ bad) {
   const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gwarp >= nslices) return;
   const long long r = gwarp * 32 + lane;
-  int len = (r < nrows) ? int(rowptr[r + 1] - rowptr[r]) : 0;
+  const long long len64 = (r < nrows) ? rowptr[r + 1] - rowptr[r] : 0;
+  if (len64 < 0 || len64 > 0x7fffffffll) *bad = 1;
+  int len = (len64 < 0 || len64 > 0x7fffffffll) ? 0 : int(len64);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
   if (lane == 0) width[gwarp] = len;
@@ -214,7 +218,7 @@ template <int ES>
 __global__ void sell_fill_kernel(const long long* __restrict__ rowptr, const int* __restrict__ col,
                                  const double* __restrict__ val, long long nrows, long long nslices,
                                  const long long* __restrict__ slice_ptr, int* __restrict__ scol,
-                                 double* __restrict__ sval) {
+                                 double* __restrict__ sval, long long ncols, int* __restrict__ bad) {
   const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gwarp >= nslices) return;
@@ -231,7 +235,9 @@ __global__ void sell_fill_kernel(const long long* __restrict__ rowptr, const int
   for (int k = 0; k < width; ++k) {
     const long long dst = base + (long long)k * 32 + lane;
     if (k < len) {
-      scol[dst] = col[p0 + k];
+      const int cc = col[p0 + k];
+      if (cc < 0 || cc >= ncols) *bad = 2;
+      scol[dst] = (cc < 0 || cc >= ncols) ? self : cc;
 #pragma unroll
       for (int e = 0; e < ES; ++e) sval[dst * ES + e] = val[(p0 + k) * ES + e];
     } else {
@@ -271,6 +277,7 @@ struct SellOp : cmb_op {
       // kernel gets extra leading CTAs that push; a pack kernel + ncclSend/ncclRecv group otherwise
       CMB_TRY(halo->exchange(ctx, w, sc.halt));
       d_halo = halo->pull_args();
+      d_halo.halt = sc.halt;
       if (halo->p2p) {
         if (2 * n_interior < nslices) {
           // most slices read remote columns, so there is little to hide the exchange behind: all CTAs push first.
@@ -341,7 +348,8 @@ struct SellOp : cmb_op {
   }
 };
 
-static int build_sell(SellOp* op, const int64_t* rowptr, const int32_t* col, const void* val) {
+// ncols: number of valid column indices (n_global on a single rank, n_local + halo entries for a shard)
+static int build_sell(SellOp* op, const int64_t* rowptr, const int32_t* col, const void* val, long long ncols) {
   cmb_ctx* ctx = op->ctx;
   const int es = op->cplx ? 2 : 1;
   const long long n = op->n_local;
@@ -352,17 +360,21 @@ static int build_sell(SellOp* op, const int64_t* rowptr, const int32_t* col, con
   int* d_ccol = nullptr;
   double* d_cval = nullptr;
   int* d_width = nullptr;
+  int* d_bad = nullptr;
   auto cleanup = [&]() {
     pool_free(ctx, d_rowptr);
     pool_free(ctx, d_ccol);
     pool_free(ctx, d_cval);
     pool_free(ctx, d_width);
+    pool_free(ctx, d_bad);
   };
   int rc = [&]() -> int {
     CMB_TRY(pool_alloc(ctx, &d_rowptr, sizeof(long long) * (n + 1)));
     CMB_TRY(pool_alloc(ctx, &d_ccol, sizeof(int) * std::max<long long>(nnz, 1)));
     CMB_TRY(pool_alloc(ctx, &d_cval, sizeof(double) * es * std::max<long long>(nnz, 1)));
     CMB_TRY(pool_alloc(ctx, &d_width, sizeof(int) * std::max<long long>(op->nslices, 1)));
+    CMB_TRY(pool_alloc(ctx, &d_bad, sizeof(int)));
+    CMB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
     CMB_CUDA(cudaMemcpyAsync(d_rowptr, rowptr, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
     CMB_CUDA(cudaMemcpyAsync(d_ccol, col, sizeof(int) * nnz, cudaMemcpyHostToDevice, ctx->stream));
     CMB_CUDA(cudaMemcpyAsync(d_cval, val, sizeof(double) * es * nnz, cudaMemcpyHostToDevice, ctx->stream));
@@ -371,12 +383,18 @@ static int build_sell(SellOp* op, const int64_t* rowptr, const int32_t* col, con
     const int grid = int((nthreads + threads - 1) / threads);
     if (op->nslices > 0) {
       LaunchScope ls(ctx, "sell_build");
-      sell_width_kernel<<<grid, threads, 0, ctx->stream>>>(d_rowptr, n, op->nslices, d_width);
+      sell_width_kernel<<<grid, threads, 0, ctx->stream>>>(d_rowptr, n, op->nslices, d_width, d_bad);
     }
     CMB_CUDA(cudaGetLastError());
     std::vector<int> width(op->nslices);
+    int bad = 0;
     CMB_CUDA(cudaMemcpyAsync(width.data(), d_width, sizeof(int) * op->nslices, cudaMemcpyDeviceToHost, ctx->stream));
+    CMB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bad) {
+      set_error("CSR rowptr is not non-decreasing (or a row is longer than 2^31 entries)");
+      return CMB_ERR_INVALID;
+    }
     // stencil-like matrices: pad every slice to the maximum width when that costs < 5 % extra entries, which
     // enables the fully unrolled uniform-width kernel
     int maxw = 0;
@@ -402,13 +420,18 @@ static int build_sell(SellOp* op, const int64_t* rowptr, const int32_t* col, con
       LaunchScope ls(ctx, "sell_build");
       if (es == 2)
         sell_fill_kernel<2><<<grid, threads, 0, ctx->stream>>>(d_rowptr, d_ccol, d_cval, n, op->nslices,
-                                                               op->d_slice_ptr, op->d_col, op->d_val);
+                                                               op->d_slice_ptr, op->d_col, op->d_val, ncols, d_bad);
       else
         sell_fill_kernel<1><<<grid, threads, 0, ctx->stream>>>(d_rowptr, d_ccol, d_cval, n, op->nslices,
-                                                               op->d_slice_ptr, op->d_col, op->d_val);
+                                                               op->d_slice_ptr, op->d_col, op->d_val, ncols, d_bad);
     }
     CMB_CUDA(cudaGetLastError());
+    CMB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bad) {
+      set_error("CSR column index outside [0, %lld)", ncols);
+      return CMB_ERR_INVALID;
+    }
     return CMB_OK;
   }();
   cleanup();
@@ -614,10 +637,10 @@ int cmb_op_csr_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t r
       op->halo = new (std::nothrow) HaloExchange();
       rc = op->halo ? op->halo->setup(ctx, n_global, op->cplx ? 2 : 1, halo_cols, per_owner) : CMB_ERR_NOMEM;
     }
-    if (rc == CMB_OK) rc = build_sell(op, rowptr, col_local.data(), val);
+    if (rc == CMB_OK) rc = build_sell(op, rowptr, col_local.data(), val, n + int64_t(halo_cols.size()));
     if (rc == CMB_OK && op->halo->p2p) rc = build_slice_order(op);
   } else {
-    rc = build_sell(op, rowptr, col, val);
+    rc = build_sell(op, rowptr, col, val, n_global);
   }
   if (rc != CMB_OK) {
     delete op;
@@ -720,8 +743,9 @@ int cmb_op_apply_host(cmb_op* op, const void* x, void* y) {
   const int64_t nd = op->n_local * es;
   if (nd == 0) return CMB_OK;
   const int64_t ld = (nd + 511) / 512 * 512;
+  if (ctx->dead) return check_peer_wait(ctx);
   double* buf = nullptr;
-  CMB_CUDA(cudaMalloc(&buf, sizeof(double) * (3 * ld + 8)));
+  CMB_TRY(pool_alloc(ctx, &buf, sizeof(double) * (3 * ld + 8)));  // stream-ordered pool: no cudaMalloc/cudaFree per apply
   int rc = [&]() -> int {
     double *w = buf, *u = buf + ld, *v = buf + 2 * ld, *sc = buf + 3 * ld;
     CMB_CUDA(cudaMemsetAsync(buf, 0, sizeof(double) * (3 * ld + 8), ctx->stream));
@@ -737,9 +761,10 @@ int cmb_op_apply_host(cmb_op* op, const void* x, void* y) {
     CMB_TRY(op->apply(w, u, v, 0.0, 0.0, s));
     CMB_CUDA(cudaMemcpyAsync(y, v, sizeof(double) * nd, cudaMemcpyDeviceToHost, ctx->stream));
     CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    CMB_TRY(check_peer_wait(ctx));  // a timed-out halo wait must not return stale data silently
     return CMB_OK;
   }();
-  cudaFree(buf);
+  pool_free(ctx, buf);
   return rc;
 }
 

@@ -14,12 +14,95 @@ from . import capi
 from .capi import check, lib, ptr
 
 
+class VirtualGroup:
+    """nranks virtual ranks on one device (cmpt_b200_debug.h): test vehicle for the multi-rank code paths on a box
+    with a single GPU.  Every rank must be driven by its own host thread; see run_virtual_ranks()."""
+
+    def __init__(self, device=0, nranks=2):
+        h = C.c_void_p()
+        check(lib().cmb_vgroup_create(int(device), int(nranks), C.byref(h)))
+        self.h, self.device, self.nranks = h, device, nranks
+
+    def info(self):
+        n, g, sm = C.c_int(), C.c_int(), C.c_int()
+        check(lib().cmb_vgroup_info(self.h, C.byref(n), C.byref(g), C.byref(sm)))
+        return {"nranks": n.value, "green_contexts": bool(g.value), "sms_per_rank": sm.value}
+
+    def close(self):
+        if self.h:
+            lib().cmb_vgroup_destroy(self.h)
+            self.h = None
+
+
+def run_virtual_ranks(nranks, fn, device=0, timeout=600.0):
+    """Runs fn(ctx, comm) on nranks virtual ranks, one host thread each, and returns the list of results.  comm offers
+    rank, world, barrier(), gather(obj) -> list over ranks, row_range(n).  The first exception of any rank is re-raised."""
+    import threading
+
+    group = VirtualGroup(device, nranks)
+    barrier = threading.Barrier(nranks)
+    box = [None] * nranks
+    results, errors = [None] * nranks, [None] * nranks
+
+    class Comm:
+        def __init__(self, rank):
+            self.rank, self.world = rank, nranks
+
+        def barrier(self):
+            barrier.wait(timeout)
+
+        def gather(self, obj):
+            box[self.rank] = obj
+            barrier.wait(timeout)
+            out = list(box)
+            barrier.wait(timeout)
+            return out
+
+        def row_range(self, n):
+            return (self.rank * n) // nranks, ((self.rank + 1) * n) // nranks
+
+    def work(rank):
+        ctx = None
+        try:
+            ctx = Context(device, virtual=(group, rank))
+            results[rank] = fn(ctx, Comm(rank))
+        except BaseException as e:  # noqa: BLE001 - re-raised in the caller's thread
+            errors[rank] = e
+            barrier.abort()
+        finally:
+            try:
+                if ctx is not None:
+                    ctx.close()
+            except Exception:
+                pass
+
+    threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(nranks)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout)
+    group_info = group.info()
+    alive = [t.is_alive() for t in threads]
+    if not any(alive):
+        group.close()
+    first = [e for e in errors if e is not None and not isinstance(e, threading.BrokenBarrierError)] or [e for e in errors if e is not None]
+    if first:
+        raise first[0]
+    if any(alive):
+        raise TimeoutError("virtual ranks did not finish within %.0f s" % timeout)
+    return results, group_info
+
+
 class Context:
     """One GPU / one rank (cmb_ctx)."""
 
-    def __init__(self, device=0, rank=0, nranks=1, nccl_id=None):
+    def __init__(self, device=0, rank=0, nranks=1, nccl_id=None, virtual=None):
         h = C.c_void_p()
-        if nranks == 1:
+        if virtual is not None:
+            group, rank = virtual
+            nranks = group.nranks
+            check(lib().cmb_ctx_create_virtual(group.h, int(rank), C.byref(h)))
+        elif nranks == 1:
             check(lib().cmb_ctx_create(int(device), C.byref(h)))
         else:
             idbuf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
@@ -61,6 +144,9 @@ class Context:
     def flush_l2(self):
         check(lib().cmb_ctx_flush_l2(self.h))
 
+    def set_spin_timeout(self, seconds):
+        check(lib().cmb_ctx_set_spin_timeout(self.h, float(seconds)))
+
     def close(self):
         if self.h:
             for s in list(self._solvers):
@@ -92,6 +178,8 @@ class DeviceOperator:
         val = np.ascontiguousarray(val, dtype=capi.np_dtype(code))
         nloc = rowptr.size - 1
         n_global = nloc if n_global is None else n_global
+        if nloc < 0 or rowptr[0] != 0 or col.size < rowptr[-1] or val.size < rowptr[-1]:
+            raise ValueError("inconsistent CSR arrays: rowptr must start at 0 and col/val must hold rowptr[-1] entries")
         h = C.c_void_p()
         check(lib().cmb_op_csr_create(ctx.h, code, n_global, row_begin, row_begin + nloc, ptr(rowptr), ptr(col),
                                       ptr(val), C.byref(h)))

@@ -5,7 +5,7 @@
  * plus the solver classes built on it.  This header is the boundary the B200 build puts under those
  * classes: plain pointers and sizes, opaque handles, int status codes, no C++/torch types.  The C++
  * drop-in headers (include/cmpt/eigen_ex/lanczos.hpp, arnoldi.hpp) and the ctypes binding
- * (cmpt-eigenex_b200/capi.py) are both written against exactly these entry points.
+ * (cmpt_eigenex_b200/capi.py) are both written against exactly these entry points.
  *
  * Conventions
  *   - every function returns CMB_OK (0) or a negative error class and never throws;
@@ -96,10 +96,6 @@ int cmb_op_dense_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t
 /* matrix-free spin-1/2 Heisenberg chain (cfg 5): H = J sum_i [SzSz + (S+S- + S-S+)/2]_{i,i+1}; the
  * top log2(nranks) bits of the state index are the rank. */
 int cmb_op_heisenberg_create(cmb_ctx* ctx, cmb_dtype dtype, int L, double J, int pbc, cmb_op** out);
-/* diagnostic / test entry: the row-partitioned Heisenberg operator with nranks VIRTUAL ranks on one GPU (same
- * kernels and packing as real ranks, the NVLink exchange replaced by device copies); x, y: full 2^L host vectors */
-int cmb_debug_heisenberg_virtual(cmb_ctx* ctx, cmb_dtype dtype, int L, double J, int pbc, int nranks, const void* x,
-                                 void* y);
 /* host-only: the exchange plan of rank `rank` of `nranks` for the matrix-free Heisenberg chain.  Entry k of the
  * outputs (capacity >= 8) describes remote bond k: kind (2 straddle, 3 rank-rank, 4 periodic wrap), partner rank,
  * whether a slab travels, its offset in this rank's receive buffer and its length, both in units of the local slab
@@ -110,6 +106,7 @@ int cmb_heisenberg_plan(int L, int pbc, int nranks, int rank, int* kind, int* pa
  * slabs (single-rank contexts only).  Costs one D2H + one H2D of an n-vector per Krylov step. */
 typedef void (*cmb_matmul_fn)(const void* in, void* out, void* user);
 int cmb_op_callback_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n, cmb_matmul_fn fn, void* user, cmb_op** out);
+/* collective on multi-rank contexts when the operator exchanges halos through peer memory: every rank must call it */
 int cmb_op_destroy(cmb_op* op);
 cmb_ctx* cmb_op_context(const cmb_op* op);
 int64_t cmb_op_row_begin(const cmb_op* op);
@@ -176,10 +173,6 @@ int cmb_arnoldi_run(cmb_krylov* k, cmb_op* op, const void* shift, double thresho
  * leading dimension ldx) in coef_dtype (a real basis with complex coefficients gives complex vectors). */
 int cmb_krylov_ritz_vectors(cmb_krylov* k, cmb_dtype coef_dtype, const void* coef, int64_t ldc,
                             int64_t ncoef, int64_t nev, void* x_host, int64_t ldx);
-
-/* diagnostic: mean device time of one Gram-Schmidt pass (mode 0 DOT, 1 UPDATE_DOT, 2 UPDATE_NORM) over the first
- * ncols columns of the basis, `reps` back-to-back launches timed with CUDA events */
-int cmb_debug_cgs_pass(cmb_krylov* k, int mode, int ncols, int reps, double* ms_per_launch);
 
 /* g = V^H x over the Krylov vectors (x: local host slab; g: ncols dtype elements) and out = sum_m coef_m u_m over the
  * first ncoef Krylov vectors (plain combination: no normalisation, no phase).  Together they evaluate functions of

@@ -3,7 +3,7 @@
 The library is the CPU restatement of the reference's Krylov step functions
 (see krylov_oracle.cpp for the file:line map).  Importers: tests/, the smoke
 check in __graft_entry__.py and the cpu_baseline / --impl reference legs of
-bench.py.  The product (cmpt-eigenex_b200/, include/) never imports this.
+bench.py.  The product (cmpt_eigenex_b200/, include/) never imports this.
 """
 import ctypes as C
 import os

@@ -3,7 +3,7 @@
 // TEST INFRASTRUCTURE ONLY.  This file is a CPU restatement of the reference's
 // Krylov basis builders (versmc/cmpt-eigenex, include/cmpt/eigen_ex/lanczos.hpp
 // and arnoldi.hpp).  It is the checker for the CUDA path and the timed CPU
-// baseline; nothing under cmpt-eigenex_b200/ or include/ may include, link or
+// baseline; nothing under cmpt_eigenex_b200/ or include/ may include, link or
 // call it.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs load the library built from it.
 //

@@ -6,5 +6,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# virtual ranks (tests/test_virtual_ranks.py): the streams of different ranks must not share a hardware queue; the
+# variable is read when CUDA initialises, so it has to be set before the first test touches the library
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")

@@ -636,3 +636,27 @@ def test_exponential_solver_matches_oracle_and_expm(ctx, dtype, x):
     np.testing.assert_allclose(t1, sla.expm(x * A) @ x0, atol=1e-10)
     t2 = es2.expSolveWithTaylor(x * 0.1, radius, x0, auto_division=False)
     np.testing.assert_allclose(t2, sla.expm(0.1 * x * A) @ x0, atol=1e-10)
+
+
+def test_invalid_csr_is_rejected_on_the_device(ctx):
+    """Bad column indices / a decreasing rowptr are caught during the SELL build (no out-of-bounds operator is left behind)."""
+    rp, c, v = syn.laplacian2d_csr(10)
+    bad = c.copy()
+    bad[17] = 100  # n = 100: one past the end
+    with pytest.raises(capi.CmbError) as e:
+        pkg.DeviceOperator.from_csr(ctx, rp, bad, v)
+    assert e.value.code == -1 and "column index" in str(e.value)
+    bad[17] = -3
+    with pytest.raises(capi.CmbError):
+        pkg.DeviceOperator.from_csr(ctx, rp, bad, v)
+    rp2 = rp.copy()
+    rp2[5], rp2[6] = rp2[6], rp2[5] - 1  # decreasing
+    with pytest.raises(capi.CmbError) as e:
+        pkg.DeviceOperator.from_csr(ctx, rp2, c, v)
+    assert "rowptr" in str(e.value)
+    with pytest.raises(ValueError):
+        pkg.DeviceOperator.from_csr(ctx, rp, c[:-3], v)
+    # the context is still healthy
+    op = pkg.DeviceOperator.from_csr(ctx, rp, c, v)
+    x = syn.start_vector(100, seed=1)
+    np.testing.assert_allclose(op.apply(x), core.Operator.csr(rp, c, v).apply(x), atol=1e-14)

@@ -75,7 +75,7 @@ def test_hessenberg_eigen_real_nonsymmetric_conjugate_pairs():
 
 def _declared_in_headers():
     names = set()
-    for hdr in ("cmpt_b200.h", "cmpt_b200_solver.h"):
+    for hdr in ("cmpt_b200.h", "cmpt_b200_solver.h", "cmpt_b200_debug.h"):
         src = open(os.path.join(ROOT, "include", hdr)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names.update(re.findall(r"\b(cmbs?_[a-z0-9_]+)\s*\(", src))
