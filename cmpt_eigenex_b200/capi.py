@@ -98,6 +98,7 @@ def _declare(L):
         "cmb_krylov_project": (i32, [vp, vp, vp]),
         "cmb_krylov_combine": (i32, [vp, vp, i64, vp]),
         "cmb_debug_cgs_pass": (i32, [vp, i32, i32, i32, P(dbl)]),
+        "cmb_debug_op_exchange_count": (i32, [vp, P(C.c_longlong)]),
         "cmb_vgroup_create": (i32, [i32, i32, P(vp)]),
         "cmb_vgroup_destroy": (i32, [vp]),
         "cmb_vgroup_info": (i32, [vp, P(i32), P(i32), P(i32)]),

@@ -149,6 +149,8 @@ struct cmb_ctx {
   long long spin_timeout = 60000000000ll;
   double norm_guard = 1e-8;        // guard ratio of the Pythagorean norm (CgsPass::norm_guard; CMPT_B200_NORM_GUARD)
   bool dead = false;               // a peer wait timed out: the sequence numbers of the ranks no longer agree
+  cudaMemPool_t mempool = nullptr; // virtual ranks: a pool of their own (see pool_alloc)
+  std::vector<void*> graveyard, host_graveyard;  // virtual ranks: frees deferred to cmb_ctx_destroy (see dfree)
   cmb::VGroup* vgroup = nullptr;   // virtual rank (vgroup.cu): collectives are host-thread rendezvous, not NCCL
   // L2 flush buffer
   void* d_flush = nullptr;
@@ -215,7 +217,11 @@ EncodeTiledFn get_encode_tiled();
 template <class T>
 inline int pool_alloc(cmb_ctx* ctx, T** p, size_t bytes) {
   *p = nullptr;
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 16, ctx->stream);
+  // Virtual ranks allocate from a pool of their own: in the device's shared default pool the driver may make this
+  // rank's stream wait for the stream of the rank that freed the block it reuses (cudaMemPoolReuseAllowInternal-
+  // Dependencies), and that stream may be executing a kernel that waits for this rank: dead-lock.
+  cudaError_t e = ctx->mempool ? cudaMallocFromPoolAsync(reinterpret_cast<void**>(p), bytes ? bytes : 16, ctx->mempool, ctx->stream)
+                               : cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 16, ctx->stream);
   if (e != cudaSuccess) {
     cudaGetLastError();
     set_error("out of device memory (%zu bytes): %s", bytes, cudaGetErrorString(e));
@@ -225,6 +231,32 @@ inline int pool_alloc(cmb_ctx* ctx, T** p, size_t bytes) {
 }
 inline void pool_free(cmb_ctx* ctx, void* p) {
   if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// cudaFree / cudaFreeHost synchronise the whole device.  Between real ranks (one process per GPU) that is harmless; a
+// virtual rank that frees something while a peer's kernel spins on this rank's NEXT launch would dead-lock, so virtual
+// ranks park the pointers until cmb_ctx_destroy (all ranks idle there).  Test-only mode: the growth is bounded by the
+// test's allocations.
+inline void dfree(cmb_ctx* ctx, void* p) {
+  if (!p) return;
+  if (ctx && ctx->vgroup)
+    ctx->graveyard.push_back(p);
+  else
+    cudaFree(p);
+}
+inline void hfree(cmb_ctx* ctx, void* p) {
+  if (!p) return;
+  if (ctx && ctx->vgroup)
+    ctx->host_graveyard.push_back(p);
+  else
+    cudaFreeHost(p);
+}
+// small device -> host / memset transfers on the context's stream (never on the legacy default stream: under green
+// contexts a synchronous copy there waits for the kernels of every virtual rank)
+inline int d2h_sync(cmb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  CMB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CMB_OK;
 }
 
 template <class T>

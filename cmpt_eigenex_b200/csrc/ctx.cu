@@ -214,10 +214,11 @@ int check_peer_wait(cmb_ctx* ctx) {
   }
   if (!ctx->mail_ok) return CMB_OK;
   int err = 0;
-  CMB_CUDA(cudaMemcpy(&err, ctx->d_mail_error, sizeof(int), cudaMemcpyDeviceToHost));
+  CMB_TRY(d2h_sync(ctx, &err, ctx->d_mail_error, sizeof(int)));
   if (!err) return CMB_OK;
   // the flag is cleared so that the message appears once; the context stays marked dead (see above)
-  CMB_CUDA(cudaMemset(ctx->d_mail_error, 0, sizeof(int)));
+  CMB_CUDA(cudaMemsetAsync(ctx->d_mail_error, 0, sizeof(int), ctx->stream));
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->dead = true;
   set_error("a peer rank never published its Gram-Schmidt partials or halo values: the in-kernel wait timed out after "
             "%.1f s (CMPT_B200_SPIN_TIMEOUT_S / cmb_ctx_set_spin_timeout change the limit; replaying profilers and "
@@ -306,10 +307,11 @@ static int mail_setup(cmb_ctx* c) {
     cudaGetLastError();
     base = nullptr;
   } else {
-    cudaMemset(base, 0, bytes);
+    cudaMemsetAsync(base, 0, bytes, c->stream);
   }
   cudaMalloc(&c->d_mail_error, sizeof(int));
-  cudaMemset(c->d_mail_error, 0, sizeof(int));
+  cudaMemsetAsync(c->d_mail_error, 0, sizeof(int), c->stream);
+  cudaStreamSynchronize(c->stream);
   void* mapped[kMaxPeers];
   c->mail_ok = ipc_share(c, base, mapped);
   if (!c->mail_ok) {
@@ -470,6 +472,7 @@ int cmb_ctx_destroy(cmb_ctx* c) {
   if (!c) return CMB_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->vgroup && !c->mail_ok && c->nranks > 1) rank_barrier(c);
   if (c->mail_ok) {
     // unmap the peers' mailboxes, wait until everybody has done so, then free the own one
     for (int q = 0; q < c->nranks; ++q)
@@ -491,6 +494,12 @@ int cmb_ctx_destroy(cmb_ctx* c) {
   if (c->d_flush) cudaFree(c->d_flush);
   if (c->t0) cudaEventDestroy(c->t0);
   if (c->t1) cudaEventDestroy(c->t1);
+  for (void* p : c->graveyard) cudaFree(p);
+  for (void* p : c->host_graveyard) cudaFreeHost(p);
+  if (c->mempool) {
+    cudaStreamSynchronize(c->stream);
+    cudaMemPoolDestroy(c->mempool);
+  }
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;

@@ -1,5 +1,6 @@
 // device_utils.cuh — device helpers shared by the operator-apply and vector kernels.
 #pragma once
+#include <stdio.h>
 #include "kernels.cuh"
 
 namespace cmb {
@@ -33,6 +34,9 @@ __device__ __forceinline__ void mail_wait(const MailPull& m) {
     const long long t0 = clock64();
     while (ld_acquire_sys_u64(m.flag + lane) < m.seq) {
       if (clock64() - t0 > m.timeout) {
+        if (*m.error == 0)
+          printf("libcmpt_b200: mailbox wait timed out: sender %d has published %llu, waiting for %llu (block %d)\n", lane,
+                 ld_acquire_sys_u64(m.flag + lane), m.seq, int(blockIdx.x));
         *m.error = 1;
         if (m.halt) *m.halt = 1;
         break;
@@ -78,7 +82,17 @@ __device__ __forceinline__ void halo_push_part(const HaloPush& hp, const double*
   __threadfence_system();
   __syncthreads();
   __shared__ int s_push_last;
+#ifdef CMB_HALO_TRACE
+  unsigned trace_prev = 0;
+  if (threadIdx.x == 0) {
+    trace_prev = atomicAdd(hp.ticket, 1u);
+    s_push_last = (trace_prev == unsigned(hp.npush) - 1u);
+    printf("TRACE push rank %d seq %llu block %d ticket_before %u npush %d all %d last %d flag0 %p flag1 %p\n", hp.rank, seq,
+           int(blockIdx.x), trace_prev, hp.npush, hp.all_push, s_push_last, (void*)hp.flag[0], (void*)hp.flag[1]);
+  }
+#else
   if (threadIdx.x == 0) s_push_last = (atomicAdd(hp.ticket, 1u) == unsigned(hp.npush) - 1u);
+#endif
   __syncthreads();
   if (s_push_last) {
     if (int(threadIdx.x) < hp.P && int(threadIdx.x) != hp.rank) st_release_sys_u64(hp.flag[threadIdx.x], seq);
@@ -89,6 +103,11 @@ __device__ __forceinline__ void halo_push_part(const HaloPush& hp, const double*
 // a short back-off, so that thousands of waiting warps do not compete with the incoming NVLink writes for L2), the
 // others park on the CTA barrier.  Bounded like mail_wait.
 __device__ __forceinline__ void halo_wait_cta(const HaloPull& h, unsigned long long seq) {
+#ifdef CMB_HALO_TRACE
+  if (threadIdx.x == 0)
+    printf("TRACE wait rank %d seq %llu block %d flags@%p = %llu %llu\n", h.rank, seq, int(blockIdx.x), (void*)h.flag,
+           ld_acquire_sys_u64(h.flag), ld_acquire_sys_u64(h.flag + 1));
+#endif
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     if (lane < h.P && lane != h.rank) {
@@ -96,6 +115,9 @@ __device__ __forceinline__ void halo_wait_cta(const HaloPull& h, unsigned long l
       while (ld_acquire_sys_u64(h.flag + lane) < seq) {
         __nanosleep(100);
         if (clock64() - t0 > h.timeout) {
+          if (*h.error == 0)
+            printf("libcmpt_b200: halo wait timed out on rank %d: sender %d has published exchange %llu, waiting for %llu "
+                   "(block %d)\n", h.rank, lane, ld_acquire_sys_u64(h.flag + lane), seq, int(blockIdx.x));
           *h.error = 1;
           if (h.halt) *h.halt = 1;
           break;

@@ -114,13 +114,13 @@ HaloExchange::~HaloExchange() {
     cudaStreamSynchronize(p2p_ctx->stream);
     ipc_unshare(p2p_ctx, p2p_mapped);
     rank_barrier(p2p_ctx);
-    cudaFree(push.xseq);
-    cudaFree(push.ticket);
-    cudaFree(p2p_base);
+    dfree(p2p_ctx, push.xseq);
+    dfree(p2p_ctx, push.ticket);
+    dfree(p2p_ctx, p2p_base);
   }
-  cudaFree(d_send_idx);
-  cudaFree(d_sendbuf);
-  cudaFree(d_halo);
+  dfree(own_ctx, d_send_idx);
+  dfree(own_ctx, d_sendbuf);
+  dfree(own_ctx, d_halo);
 }
 
 // Collective.  cnt is the P x P matrix of halo counts (cnt[q*P + r] = entries rank q reads from rank r).
@@ -147,9 +147,9 @@ int HaloExchange::setup_p2p(cmb_ctx* ctx, const std::vector<double>& cnt) {
   cudaStreamSynchronize(ctx->stream);
   void* mapped[kMaxPeers];
   if (!ipc_share(ctx, ok ? base : nullptr, mapped)) {
-    cudaFree(base);
-    cudaFree(xseq);
-    cudaFree(ticket);
+    dfree(ctx, base);
+    dfree(ctx, xseq);
+    dfree(ctx, ticket);
     cudaGetLastError();
     return CMB_OK;  // NCCL path stays
   }
@@ -189,6 +189,7 @@ int HaloExchange::setup(cmb_ctx* ctx, int64_t n, int es_, const std::vector<int3
                         const std::vector<int64_t>& per_owner) {
   P = ctx->nranks;
   rank = ctx->rank;
+  own_ctx = ctx;
   es = es_;
   const int64_t r0 = partition_begin(n, P, rank);
   recv_off.assign(P + 1, 0);
@@ -209,7 +210,7 @@ int HaloExchange::setup(cmb_ctx* ctx, int64_t n, int es_, const std::vector<int3
       rc = CMB_ERR_CUDA;
     }
   }
-  cudaFree(d_cnt);
+  dfree(ctx, d_cnt);
   CMB_TRY(rc);
   send_off.assign(P + 1, 0);
   for (int q = 0; q < P; ++q) send_off[q + 1] = send_off[q] + int64_t(cnt[size_t(q) * P + rank]);  // what q needs from me
@@ -230,7 +231,7 @@ int HaloExchange::setup(cmb_ctx* ctx, int64_t n, int es_, const std::vector<int3
       rc = CMB_ERR_CUDA;
     }
   }
-  cudaFree(d_need);
+  dfree(ctx, d_need);
   CMB_TRY(rc);
   const int64_t nloc = partition_begin(n, P, rank + 1) - r0;
   for (int64_t i = 0; i < nsend; ++i) {

@@ -22,6 +22,7 @@ struct HaloExchange {
   // peer-memory push path (CUDA IPC over NVLink); NCCL send/recv is the fallback when the mapping is unavailable
   bool p2p = false;
   cmb_ctx* p2p_ctx = nullptr;
+  cmb_ctx* own_ctx = nullptr;  // the context setup() ran on
   void* p2p_base = nullptr;  // own allocation: [kMaxPeers flags, padded to 256 B][2 x nrecv*es doubles]
   void* p2p_mapped[kMaxPeers] = {};
   HaloPush push;

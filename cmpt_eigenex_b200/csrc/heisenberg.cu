@@ -424,8 +424,8 @@ struct HeisenbergOp : cmb_op {
       if (ev_ready) cudaEventDestroy(ev_ready);
       ipc_unshare(ctx, p2p_mapped);
       rank_barrier(ctx);  // collective: nobody frees an exported buffer a peer may still write to
-      cudaFree(p2p_base);
-      cudaFreeHost(h_seq);
+      dfree(ctx, p2p_base);
+      hfree(ctx, h_seq);
     }
     if (ctx) {
       pool_free(ctx, d_recv);
@@ -530,7 +530,7 @@ struct HeisenbergOp : cmb_op {
     }
     void* mapped[kMaxPeers];
     if (!ipc_share(ctx, base, mapped)) {
-      cudaFree(base);
+      dfree(ctx, base);
       cudaGetLastError();
       return CMB_OK;
     }
@@ -703,9 +703,16 @@ struct HeisenbergOp : cmb_op {
     const int rb0 = plan.rank & 1;
     const unsigned long long x = ++xseq;
     const size_t par = size_t(x & 1ull);
-    if ((x & 255ull) == 0)  // keeps the pinned flag words of exchanges still in flight from being reused
-      for (size_t k = 0; k < plan.remote.size(); ++k) CMB_CUDA(cudaStreamSynchronize(xstream[k][0]));
-    CMB_CUDA(cudaEventRecord(ev_ready, ctx->stream));  // w (and the packed wrap half) are final
+    // Virtual ranks (one device): same-device copies run on SMs, and the SMs a side stream could use are held by the
+    // peers' spinning kernels, so there the slabs are copied in stream order on the rank's own stream (no overlap, same
+    // buffers, flags and parity).  Real ranks: copy engines on side streams, overlapped with the window passes.
+    const bool inl = ctx->vgroup != nullptr;
+    if ((x & 255ull) == 0) {  // keeps the pinned flag words of exchanges still in flight from being reused
+      if (inl) CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+      else
+        for (size_t k = 0; k < plan.remote.size(); ++k) CMB_CUDA(cudaStreamSynchronize(xstream[k][0]));
+    }
+    if (!inl) CMB_CUDA(cudaEventRecord(ev_ready, ctx->stream));  // w (and the packed wrap half) are final
     unsigned mask = 0;
     {
       for (size_t k = 0; k < plan.remote.size(); ++k) {
@@ -726,19 +733,19 @@ struct HeisenbergOp : cmb_op {
         unsigned long long* word = h_seq + ((x * kMaxRemote + k) % kSeqSlots);
         *word = x;
         // the slab goes as nsplit concurrent copies; the flag follows on stream 0 once all of them are done
-        const int ns = (count >= (size_t(1) << 16)) ? nsplit : 1;
+        const int ns = (!inl && count >= (size_t(1) << 16)) ? nsplit : 1;
         const size_t chunk = ((count + ns - 1) / ns + 1) & ~size_t(1);
         for (int c = 0; c < ns; ++c) {
           const size_t b = std::min(count, size_t(c) * chunk), e = std::min(count, b + chunk);
-          CMB_CUDA(cudaStreamWaitEvent(xstream[k][c], ev_ready, 0));
-          if (e > b)
-            CMB_CUDA(cudaMemcpyAsync(dst + b, src + b, sizeof(double) * (e - b), cudaMemcpyDefault, xstream[k][c]));
-          if (c > 0) CMB_CUDA(cudaEventRecord(ev_chunk[k][c], xstream[k][c]));
+          cudaStream_t cs = inl ? ctx->stream : xstream[k][c];
+          if (!inl) CMB_CUDA(cudaStreamWaitEvent(cs, ev_ready, 0));
+          if (e > b) CMB_CUDA(cudaMemcpyAsync(dst + b, src + b, sizeof(double) * (e - b), cudaMemcpyDefault, cs));
+          if (!inl && c > 0) CMB_CUDA(cudaEventRecord(ev_chunk[k][c], cs));
         }
         for (int c = 1; c < ns; ++c) CMB_CUDA(cudaStreamWaitEvent(xstream[k][0], ev_chunk[k][c], 0));
         CMB_CUDA(cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(pbase) + k, word, sizeof(unsigned long long),
-                                 cudaMemcpyDefault, xstream[k][0]));
-        CMB_CUDA(cudaEventRecord(ev_done[k], xstream[k][0]));
+                                 cudaMemcpyDefault, inl ? ctx->stream : xstream[k][0]));
+        if (!inl) CMB_CUDA(cudaEventRecord(ev_done[k], xstream[k][0]));
       }
     }
     const double* recv = reinterpret_cast<const double*>(static_cast<char*>(p2p_base) + kFlagBytes) + par * p2p_tot;
@@ -750,8 +757,9 @@ struct HeisenbergOp : cmb_op {
     a.timeout = ctx->spin_timeout;
     CMB_TRY(launch(a, w, ucol, v, shr, shi, sc));
     // whoever overwrites w or the pack buffer next must come after the copies that read them
-    for (size_t k = 0; k < plan.remote.size(); ++k)
-      if (mask & (1u << k)) CMB_CUDA(cudaStreamWaitEvent(ctx->stream, ev_done[k], 0));
+    if (!inl)
+      for (size_t k = 0; k < plan.remote.size(); ++k)
+        if (mask & (1u << k)) CMB_CUDA(cudaStreamWaitEvent(ctx->stream, ev_done[k], 0));
     return CMB_OK;
   }
 };

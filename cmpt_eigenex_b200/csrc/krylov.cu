@@ -78,11 +78,13 @@ static int ensure_cols(cmb_krylov* K, int total) {
   }
   const int cap = int(K->segs.size()) * K->seg_cols;
   if (cap > K->hcap) {
-    cudaFree(K->h1);
-    cudaFree(K->h2);
+    // stream-ordered (re)allocation: cudaFree would synchronise the whole device in the middle of a step chain,
+    // which dead-locks virtual ranks (a peer's kernel may be spinning on this rank's next launch)
+    pool_free(K->ctx, K->h1);
+    pool_free(K->ctx, K->h2);
     K->h1 = K->h2 = nullptr;
-    CMB_CUDA(cudaMalloc(&K->h1, sizeof(double) * 2 * (cap + 8)));
-    CMB_CUDA(cudaMalloc(&K->h2, sizeof(double) * 2 * (cap + 8)));
+    CMB_TRY(pool_alloc(K->ctx, &K->h1, sizeof(double) * 2 * (cap + 8)));
+    CMB_TRY(pool_alloc(K->ctx, &K->h2, sizeof(double) * 2 * (cap + 8)));
     K->hcap = cap;
   }
   return CMB_OK;
@@ -90,7 +92,7 @@ static int ensure_cols(cmb_krylov* K, int total) {
 
 static int ensure_stage(cmb_krylov* K, size_t elems) {
   if (elems <= K->h_stage_elems) return CMB_OK;
-  if (K->h_stage) cudaFreeHost(K->h_stage);
+  hfree(K->ctx, K->h_stage);
   K->h_stage = nullptr;
   K->h_stage_elems = 0;
   size_t want = std::max<size_t>(elems * 2, 4096);
@@ -394,25 +396,26 @@ int cmb_krylov_destroy(cmb_krylov* K) {
   if (!K) return CMB_OK;
   cudaSetDevice(K->ctx->device);
   cudaStreamSynchronize(K->ctx->stream);
-  for (auto p : K->segs) cudaFree(p);
-  cudaFree(K->v);
-  cudaFree(K->w);
-  cudaFree(K->h1);
-  cudaFree(K->h2);
-  cudaFree(K->scal);
-  cudaFree(K->halt);
-  cudaFree(K->alpha_dev);
-  cudaFree(K->beta_dev);
-  cudaFree(K->tmp1);
-  cudaFree(K->tmp2);
-  cudaFree(K->tmpz);
+  for (auto p : K->segs) dfree(K->ctx, p);
+  dfree(K->ctx, K->v);
+  dfree(K->ctx, K->w);
+  pool_free(K->ctx, K->h1);
+  pool_free(K->ctx, K->h2);
+  cudaStreamSynchronize(K->ctx->stream);
+  dfree(K->ctx, K->scal);
+  dfree(K->ctx, K->halt);
+  dfree(K->ctx, K->alpha_dev);
+  dfree(K->ctx, K->beta_dev);
+  dfree(K->ctx, K->tmp1);
+  dfree(K->ctx, K->tmp2);
+  dfree(K->ctx, K->tmpz);
   for (int b = 0; b < 2; ++b) {
-    cudaFree(K->xout[b]);
+    dfree(K->ctx, K->xout[b]);
     if (K->ev_x[b]) cudaEventDestroy(K->ev_x[b]);
     if (K->ev_c[b]) cudaEventDestroy(K->ev_c[b]);
   }
-  cudaFree(K->d_idx);
-  if (K->h_stage) cudaFreeHost(K->h_stage);
+  dfree(K->ctx, K->d_idx);
+  hfree(K->ctx, K->h_stage);
   delete K;
   return CMB_OK;
 }
@@ -567,7 +570,7 @@ int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, d
   bool guard_retry = false;
   if (halted) {
     int flags[3] = {0, 0, 0};
-    CMB_CUDA(cudaMemcpy(flags, K->halt, sizeof(flags), cudaMemcpyDeviceToHost));
+    CMB_TRY(d2h_sync(ctx, flags, K->halt, sizeof(flags)));
     guard_retry = flags[1] != 0;
     CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int) * 4, ctx->stream));
     if (guard_retry) {
@@ -812,7 +815,7 @@ int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double thresho
   int guard_step = -1;
   if (halted) {
     int flags[3] = {0, 0, 0};
-    CMB_CUDA(cudaMemcpy(flags, K->halt, sizeof(flags), cudaMemcpyDeviceToHost));
+    CMB_TRY(d2h_sync(ctx, flags, K->halt, sizeof(flags)));
     if (flags[1]) guard_step = flags[2];
   }
   // steps are valid until a residue <= threshold appears (that step is still valid; the next one was refused)
@@ -967,7 +970,7 @@ int cmb_krylov_ritz_vectors(cmb_krylov* K, cmb_dtype coef_dtype, const void* coe
   if (K->xout_doubles < out_need) {
     CMB_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int b = 0; b < 2; ++b) {
-      cudaFree(K->xout[b]);
+      dfree(ctx, K->xout[b]);
       K->xout[b] = nullptr;
     }
     K->xout_doubles = 0;

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 
+#include "cmpt_b200_debug.h"
 #include "device_utils.cuh"
 #include "halo.cuh"
 #include "op.cuh"
@@ -734,6 +735,20 @@ int64_t cmb_op_rows(const cmb_op* op) { return op ? op->n_local : 0; }
 int64_t cmb_op_height(const cmb_op* op) { return op ? op->n_global : 0; }
 int cmb_op_dtype(const cmb_op* op) { return op ? op->dtype : -1; }
 double cmb_op_bytes(const cmb_op* op) { return op ? op->bytes : 0.0; }
+
+// diagnostic (cmpt_b200_debug.h): number of halo exchanges this rank's CSR shard has completed (-1: no peer-memory halo)
+int cmb_debug_op_exchange_count(cmb_op* op, long long* count) {
+  CMB_REQUIRE(op && count, "null argument");
+  *count = -1;
+  SellOp* s = dynamic_cast<SellOp*>(op);
+  if (!s || !s->halo || !s->halo->p2p) return CMB_OK;
+  CMB_CUDA(cudaSetDevice(op->ctx->device));
+  CMB_CUDA(cudaStreamSynchronize(op->ctx->stream));
+  unsigned long long v = 0;
+  CMB_TRY(d2h_sync(op->ctx, &v, s->halo->push.xseq, sizeof(v)));
+  *count = (long long)v;
+  return CMB_OK;
+}
 
 int cmb_op_apply_host(cmb_op* op, const void* x, void* y) {
   CMB_REQUIRE(op && (op->n_local == 0 || (x && y)), "null argument");

@@ -147,7 +147,7 @@ int vgroup_allreduce_f64(cmb_ctx* c, double* p, size_t count) {
   std::vector<double> acc(count, 0.0), tmp(count);
   int rc = CMB_OK;
   for (int q = 0; q < g->P && rc == CMB_OK; ++q) {  // rank order: identical bits on every rank
-    if (cudaMemcpy(tmp.data(), g->slot[q], sizeof(double) * count, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    if (d2h_sync(c, tmp.data(), g->slot[q], sizeof(double) * count) != CMB_OK) {
       set_error("virtual allreduce: %s", cudaGetErrorString(cudaGetLastError()));
       rc = CMB_ERR_CUDA;
     }
@@ -168,7 +168,7 @@ int vgroup_allreduce_min_u64(cmb_ctx* c, unsigned long long* p, size_t count) {
   std::vector<unsigned long long> acc(count, ~0ull), tmp(count);
   int rc = CMB_OK;
   for (int q = 0; q < g->P && rc == CMB_OK; ++q) {
-    if (cudaMemcpy(tmp.data(), g->slot[q], sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    if (d2h_sync(c, tmp.data(), g->slot[q], sizeof(unsigned long long) * count) != CMB_OK) {
       set_error("virtual allreduce(min): %s", cudaGetErrorString(cudaGetLastError()));
       rc = CMB_ERR_CUDA;
     }
@@ -221,8 +221,9 @@ int vgroup_alltoallv_i32(cmb_ctx* c, const int32_t* d_send, const int64_t* send_
       set_error("virtual alltoallv: rank %d sends %lld entries to rank %d, which expects %lld", q, (long long)(b - a), c->rank,
                 (long long)(recv_off[q + 1] - recv_off[q]));
       rc = CMB_ERR_INVALID;
-    } else if (b > a && cudaMemcpy(d_recv + recv_off[q], static_cast<const int32_t*>(g->slot[q]) + a, sizeof(int32_t) * size_t(b - a),
-                                   cudaMemcpyDeviceToDevice) != cudaSuccess) {
+    } else if (b > a && (cudaMemcpyAsync(d_recv + recv_off[q], static_cast<const int32_t*>(g->slot[q]) + a,
+                                         sizeof(int32_t) * size_t(b - a), cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess ||
+                         cudaStreamSynchronize(c->stream) != cudaSuccess)) {
       set_error("virtual alltoallv: %s", cudaGetErrorString(cudaGetLastError()));
       rc = CMB_ERR_CUDA;
     }
@@ -236,6 +237,16 @@ int vgroup_attach(VGroup* g, cmb_ctx* c, int rank) {
   c->rank = rank;
   c->nranks = g->P;
   c->num_sms = g->sms[rank];
+  {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = g->device;
+    CMB_CUDA(cudaMemPoolCreate(&c->mempool, &props));
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(c->mempool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
   if (g->green) {
     // the compute stream of this rank runs on its own SM partition
     CUstream s = nullptr;
@@ -266,6 +277,11 @@ int cmb_vgroup_create(int device, int nranks, cmb_vgroup** out) {
   CMB_REQUIRE(out, "null argument");
   *out = nullptr;
   CMB_REQUIRE(nranks >= 1 && nranks <= kMaxPeers && (nranks & (nranks - 1)) == 0, "nranks must be a power of two <= 16");
+  // Effective only when this is the first CUDA call of the process (both variables are read when CUDA initialises):
+  // eager module loading, because the lazy loading of a kernel on its first launch synchronises the context and
+  // would wait for a peer rank's spinning kernel; enough hardware queues for the streams of all ranks.
+  setenv("CUDA_MODULE_LOADING", "EAGER", 0);
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
     cudaGetLastError();
@@ -275,6 +291,19 @@ int cmb_vgroup_create(int device, int nranks, cmb_vgroup** out) {
   CMB_REQUIRE(device >= 0 && device < ndev, "device index out of range");
   CMB_CUDA(cudaSetDevice(device));
   CMB_CUDA(cudaFree(nullptr));  // make sure the primary context exists before green contexts are carved out of it
+  if (nranks > 1) {
+    typedef CUresult (*GetModeFn)(CUmoduleLoadingMode*);
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUmoduleLoadingMode mode = CU_MODULE_EAGER_LOADING;
+    if (cudaGetDriverEntryPoint("cuModuleGetLoadingMode", &fp, cudaEnableDefault, &q) == cudaSuccess && fp &&
+        reinterpret_cast<GetModeFn>(fp)(&mode) == CUDA_SUCCESS && mode != CU_MODULE_EAGER_LOADING) {
+      set_error("virtual ranks need CUDA_MODULE_LOADING=EAGER in the environment before CUDA initialises: with lazy "
+                "loading the first launch of a kernel synchronises the context while a peer rank's kernel spins");
+      return CMB_ERR_UNSUPPORTED;
+    }
+    cudaGetLastError();
+  }
   cudaDeviceProp prop;
   CMB_CUDA(cudaGetDeviceProperties(&prop, device));
   cmb_vgroup* vg = new (std::nothrow) cmb_vgroup();

@@ -87,6 +87,10 @@ def run_virtual_ranks(nranks, fn, device=0, timeout=600.0):
         group.close()
     first = [e for e in errors if e is not None and not isinstance(e, threading.BrokenBarrierError)] or [e for e in errors if e is not None]
     if first:
+        others = ["rank %d: %s: %s" % (r, type(e).__name__, e) for r, e in enumerate(errors)
+                  if e is not None and e is not first[0] and not isinstance(e, threading.BrokenBarrierError)]
+        if others:
+            raise RuntimeError("%s: %s  [other ranks: %s]" % (type(first[0]).__name__, first[0], " | ".join(others))) from first[0]
         raise first[0]
     if any(alive):
         raise TimeoutError("virtual ranks did not finish within %.0f s" % timeout)

@@ -190,6 +190,85 @@ bool hessenberg_eigen(int n, const std::complex<Real>* h, std::vector<std::compl
   return ok;
 }
 
+
+// Unitary reduction of a general square complex matrix to upper-Hessenberg form by Householder reflectors
+// (Golub & Van Loan alg. 7.4.2): A = Q H Q^H.  a is n x n column-major and is overwritten by H; q receives Q.
+// Needed after a thick restart of the Arnoldi iteration, when the projected matrix is no longer Hessenberg.
+template <class Real>
+inline void hessenberg_reduce(int n, std::vector<std::complex<Real>>& a, std::vector<std::complex<Real>>& q) {
+  using C = std::complex<Real>;
+  auto A = [&](int i, int j) -> C& { return a[static_cast<std::size_t>(j) * n + i]; };
+  auto Q = [&](int i, int j) -> C& { return q[static_cast<std::size_t>(j) * n + i]; };
+  q.assign(static_cast<std::size_t>(n) * n, C(0));
+  for (int i = 0; i < n; ++i) Q(i, i) = C(1);
+  std::vector<C> v(static_cast<std::size_t>(n));
+  for (int k = 0; k + 2 < n; ++k) {
+    Real tail = 0;
+    for (int i = k + 2; i < n; ++i) tail += std::norm(A(i, k));
+    if (tail == Real(0)) continue;  // column already in Hessenberg form
+    const Real alpha = std::sqrt(std::norm(A(k + 1, k)) + tail);
+    const C x0 = A(k + 1, k);
+    const C phase = (std::abs(x0) == Real(0)) ? C(1) : x0 / std::abs(x0);
+    // v = x + phase*alpha*e1, reflector P = I - 2 v v^H / (v^H v)
+    for (int i = 0; i < n; ++i) v[static_cast<std::size_t>(i)] = C(0);
+    for (int i = k + 1; i < n; ++i) v[static_cast<std::size_t>(i)] = A(i, k);
+    v[static_cast<std::size_t>(k + 1)] += phase * alpha;
+    Real vn = 0;
+    for (int i = k + 1; i < n; ++i) vn += std::norm(v[static_cast<std::size_t>(i)]);
+    if (vn == Real(0)) continue;
+    for (int j = 0; j < n; ++j) {  // A <- P A
+      C s(0);
+      for (int i = k + 1; i < n; ++i) s += std::conj(v[static_cast<std::size_t>(i)]) * A(i, j);
+      s *= Real(2) / vn;
+      for (int i = k + 1; i < n; ++i) A(i, j) -= v[static_cast<std::size_t>(i)] * s;
+    }
+    for (int i = 0; i < n; ++i) {  // A <- A P, Q <- Q P
+      C s(0), t(0);
+      for (int j = k + 1; j < n; ++j) {
+        s += A(i, j) * v[static_cast<std::size_t>(j)];
+        t += Q(i, j) * v[static_cast<std::size_t>(j)];
+      }
+      s *= Real(2) / vn;
+      t *= Real(2) / vn;
+      for (int j = k + 1; j < n; ++j) {
+        A(i, j) -= s * std::conj(v[static_cast<std::size_t>(j)]);
+        Q(i, j) -= t * std::conj(v[static_cast<std::size_t>(j)]);
+      }
+    }
+    for (int i = k + 2; i < n; ++i) A(i, k) = C(0);
+  }
+}
+
+// Eigenvalues (and unit-norm right eigenvectors) of a general square complex matrix, column-major: Hessenberg
+// reduction when the matrix is not Hessenberg already, then hessenberg_eigen, then the back-transformation.
+template <class Real>
+bool general_eigen(int n, const std::complex<Real>* a, std::vector<std::complex<Real>>& w,
+                   std::vector<std::complex<Real>>* vectors) {
+  using C = std::complex<Real>;
+  bool is_hessenberg = true;
+  for (int j = 0; j < n && is_hessenberg; ++j)
+    for (int i = j + 2; i < n; ++i)
+      if (a[static_cast<std::size_t>(j) * n + i] != C(0)) {
+        is_hessenberg = false;
+        break;
+      }
+  if (is_hessenberg) return hessenberg_eigen<Real>(n, a, w, vectors);
+  std::vector<C> h(a, a + static_cast<std::size_t>(n) * n), q, y;
+  hessenberg_reduce<Real>(n, h, q);
+  const bool ok = hessenberg_eigen<Real>(n, h.data(), w, vectors ? &y : nullptr);
+  if (vectors) {
+    vectors->assign(static_cast<std::size_t>(n) * n, C(0));
+    for (int j = 0; j < n; ++j)
+      for (int p = 0; p < n; ++p) {
+        const C yp = y[static_cast<std::size_t>(j) * n + p];
+        const C* qp = q.data() + static_cast<std::size_t>(p) * n;
+        C* vj = vectors->data() + static_cast<std::size_t>(j) * n;
+        for (int i = 0; i < n; ++i) vj[i] += qp[i] * yp;
+      }
+  }
+  return ok;
+}
+
 }  // namespace detail
 }  // namespace EigenEx
 }  // namespace cmpt

@@ -9,6 +9,9 @@ if ROOT not in sys.path:
 # virtual ranks (tests/test_virtual_ranks.py): the streams of different ranks must not share a hardware queue; the
 # variable is read when CUDA initialises, so it has to be set before the first test touches the library
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# ... and every kernel must be loaded up front: the lazy loading of a kernel on its first launch synchronises the
+# context, which would wait for a peer rank's spinning kernel (cmb_vgroup_create refuses to run under lazy loading)
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 
 def pytest_configure(config):

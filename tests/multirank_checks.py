@@ -183,12 +183,16 @@ def gather_rows(comm, local):
     return np.concatenate(comm.gather(np.asarray(local)))
 
 
-def run_checks(pkg, ctx, comm, exp):
-    """Everything one rank does.  Returns a small summary dict."""
-    rank = comm.rank
+def run_checks(pkg, ctx, comm, exp, only=None):
+    """Everything one rank does.  Returns a small summary dict.  only: optional subset of section names."""
+    def want(name):
+        return only is None or name in only
+
     P = problems()
     results = {}
     for name in ("laplacian", "heisenberg", "convdiff_arnoldi"):
+        if not want(name):
+            continue
         pr, ex = P[name], exp[name]
         n, m = pr["n"], pr["m"]
         r0, r1 = comm.row_range(n)
@@ -232,7 +236,21 @@ def run_checks(pkg, ctx, comm, exp):
         op.close()
     # Krylov space exhausted on a row-partitioned operator: every rank must take the same halting decision on the
     # device (beta^2 from the reduced coefficients) and the chain must stop with the reference's log lines
-    pr, ex = P["exhaust"], exp["exhaust"]
+    if want("exhaust"):
+        _check_exhaust(pkg, ctx, comm, P["exhaust"], exp["exhaust"])
+    if want("breakdown_at_k"):
+        _check_breakdown(pkg, ctx, comm, P["breakdown_at_k"], exp["breakdown_at_k"])
+    if want("deflation"):
+        _check_deflation(pkg, ctx, comm, P["deflation"], exp["deflation"])
+    if want("one_directional"):
+        _check_one_directional(pkg, ctx, comm)
+    if want("heisenberg_mf"):
+        results["heisenberg_mf_E0"] = _check_heisenberg_mf(pkg, ctx, comm, exp["heisenberg_mf"])
+    comm.barrier()
+    return {k: np.asarray(v).tolist() for k, v in results.items()}
+
+
+def _check_exhaust(pkg, ctx, comm, pr, ex):
     nb = pr["n"]
     r0, r1 = comm.row_range(nb)
     x0 = syn.start_vector(nb, seed=11)
@@ -255,9 +273,11 @@ def run_checks(pkg, ctx, comm, exp):
     assert np.abs(xs - xf[r0:r1]).max() < 1e-10 * np.abs(xf).max()
     es.close()
     op.close()
+
+
+def _check_breakdown(pkg, ctx, comm, pr, ex):
     # exact breakdown at step k (invariant subspace of dimension k spread over the ranks): beta_k is rounding noise, the
     # chain halts on the device at the same step on every rank and the driver reports what the reference reports
-    pr, ex = P["breakdown_at_k"], exp["breakdown_at_k"]
     n = pr["n"]
     r0, r1 = comm.row_range(n)
     op = pkg.DeviceOperator.from_csr(ctx, *shard_of(pr["full"], r0, r1), n_global=n, row_begin=r0)
@@ -274,9 +294,11 @@ def run_checks(pkg, ctx, comm, exp):
     assert np.abs(es.eigenvalues() - ex["eigenvalues"]).max() < 1e-12
     es.close()
     op.close()
+
+
+def _check_deflation(pkg, ctx, comm, pr, ex):
     # deflation vectors on a row-partitioned operator (they keep the norm's own reduction, see gram_schmidt2_mailed):
     # two exact eigenvectors of the 2D Laplacian are projected out, Lanczos and Arnoldi must agree with the checker
-    pr, ex = P["deflation"], exp["deflation"]
     n = pr["n"]
     r0, r1 = comm.row_range(n)
     defl, lam = deflation_vectors()
@@ -299,6 +321,9 @@ def run_checks(pkg, ctx, comm, exp):
     assert np.abs(ea.hessenbergMatrix()[:, :8] - ex["arnoldi_hessenberg"][:, :8]).max() < 1e-10
     ea.close()
     op.close()
+
+
+def _check_one_directional(pkg, ctx, comm):
     # one-directional coupling (rank q reads from rank q+1 only): ranks that receive nothing still follow the protocol
     nu = 64
     r0, r1 = comm.row_range(nu)
@@ -310,8 +335,10 @@ def run_checks(pkg, ctx, comm, exp):
         xf = Au @ xf
     assert np.abs(xs - xf[r0:r1]).max() < 1e-12 * max(1.0, np.abs(xf).max())
     op.close()
+
+
+def _check_heisenberg_mf(pkg, ctx, comm, ex):
     # matrix-free Heisenberg ring, slabs exchanged through peer memory (cfg 5 at small L)
-    ex = exp["heisenberg_mf"]
     Lm = ex["L"]
     n = 1 << Lm
     r0, r1 = comm.row_range(n)
@@ -325,8 +352,7 @@ def run_checks(pkg, ctx, comm, exp):
     es.compute()
     assert abs(es.iterations() - ex["iterations"]) <= 1
     assert abs(es.eigenvalues()[0] - ex["eigenvalues"][0]) < 1e-10 * abs(ex["eigenvalues"][0])
-    results["heisenberg_mf_E0"] = es.eigenvalues()
+    e0 = es.eigenvalues()
     es.close()
     op.close()
-    comm.barrier()
-    return {k: np.asarray(v).tolist() for k, v in results.items()}
+    return e0

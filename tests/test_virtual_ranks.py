@@ -18,6 +18,13 @@ from cmpt_eigenex_b200 import synthetic as syn
 
 pytestmark = pytest.mark.gpu
 
+# Every section of the shared checks except the matrix-free Heisenberg slab exchange: between real GPUs the slabs travel
+# by copy engines over NVLink while the window passes run; on ONE device a slab copy needs SMs, which the peers'
+# spinning persistent kernels hold, so that overlap scheme cannot make progress there.  Its packing, offsets and
+# parity logic are covered on one GPU by test_heisenberg_partitioned_virtual_ranks (tests/test_gpu_parity.py, the ranks
+# run one after the other) and end to end by tests/dist_worker.py on real GPUs.
+SECTIONS = ["laplacian", "heisenberg", "convdiff_arnoldi", "exhaust", "breakdown_at_k", "deflation", "one_directional"]
+
 
 def _expected(which):
     from oracle import core
@@ -38,7 +45,7 @@ def _expected(which):
 @pytest.mark.parametrize("nranks", [2, 4, 8])
 def test_virtual_ranks_match_restatement(nranks):
     exp = _expected("restatement")
-    results, info = pkg.run_virtual_ranks(nranks, lambda ctx, comm: mc.run_checks(pkg, ctx, comm, exp))
+    results, info = pkg.run_virtual_ranks(nranks, lambda ctx, comm: mc.run_checks(pkg, ctx, comm, exp, only=SECTIONS))
     assert info["nranks"] == nranks
     for r in results[1:]:
         assert r == results[0]  # every rank reports the same eigenvalues, bit for bit
@@ -46,7 +53,7 @@ def test_virtual_ranks_match_restatement(nranks):
 
 def test_virtual_ranks_match_the_reference_itself():
     exp = _expected("reference")
-    results, _ = pkg.run_virtual_ranks(4, lambda ctx, comm: mc.run_checks(pkg, ctx, comm, exp))
+    results, _ = pkg.run_virtual_ranks(4, lambda ctx, comm: mc.run_checks(pkg, ctx, comm, exp, only=SECTIONS))
     assert all(r == results[0] for r in results)
 
 
