@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcmpt_b200.so")
 
 CMB_F64, CMB_C64 = 0, 1
-CMBS_LANCZOS, CMBS_ARNOLDI, CMBS_THICK_RESTART = 0, 1, 2
+CMBS_LANCZOS, CMBS_ARNOLDI, CMBS_THICK_RESTART, CMBS_THICK_RESTART_ARNOLDI = 0, 1, 2, 3
 CMB_OK = 0
 CMB_ERR_NO_DEVICE = -6
 STEP_OK, STEP_BREAKDOWN, STEP_NOSTART, STEP_FULL = 0, 1, 2, 4
@@ -91,6 +91,7 @@ def _declare(L):
         "cmb_lanczos_run": (i32, [vp, vp, dbl, i64, dbl, i64, vp, vp, P(i64), P(i32)]),
         "cmb_lanczos_residual_norm": (i32, [vp, P(dbl)]),
         "cmb_lanczos_thick_restart": (i32, [vp, P(dbl), i64, i64, i64]),
+        "cmb_arnoldi_thick_restart": (i32, [vp, vp, i64, i64, i64]),
         "cmb_arnoldi_run": (i32, [vp, vp, vp, dbl, i64, vp, i64, vp, P(i64), P(i32)]),
         "cmb_arnoldi_step": (i32, [vp, vp, vp, dbl, vp, P(dbl), P(i32)]),
         "cmb_krylov_ritz_vectors": (i32, [vp, i32, vp, i64, i64, i64, vp, i64]),

@@ -721,6 +721,41 @@ int cmb_lanczos_thick_restart(cmb_krylov* K, const double* coef, int64_t ldc, in
   return CMB_OK;
 }
 
+// Thick restart of the Arnoldi iteration (Krylov-Schur style; Stewart, SIAM J. Matrix Anal. Appl. 23 (2001)).  State on
+// entry: Arnoldi vectors q_0..q_{m-1} (nk = m), w = the unnormalised residual vector of the last step with ||w|| =
+// residue.  coef is the m x nkeep matrix (column-major, leading dimension ldc, elements of the basis dtype) of an
+// orthonormal basis Z of the subspace to keep; the basis becomes Q Z (nkeep vectors), w and its norm stay, so the next
+// cmb_arnoldi_run step turns w into vector number nkeep and orthogonalises A q against the compressed basis.  The caller
+// keeps the projected matrix: Z^H H Z in the leading block and residue * Z(m-1, :) as row nkeep.
+int cmb_arnoldi_thick_restart(cmb_krylov* K, const void* coef, int64_t ldc, int64_t m, int64_t nkeep) {
+  CMB_REQUIRE(K && coef, "null argument");
+  CMB_REQUIRE(m >= 1 && m == K->nk && nkeep >= 1 && nkeep <= m && ldc >= m, "bad shape for a thick restart");
+  cmb_ctx* ctx = K->ctx;
+  CMB_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->dead) return check_peer_wait(ctx);
+  CMB_TRY(ensure_cols(K, K->ndefl + int(m) + int(nkeep)));  // scratch columns behind the basis
+  std::vector<Chunk> chunks;
+  contiguous_chunks(K, K->ndefl, K->ndefl + int(m), chunks);
+  const int es = K->es;
+  CMB_TRY(ensure_stage(K, size_t(nkeep) * size_t(m) * es + 8));
+  const double* cf = static_cast<const double*>(coef);
+  // the device scalars of the pending residual vector must survive the assembly passes (they use scal[1] only)
+  for (int64_t i = 0; i < nkeep; ++i) {
+    double* hs = K->h_stage + size_t(i) * size_t(m) * es;
+    for (int64_t r = 0; r < m * es; ++r) hs[r] = -cf[size_t(i) * ldc * es + r];  // y = 0 - V (-z_i)
+    CMB_CUDA(cudaMemcpyAsync(K->h1, hs, sizeof(double) * m * es, cudaMemcpyHostToDevice, ctx->stream));
+    CMB_TRY(subtract_cols(K, chunks, K->h1, nullptr, K->col(K->ndefl + int(m) + int(i)), K->scal + 1, "ritz_assemble"));
+    K->bytes += (double(m) + 1.0) * double(K->n_local) * (K->cplx ? 16.0 : 8.0);
+  }
+  const size_t colbytes = sizeof(double) * size_t(K->ld);
+  for (int64_t i = 0; i < nkeep; ++i)
+    CMB_CUDA(cudaMemcpyAsync(K->col(K->ndefl + int(i)), K->col(K->ndefl + int(m) + int(i)), colbytes, cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+  K->nk = int(nkeep);
+  CMB_CUDA(cudaStreamSynchronize(ctx->stream));  // the staging slices are reused by the next call
+  return CMB_OK;
+}
+
 int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double threshold, int64_t nsteps, void* hcols,
                     int64_t ldh, double* residues, int64_t* steps_done, int* status) {
   CMB_TRY(check_pair(K, op));

@@ -7,6 +7,7 @@
 
 #include "cmpt/eigen_ex/arnoldi.hpp"
 #include "cmpt/eigen_ex/lanczos.hpp"
+#include "cmpt/eigen_ex/arnoldi_restart.hpp"
 #include "cmpt/eigen_ex/thick_restart.hpp"
 #include "cmpt/eigen_ex/detail/symmetric_eigen.hpp"
 #include "cmpt_b200_solver.h"
@@ -380,6 +381,114 @@ struct ThickS : cmbs_solver {
   double bytes() override { return es.deviceBytes(); }
 };
 
+// ThickRestartArnoldi<Scalar> (additive solver, arnoldi_restart.hpp)
+template <class Scalar>
+struct ThickArnoldiS : cmbs_solver {
+  using Solver = ThickRestartArnoldi<Scalar>;
+  using Index = typename Solver::Index;
+  using C = std::complex<double>;
+  Solver es;
+  [[noreturn]] static void no(const char* what) {
+    throw LanczosException(std::string(what) + " is not available for the thick-restart Arnoldi solver");
+  }
+  void set_operator(cmb_op* op) override { es.setMatrixMultiplication(DeviceOperator<Scalar>::borrow(op)); }
+  void set_callback(int64_t n, cmb_matmul_fn fn, void* user) override {
+    es.setMatrixMultiplication([fn, user](const Scalar* in, Scalar* out) { fn(in, out, user); }, Index(n));
+  }
+  bool set_int(const std::string& k, int64_t v) override {
+    if (k == "wanted") es.setWanted(v);
+    else if (k == "maxBasis") es.setMaxBasis(v);
+    else if (k == "keep") es.setKeep(v);
+    else if (k == "maxRestarts") es.setMaxRestarts(v);
+    else if (k == "which") es.setWhich(static_cast<typename Solver::Which>(v));
+    else if (k == "computeEigenvectorsOn") es.setComputeEigenvectorsOn(v != 0);
+    else return false;
+    return true;
+  }
+  bool set_real(const std::string& k, double v) override {
+    if (k == "tolerance") es.setTolerance(v);
+    else if (k == "threshold") es.setThreshold(v);
+    else if (k == "eigenvalueShift") es.setEigenvalueShift(Scalar(v));
+    else return false;
+    return true;
+  }
+  bool set_complex(const std::string& k, double re, double im) override {
+    if (k != "eigenvalueShift") return false;
+    es.setEigenvalueShift(make_shift(re, im, static_cast<Scalar*>(nullptr)));
+    return true;
+  }
+  static double make_shift(double re, double, double*) { return re; }
+  static C make_shift(double re, double im, C*) { return C(re, im); }
+  bool get_int(const std::string& k, int64_t* v) override {
+    if (k == "wanted") *v = es.wanted();
+    else if (k == "maxBasis") *v = es.maxBasis();
+    else if (k == "keep") *v = es.keep();
+    else if (k == "maxRestarts") *v = es.maxRestarts();
+    else if (k == "restarts") *v = es.restarts();
+    else if (k == "operatorApplications" || k == "iterations") *v = es.operatorApplications();
+    else if (k == "converged") *v = es.converged();
+    else if (k == "neigenvalues") *v = es.eigenvalues().size();
+    else if (k == "nlog") *v = int64_t(es.log().size());
+    else if (k == "nvectors") *v = es.arnoldiBase().arnoldivectorsSize();
+    else if (k == "matrixHeight") *v = es.arnoldiBase().matrixHeight();
+    else if (k == "localHeight") *v = es.localHeight();
+    else if (k == "hasWARN" || k == "hasERROR") {
+      const std::string head = (k == "hasWARN") ? Solver::headWARN() : std::string("ERROR     ");
+      int64_t c = 0;
+      for (const auto& l : es.log()) c += (l.find(head) == 0);
+      *v = c;
+    } else return false;
+    return true;
+  }
+  bool get_real(const std::string& k, double* v) override {
+    if (k == "tolerance") *v = es.tolerance();
+    else return false;
+    return true;
+  }
+  void set_indices(const int64_t*, int64_t) override { no("indicesForConvergence"); }
+  void set_initial(const void* v, int64_t n) override {
+    if (n == 0) {
+      es.setInitialVector();
+      return;
+    }
+    typename Solver::VectorType x(n);
+    memcpy(x.data(), v, sizeof(Scalar) * size_t(n));
+    es.setInitialVector(x);
+  }
+  void set_ortho(int64_t nvec, const void* vecs, int64_t ld) override {
+    std::vector<typename Solver::VectorType> o;
+    const Scalar* p = static_cast<const Scalar*>(vecs);
+    const Index n = es.localHeight();
+    for (int64_t j = 0; j < nvec; ++j) {
+      typename Solver::VectorType x(n);
+      memcpy(x.data(), p + size_t(j) * ld, sizeof(Scalar) * size_t(n));
+      o.push_back(std::move(x));
+    }
+    es.setOrthogonalizingVectors(o);
+  }
+  void compute() override { es.compute(); }
+  void continue_compute() override { no("continueToCompute"); }
+  void clear() override { es = Solver(); }
+  void clear_computed() override { no("clearComputedData"); }
+  void eigenvalues(void* out) override {
+    C* o = static_cast<C*>(out);
+    for (Index i = 0; i < Index(es.eigenvalues().size()); ++i) o[i] = es.eigenvalues()[i];
+  }
+  void eigenvectors_ptr(const void** p, int64_t* r, int64_t* c) override {
+    *p = es.eigenvectors().data();
+    *r = es.eigenvectors().rows();
+    *c = es.eigenvectors().cols();
+  }
+  void residuals(double* out) override {
+    for (Index i = 0; i < Index(es.residuals().size()); ++i) out[i] = es.residuals()[i];
+  }
+  void small_vectors(void*, int64_t*, int64_t*) override { no("the projected eigenvectors"); }
+  void basis_vector(int64_t, void*) override { no("basis vectors"); }
+  const std::vector<std::string>& log() override { return es.log(); }
+  void conv_log(int64_t, void*, int64_t* n) override { *n = 0; }
+  double bytes() override { return es.deviceBytes(); }
+};
+
 template <class F>
 int guarded(F&& f) {
   try {
@@ -416,6 +525,8 @@ int cmbs_create(int kind, cmb_dtype dtype, cmbs_solver** out) {
     else if (kind == CMBS_ARNOLDI && dtype == CMB_C64) s = new ArnoldiS<std::complex<double>>();
     else if (kind == CMBS_THICK_RESTART && dtype == CMB_F64) s = new ThickS<double>();
     else if (kind == CMBS_THICK_RESTART && dtype == CMB_C64) s = new ThickS<std::complex<double>>();
+    else if (kind == CMBS_THICK_RESTART_ARNOLDI && dtype == CMB_F64) s = new ThickArnoldiS<double>();
+    else if (kind == CMBS_THICK_RESTART_ARNOLDI && dtype == CMB_C64) s = new ThickArnoldiS<std::complex<double>>();
     S_REQ(s, "unknown solver kind / dtype");
     s->kind = kind;
     s->dtype = dtype;

@@ -326,7 +326,7 @@ class _Solver:
         return self._setr("threshold", v)
 
     def setEigenvalueShift(self, v):
-        if isinstance(v, complex) and self.kind == capi.CMBS_ARNOLDI:
+        if isinstance(v, complex) and self.kind in (capi.CMBS_ARNOLDI, capi.CMBS_THICK_RESTART_ARNOLDI):
             check(lib().cmbs_set_complex(self.h, b"eigenvalueShift", v.real, v.imag))
             return self
         return self._setr("eigenvalueShift", float(np.real(v)))
@@ -527,6 +527,27 @@ class ThickRestartLanczos(_Solver):
 
     def converged(self):
         return self._geti("converged")
+
+
+class ThickRestartArnoldi(ThickRestartLanczos):
+    """cmpt::EigenEx::ThickRestartArnoldi<Scalar> (include/cmpt/eigen_ex/arnoldi_restart.hpp; additive, Krylov-Schur):
+    the `wanted` eigenpairs of a general operator with at most `maxBasis` Arnoldi vectors on the device.  Eigenvalues and
+    eigenvectors are complex for both Scalars."""
+
+    kind = capi.CMBS_THICK_RESTART_ARNOLDI
+    LARGEST_MAGNITUDE, LARGEST_REAL, SMALLEST_REAL = 0, 1, 2
+
+    def _vec_dtype(self):
+        return np.complex128
+
+    def setWhich(self, v):
+        return self._seti("which", v)
+
+    def eigenvalues(self):
+        out = np.empty(self._geti("neigenvalues"), dtype=np.complex128)
+        if out.size:
+            check(lib().cmbs_get_eigenvalues(self.h, ptr(out)))
+        return out
 
 
 class ArnoldiEigenSolver(_Solver):

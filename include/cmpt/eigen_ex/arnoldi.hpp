@@ -189,6 +189,7 @@ class ArnoldiBase {
   mutable std::vector<VectorType> arnoldivectors_;  // host cache, filled on demand
   RealScalar residue_;
   std::vector<std::vector<Scalar>> h_;
+  Index restartedAt_ = -1;  // > 0 after thickRestart(k): column k-1 of h_ already holds its full (k+1)-entry column
   detail::KrylovDevice<Scalar> dev_;
 
  public:
@@ -228,6 +229,7 @@ class ArnoldiBase {
     arnoldivectors_.clear();
     h_.clear();
     residue_ = 0;
+    restartedAt_ = -1;
     if (dev_.ready()) detail::check(cmb_krylov_clear(dev_.handle()), "cmb_krylov_clear");
   }
 
@@ -280,7 +282,7 @@ class ArnoldiBase {
     detail::check(rc, "cmb_arnoldi_run");
     for (Index s = 0; s < static_cast<Index>(done); ++s) {
       const Index k = k0 + s;
-      if (k > 0) {
+      if (k > 0 && k != restartedAt_) {
         h_[k - 1].resize(k + 1);
         h_[k - 1][k] = Scalar(residue_);  // sub-diagonal entry of the previous column (arnoldi.hpp:362-363)
       }
@@ -292,6 +294,29 @@ class ArnoldiBase {
       ++iterations_;
     }
     return static_cast<Index>(done);
+  }
+
+  /// additive (thick restart, Krylov-Schur style; arnoldi_restart.hpp): with m = arnoldivectorsSize() vectors and the
+  /// residual of the last step pending, replace the basis by Q Z, where Z (m x k, column-major in coef) is an orthonormal
+  /// basis of an invariant subspace of the projected matrix H.  The projected matrix becomes [T ; b^T] in its first k
+  /// columns (T = Z^H H Z supplied by the caller column-major in t, b_j = residue * Z(m-1, j) in b); the next
+  /// updateArnoldiSteps() continues from the pending residual vector, which becomes vector number k.
+  void thickRestart(const std::vector<Scalar>& coef, Index k, const std::vector<Scalar>& t, const std::vector<Scalar>& b) {
+    const Index m = nvectors_;
+    if (m < 1 || k < 1 || k > m || static_cast<Index>(coef.size()) != m * k || static_cast<Index>(t.size()) != k * k ||
+        static_cast<Index>(b.size()) != k)
+      throw ArnoldiException("thickRestart: bad shapes");
+    detail::check(cmb_arnoldi_thick_restart(dev_.handle(), coef.data(), m, m, k), "cmb_arnoldi_thick_restart");
+    h_.assign(static_cast<std::size_t>(k), std::vector<Scalar>());
+    for (Index c = 0; c < k; ++c) {
+      std::vector<Scalar>& col = h_[static_cast<std::size_t>(c)];
+      col.resize(static_cast<std::size_t>(k) + 1);
+      for (Index r = 0; r < k; ++r) col[static_cast<std::size_t>(r)] = t[static_cast<std::size_t>(c) * k + r];
+      col[static_cast<std::size_t>(k)] = b[static_cast<std::size_t>(c)];
+    }
+    nvectors_ = k;
+    restartedAt_ = k;
+    arnoldivectors_.clear();
   }
 
   /// dense copy of the basis, n x (number of Hessenberg columns) (arnoldi.hpp:398-409)

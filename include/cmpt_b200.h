@@ -156,6 +156,13 @@ int cmb_lanczos_residual_norm(cmb_krylov* k, double* out);
  * cmb_lanczos_run step continues from u_m (full reorthogonalisation only). */
 int cmb_lanczos_thick_restart(cmb_krylov* k, const double* coef, int64_t ldc, int64_t m, int64_t nkeep);
 
+/* Thick restart of the Arnoldi iteration (additive; Krylov-Schur, Stewart 2001).  With Arnoldi vectors q_0..q_{m-1} on
+ * the device and the residual vector of the last step pending, replaces the basis by Q coef: coef is the m x nkeep
+ * (column-major, leading dimension ldc, elements of the basis dtype) orthonormal basis of the subspace of the projected
+ * matrix to keep.  The residual vector and its norm stay, so the next cmb_arnoldi_run step continues from it; the caller
+ * keeps the projected matrix (coef^H H coef in the leading block, residue * coef(m-1, :) as row nkeep). */
+int cmb_arnoldi_thick_restart(cmb_krylov* k, const void* coef, int64_t ldc, int64_t m, int64_t nkeep);
+
 /* updateArnoldiSteps() (arnoldi.hpp:312-392).  hcol receives h(0..ncols-1, ncols-1) of the new column
  * (dtype elements); *residue the new residual norm.  shift points at one dtype element. */
 int cmb_arnoldi_step(cmb_krylov* k, cmb_op* op, const void* shift, double threshold, void* hcol,

@@ -24,7 +24,12 @@ extern "C" {
 #endif
 
 typedef struct cmbs_solver cmbs_solver;
-enum { CMBS_LANCZOS = 0, CMBS_ARNOLDI = 1, CMBS_THICK_RESTART = 2 /* additive: ThickRestartLanczos */ };
+enum {
+  CMBS_LANCZOS = 0,
+  CMBS_ARNOLDI = 1,
+  CMBS_THICK_RESTART = 2,         /* additive: ThickRestartLanczos (thick_restart.hpp) */
+  CMBS_THICK_RESTART_ARNOLDI = 3  /* additive: ThickRestartArnoldi (arnoldi_restart.hpp); integer setting "which": 0 largest |lambda|, 1 largest real, 2 smallest real */
+};
 
 int cmbs_create(int kind, cmb_dtype dtype, cmbs_solver** out);
 int cmbs_destroy(cmbs_solver* s);
