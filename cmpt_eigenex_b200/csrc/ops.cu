@@ -7,6 +7,9 @@
 //   - matrix-free spin-1/2 Heisenberg chain (cfg 5): heisenberg.cu;
 //   - legacy host callback (reference signature), staged through pinned host memory.
 // All are HBM-bound; algorithmic bytes per apply are recorded in cmb_op::bytes.
+#include <chrono>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -620,6 +623,17 @@ int cmb_op_csr_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t r
   op_common(op, ctx, dtype, n_global, row_begin, row_end);
   op->family = "spmv_sell";
   int rc = CMB_OK;
+  // CMPT_B200_TRACE=1: wall-clock time of the build phases on stderr (each phase ends with a stream synchronisation)
+  static const bool trace = getenv("CMPT_B200_TRACE") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = trace ? now() : 0.0;
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(ctx->stream);
+    const double t1 = now();
+    fprintf(stderr, "[cmpt_b200 rank %d] csr_create %-14s %8.3f ms\n", ctx->rank, what, t1 - t0);
+    t0 = t1;
+  };
   if (ctx->nranks > 1) {
     // row-partitioned shard: the uniform partition of SURVEY.md §8(e) is required
     if (row_begin != partition_begin(n_global, ctx->nranks, ctx->rank) ||
@@ -633,15 +647,21 @@ int cmb_op_csr_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t r
     std::vector<int32_t> col_local(size_t(std::max<int64_t>(rowptr[n], 1)));
     std::vector<int32_t> halo_cols;
     std::vector<int64_t> per_owner;
+    lap("alloc");
     rc = plan_halo(n_global, ctx->nranks, ctx->rank, rowptr[n], col, col_local.data(), halo_cols, per_owner);
+    lap("plan_halo");
     if (rc == CMB_OK) {
       op->halo = new (std::nothrow) HaloExchange();
       rc = op->halo ? op->halo->setup(ctx, n_global, op->cplx ? 2 : 1, halo_cols, per_owner) : CMB_ERR_NOMEM;
     }
+    lap("halo_setup");
     if (rc == CMB_OK) rc = build_sell(op, rowptr, col_local.data(), val, n + int64_t(halo_cols.size()));
+    lap("build_sell");
     if (rc == CMB_OK && op->halo->p2p) rc = build_slice_order(op);
+    lap("slice_order");
   } else {
     rc = build_sell(op, rowptr, col, val, n_global);
+    lap("build_sell");
   }
   if (rc != CMB_OK) {
     delete op;
