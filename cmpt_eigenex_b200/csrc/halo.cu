@@ -8,6 +8,8 @@
 // and, after the owners learn what each peer needs, per apply:
 //   pack (gather owned w entries into one contiguous send buffer)  ->  ncclGroup{Send,Recv per peer}  ->  SpMV.
 // The values exchanged are the un-normalised w; 1/beta is a global scalar applied inside the SpMV.
+#include <string.h>
+
 #include <algorithm>
 #include <thread>
 
@@ -84,6 +86,163 @@ int plan_halo(int64_t n, int P, int rank, int64_t nnz, const int32_t* col, int32
     for (auto& t : th) t.join();
   }
   return CMB_OK;
+}
+
+// ---- the same plan on the device -----------------------------------------------------------------------------
+// The host version above costs a 4-byte-per-non-zero host array (allocated, page-faulted, filled, uploaded from
+// pageable memory): ~70 ms per 42 M non-zeros.  On the device the distinct remote columns are a bitmap over the global
+// column range; a popcount prefix over its words gives every remote column its rank in sorted order, i.e. its position
+// in the halo, without sorting.
+__global__ void halo_mark_kernel(const int* __restrict__ col, long long nnz, long long r0, long long r1, long long n,
+                                 unsigned* __restrict__ bitmap, int* __restrict__ bad) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+    const long long c = col[i];
+    if (c < 0 || c >= n) {
+      *bad = 1;
+    } else if (c < r0 || c >= r1) {
+      const unsigned bit = 1u << (c & 31);
+      unsigned* w = bitmap + (c >> 5);
+      if (!(__ldg(w) & bit)) atomicOr(w, bit);  // most marks repeat: test first
+    }
+  }
+}
+// popcount of every bitmap word; block sums for the two-level exclusive scan
+__global__ void halo_count_kernel(const unsigned* __restrict__ bitmap, long long nwords, unsigned* __restrict__ cnt,
+                                  unsigned long long* __restrict__ block_sum) {
+  __shared__ unsigned s[1024 / 32];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned c = i < nwords ? __popc(bitmap[i]) : 0u;
+  if (i < nwords) cnt[i] = c;
+  unsigned v = c;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned t = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) block_sum[blockIdx.x] = t;
+  }
+}
+// exclusive prefix of the block sums (one block; the number of blocks is nwords / 1024, a few hundred)
+__global__ void halo_scan_blocks_kernel(unsigned long long* __restrict__ block_sum, int nblocks, unsigned long long* total) {
+  if (threadIdx.x == 0) {
+    unsigned long long acc = 0;
+    for (int b = 0; b < nblocks; ++b) {
+      const unsigned long long v = block_sum[b];
+      block_sum[b] = acc;
+      acc += v;
+    }
+    *total = acc;
+  }
+}
+// prefix[i] = number of marked columns in words [0, i)
+__global__ void halo_prefix_kernel(const unsigned* __restrict__ cnt, long long nwords, const unsigned long long* __restrict__ block_off,
+                                   unsigned* __restrict__ prefix) {
+  __shared__ unsigned s[1024];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  s[threadIdx.x] = i < nwords ? cnt[i] : 0u;
+  __syncthreads();
+  // inclusive Hillis-Steele scan over the block
+  for (int o = 1; o < int(blockDim.x); o <<= 1) {
+    const unsigned add = threadIdx.x >= unsigned(o) ? s[threadIdx.x - o] : 0u;
+    __syncthreads();
+    s[threadIdx.x] += add;
+    __syncthreads();
+  }
+  if (i < nwords) prefix[i] = unsigned(block_off[blockIdx.x]) + s[threadIdx.x] - cnt[i];
+}
+__global__ void halo_remap_kernel(int* __restrict__ col, long long nnz, long long r0, long long r1, const unsigned* __restrict__ bitmap,
+                                  const unsigned* __restrict__ prefix) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long nloc = r1 - r0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+    const long long c = col[i];
+    if (c >= r0 && c < r1) {
+      col[i] = int(c - r0);
+    } else {
+      const unsigned w = __ldg(bitmap + (c >> 5));
+      col[i] = int(nloc + prefix[c >> 5] + __popc(w & ((1u << (c & 31)) - 1u)));
+    }
+  }
+}
+__global__ void halo_expand_kernel(const unsigned* __restrict__ bitmap, long long nwords, const unsigned* __restrict__ prefix,
+                                   int* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nwords) return;
+  unsigned w = bitmap[i];
+  unsigned pos = prefix[i];
+  while (w) {
+    const int b = __ffs(w) - 1;
+    out[pos++] = int(i * 32 + b);
+    w &= w - 1;
+  }
+}
+
+int plan_halo_device(cmb_ctx* ctx, int64_t n, int P, int rank, int64_t nnz, int32_t* d_col, std::vector<int32_t>& halo_cols,
+                     std::vector<int64_t>& per_owner) {
+  const int64_t r0 = partition_begin(n, P, rank), r1 = partition_begin(n, P, rank + 1);
+  const long long nwords = (n + 31) / 32;
+  const int nblocks = int((nwords + 1023) / 1024);
+  unsigned *d_bitmap = nullptr, *d_cnt = nullptr, *d_prefix = nullptr;
+  unsigned long long* d_bsum = nullptr;  // [nblocks] block offsets, [nblocks] total, [nblocks + 1] bad flag
+  int* d_halo = nullptr;
+  auto cleanup = [&]() {
+    pool_free(ctx, d_bitmap);
+    pool_free(ctx, d_cnt);
+    pool_free(ctx, d_prefix);
+    pool_free(ctx, d_bsum);
+    pool_free(ctx, d_halo);
+  };
+  int rc = [&]() -> int {
+    CMB_TRY(pool_alloc(ctx, &d_bitmap, sizeof(unsigned) * size_t(nwords)));
+    CMB_TRY(pool_alloc(ctx, &d_cnt, sizeof(unsigned) * size_t(nwords)));
+    CMB_TRY(pool_alloc(ctx, &d_prefix, sizeof(unsigned) * size_t(nwords)));
+    CMB_TRY(pool_alloc(ctx, &d_bsum, sizeof(unsigned long long) * size_t(nblocks + 2)));
+    CMB_CUDA(cudaMemsetAsync(d_bitmap, 0, sizeof(unsigned) * size_t(nwords), ctx->stream));
+    CMB_CUDA(cudaMemsetAsync(d_bsum, 0, sizeof(unsigned long long) * size_t(nblocks + 2), ctx->stream));
+    int* d_bad = reinterpret_cast<int*>(d_bsum + nblocks + 1);
+    const int grid = int(std::max<int64_t>(1, std::min<int64_t>((nnz + 255) / 256, int64_t(ctx->num_sms) * 16)));
+    {
+      LaunchScope ls(ctx, "halo_plan");
+      halo_mark_kernel<<<grid, 256, 0, ctx->stream>>>(d_col, nnz, r0, r1, n, d_bitmap, d_bad);
+      halo_count_kernel<<<nblocks, 1024, 0, ctx->stream>>>(d_bitmap, nwords, d_cnt, d_bsum);
+      halo_scan_blocks_kernel<<<1, 32, 0, ctx->stream>>>(d_bsum, nblocks, d_bsum + nblocks);
+      halo_prefix_kernel<<<nblocks, 1024, 0, ctx->stream>>>(d_cnt, nwords, d_bsum, d_prefix);
+    }
+    CMB_CUDA(cudaGetLastError());
+    unsigned long long tail[2] = {0, 0};
+    CMB_TRY(d2h_sync(ctx, tail, d_bsum + nblocks, sizeof(tail)));
+    int bad = 0;
+    memcpy(&bad, &tail[1], sizeof(int));
+    if (bad) {
+      set_error("column index out of range [0,%lld)", (long long)n);
+      return CMB_ERR_INVALID;
+    }
+    const int64_t nhalo = int64_t(tail[0]);
+    halo_cols.resize(size_t(nhalo));
+    CMB_TRY(pool_alloc(ctx, &d_halo, sizeof(int) * size_t(std::max<int64_t>(nhalo, 1))));
+    {
+      LaunchScope ls(ctx, "halo_plan");
+      halo_remap_kernel<<<grid, 256, 0, ctx->stream>>>(d_col, nnz, r0, r1, d_bitmap, d_prefix);
+      halo_expand_kernel<<<nblocks, 1024, 0, ctx->stream>>>(d_bitmap, nwords, d_prefix, d_halo);
+    }
+    CMB_CUDA(cudaGetLastError());
+    if (nhalo) CMB_TRY(d2h_sync(ctx, halo_cols.data(), d_halo, sizeof(int) * size_t(nhalo)));
+    else CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // owners are ranges of the sorted list
+    per_owner.assign(P, 0);
+    for (int q = 0; q < P; ++q) {
+      const auto lo = std::lower_bound(halo_cols.begin(), halo_cols.end(), int32_t(partition_begin(n, P, q)));
+      const auto hi = std::lower_bound(halo_cols.begin(), halo_cols.end(), int32_t(std::min<int64_t>(partition_begin(n, P, q + 1), INT32_MAX)));
+      per_owner[q] = int64_t(hi - lo);
+    }
+    return CMB_OK;
+  }();
+  cleanup();
+  return rc;
 }
 
 // ---- NCCL helpers --------------------------------------------------------------------------------------

@@ -12,6 +12,10 @@ int64_t partition_begin(int64_t n, int P, int q);
 int plan_halo(int64_t n, int P, int rank, int64_t nnz, const int32_t* col, int32_t* col_local,
               std::vector<int32_t>& halo_cols, std::vector<int64_t>& per_owner);
 
+// the same plan computed on the device: d_col (nnz global column indices in HBM) is remapped in place
+int plan_halo_device(cmb_ctx* ctx, int64_t n, int P, int rank, int64_t nnz, int32_t* d_col, std::vector<int32_t>& halo_cols,
+                     std::vector<int64_t>& per_owner);
+
 struct HaloExchange {
   int P = 1, rank = 0, es = 1;
   int64_t nsend = 0, nrecv = 0;

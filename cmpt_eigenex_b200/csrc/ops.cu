@@ -352,36 +352,56 @@ struct SellOp : cmb_op {
   }
 };
 
-// ncols: number of valid column indices (n_global on a single rank, n_local + halo entries for a shard)
-static int build_sell(SellOp* op, const int64_t* rowptr, const int32_t* col, const void* val, long long ncols) {
+// The CSR arrays of a shard in HBM (stream-ordered pool allocations), as uploaded from the caller's host arrays.
+struct CsrOnDevice {
+  cmb_ctx* ctx = nullptr;
+  long long* rowptr = nullptr;
+  int* col = nullptr;
+  double* val = nullptr;
+  long long nnz = 0;
+  ~CsrOnDevice() {
+    if (!ctx) return;
+    pool_free(ctx, rowptr);
+    pool_free(ctx, col);
+    pool_free(ctx, val);
+  }
+};
+static int upload_csr(SellOp* op, const int64_t* rowptr, const int32_t* col, const void* val, CsrOnDevice& d) {
   cmb_ctx* ctx = op->ctx;
   const int es = op->cplx ? 2 : 1;
   const long long n = op->n_local;
-  const long long nnz = rowptr[n];
+  d.ctx = ctx;
+  d.nnz = rowptr[n];
+  CMB_TRY(pool_alloc(ctx, &d.rowptr, sizeof(long long) * (n + 1)));
+  CMB_TRY(pool_alloc(ctx, &d.col, sizeof(int) * std::max<long long>(d.nnz, 1)));
+  CMB_TRY(pool_alloc(ctx, &d.val, sizeof(double) * es * std::max<long long>(d.nnz, 1)));
+  CMB_CUDA(cudaMemcpyAsync(d.rowptr, rowptr, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CMB_CUDA(cudaMemcpyAsync(d.col, col, sizeof(int) * d.nnz, cudaMemcpyHostToDevice, ctx->stream));
+  CMB_CUDA(cudaMemcpyAsync(d.val, val, sizeof(double) * es * d.nnz, cudaMemcpyHostToDevice, ctx->stream));
+  return CMB_OK;
+}
+
+// ncols: number of valid column indices (n_global on a single rank, n_local + halo entries for a shard)
+static int build_sell(SellOp* op, const CsrOnDevice& csr, long long ncols) {
+  cmb_ctx* ctx = op->ctx;
+  const int es = op->cplx ? 2 : 1;
+  const long long n = op->n_local;
+  const long long nnz = csr.nnz;
   op->nnz = nnz;
   op->nslices = (n + 31) / 32;
-  long long* d_rowptr = nullptr;
-  int* d_ccol = nullptr;
-  double* d_cval = nullptr;
+  long long* d_rowptr = csr.rowptr;
+  int* d_ccol = csr.col;
+  double* d_cval = csr.val;
   int* d_width = nullptr;
   int* d_bad = nullptr;
   auto cleanup = [&]() {
-    pool_free(ctx, d_rowptr);
-    pool_free(ctx, d_ccol);
-    pool_free(ctx, d_cval);
     pool_free(ctx, d_width);
     pool_free(ctx, d_bad);
   };
   int rc = [&]() -> int {
-    CMB_TRY(pool_alloc(ctx, &d_rowptr, sizeof(long long) * (n + 1)));
-    CMB_TRY(pool_alloc(ctx, &d_ccol, sizeof(int) * std::max<long long>(nnz, 1)));
-    CMB_TRY(pool_alloc(ctx, &d_cval, sizeof(double) * es * std::max<long long>(nnz, 1)));
     CMB_TRY(pool_alloc(ctx, &d_width, sizeof(int) * std::max<long long>(op->nslices, 1)));
     CMB_TRY(pool_alloc(ctx, &d_bad, sizeof(int)));
     CMB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
-    CMB_CUDA(cudaMemcpyAsync(d_rowptr, rowptr, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
-    CMB_CUDA(cudaMemcpyAsync(d_ccol, col, sizeof(int) * nnz, cudaMemcpyHostToDevice, ctx->stream));
-    CMB_CUDA(cudaMemcpyAsync(d_cval, val, sizeof(double) * es * nnz, cudaMemcpyHostToDevice, ctx->stream));
     const int threads = 256;
     const long long nthreads = op->nslices * 32;
     const int grid = int((nthreads + threads - 1) / threads);
@@ -644,23 +664,35 @@ int cmb_op_csr_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t r
       delete op;
       return CMB_ERR_INVALID;
     }
-    std::vector<int32_t> col_local(size_t(std::max<int64_t>(rowptr[n], 1)));
+    // the shard goes to HBM as it is; the halo plan (distinct remote columns, remapped indices) is made there
     std::vector<int32_t> halo_cols;
     std::vector<int64_t> per_owner;
-    lap("alloc");
-    rc = plan_halo(n_global, ctx->nranks, ctx->rank, rowptr[n], col, col_local.data(), halo_cols, per_owner);
+    CsrOnDevice csr;
+    rc = upload_csr(op, rowptr, col, val, csr);
+    lap("upload");
+    if (rc == CMB_OK) rc = plan_halo_device(ctx, n_global, ctx->nranks, ctx->rank, csr.nnz, csr.col, halo_cols, per_owner);
     lap("plan_halo");
-    if (rc == CMB_OK) {
-      op->halo = new (std::nothrow) HaloExchange();
-      rc = op->halo ? op->halo->setup(ctx, n_global, op->cplx ? 2 : 1, halo_cols, per_owner) : CMB_ERR_NOMEM;
+    // the halo set-up is collective: every rank enters it, whatever its local outcome so far
+    op->halo = new (std::nothrow) HaloExchange();
+    if (rc == CMB_OK && !op->halo) rc = CMB_ERR_NOMEM;
+    if (rc != CMB_OK) {
+      halo_cols.clear();
+      per_owner.assign(ctx->nranks, 0);
+    }
+    if (op->halo) {
+      const int rs = op->halo->setup(ctx, n_global, op->cplx ? 2 : 1, halo_cols, per_owner);
+      if (rc == CMB_OK) rc = rs;
     }
     lap("halo_setup");
-    if (rc == CMB_OK) rc = build_sell(op, rowptr, col_local.data(), val, n + int64_t(halo_cols.size()));
+    if (rc == CMB_OK) rc = build_sell(op, csr, n + int64_t(halo_cols.size()));
     lap("build_sell");
     if (rc == CMB_OK && op->halo->p2p) rc = build_slice_order(op);
     lap("slice_order");
   } else {
-    rc = build_sell(op, rowptr, col, val, n_global);
+    CsrOnDevice csr;
+    rc = upload_csr(op, rowptr, col, val, csr);
+    lap("upload");
+    if (rc == CMB_OK) rc = build_sell(op, csr, n_global);
     lap("build_sell");
   }
   if (rc != CMB_OK) {
