@@ -71,6 +71,8 @@ def _declare(L):
         "cmb_debug_heisenberg_virtual": (i32, [vp, i32, i32, dbl, i32, i32, vp, vp]),
         "cmb_heisenberg_plan": (i32, [i32, i32, i32, i32, P(i32), P(i32), P(i32), P(i32), P(i32)]),
         "cmb_op_callback_create": (i32, [vp, i32, i64, MATMUL_FN, vp, P(vp)]),
+        "cmb_op_linear_create": (i32, [vp, i64, vp, vp, P(vp)]),
+        "cmb_op_product_create": (i32, [vp, vp, vp, P(vp)]),
         "cmb_op_destroy": (i32, [vp]),
         "cmb_op_context": (vp, [vp]),
         "cmb_op_row_begin": (i64, [vp]),

@@ -20,6 +20,8 @@
 // All vectors are double arrays of padded length ld (multiple of 512, pads are zero), a complex vector
 // being ld/2 interleaved (re,im) pairs; a lane always holds one double2 per column, i.e. one complex
 // element or two real rows.
+#include <algorithm>
+
 #include "common.cuh"
 #include "device_utils.cuh"
 #include "kernels.cuh"
@@ -44,7 +46,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x, double* __restrict__ y,
            const double* __restrict__ hin, double* __restrict__ hout, double* __restrict__ partial,
            unsigned* __restrict__ ticket, const int* __restrict__ halt, int ncols, int cg, int ntiles, int stages,
-           MailPull pull, MailPush push, int norm_trick, int* retry, int retry_tag, double norm_guard) {
+           MailPull pull, MailPush push, int norm_trick, int* retry, int retry_tag, double norm_guard,
+           const __grid_constant__ SlabPush slab) {
   using Cfg = CgsCfg<WC>;
   constexpr int T = Cfg::T, WR = Cfg::WR;
   constexpr int ES = CPLX ? 2 : 1;  // doubles per coefficient
@@ -187,7 +190,24 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
       }
       yv.x = xv.x - p.x;
       yv.y = xv.y - p.y;
-      if (gc == 0) *reinterpret_cast<double2*>(y + size_t(tile) * T + row) = yv;
+      if (gc == 0) {
+        *reinterpret_cast<double2*>(y + size_t(tile) * T + row) = yv;
+        if (MODE == 2 && slab.n > 0) {  // the same two doubles go to the partner ranks that need them (NVLink stores)
+          const long long e = (long long)tile * T + row;
+          if (e < slab.nd) {
+            for (int d = 0; d < slab.n; ++d) {
+              if (slab.kind[d] == 0) {
+                if (e >= slab.lo[d] && e < slab.hi[d]) *reinterpret_cast<double2*>(slab.dst[d] + (e - slab.lo[d])) = yv;
+              } else if (CPLX) {
+                const long long idx = e >> 1;  // this lane holds one complex element
+                if ((idx & 1) == slab.lo[d]) *reinterpret_cast<double2*>(slab.dst[d] + (idx >> 1) * 2) = yv;
+              } else {
+                slab.dst[d][e >> 1] = slab.lo[d] ? yv.y : yv.x;  // one of the lane's two real elements
+              }
+            }
+          }
+        }
+      }
     }
     if (MODE <= 1) {
 #pragma unroll
@@ -218,6 +238,19 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
     }
   }
 
+  // ===== slab push: the CTA that finishes last publishes the exchange in the partners' flags =====
+  if (MODE == 2 && slab.n > 0) {
+    __threadfence_system();
+    asm volatile("bar.sync 9, %0;" ::"r"(kConsumerWarps * 32) : "memory");
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(slab.ticket, 1u);
+      if (prev == gridDim.x - 1) {
+        *slab.ticket = 0u;
+        __threadfence_system();
+        for (int d = 0; d < slab.n; ++d) st_release_sys_u64(slab.flag[d], slab.seq);
+      }
+    }
+  }
   // ===== UPDATE_NORM without a reduction of its own (norm_trick): beta^2 from the reduced coefficients =====
   __shared__ double s_fin[2 * kConsumerWarps * 32 + 8];
   if (MODE == 2 && norm_trick) {
@@ -345,6 +378,45 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
   }
 }
 
+// Stand-alone slab push: the stores of the fused version without a Gram-Schmidt pass around them.
+__global__ void __launch_bounds__(256)
+slab_push_kernel(const double* __restrict__ w, const __grid_constant__ SlabPush slab, const int* __restrict__ halt) {
+  if (*halt) return;
+  const long long stride = (long long)gridDim.x * blockDim.x * 2;
+  for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; e < slab.nd; e += stride) {
+    const double2 yv = *reinterpret_cast<const double2*>(w + e);
+    for (int d = 0; d < slab.n; ++d) {
+      if (slab.kind[d] == 0) {
+        if (e >= slab.lo[d] && e < slab.hi[d]) *reinterpret_cast<double2*>(slab.dst[d] + (e - slab.lo[d])) = yv;
+      } else if (slab.es == 2) {
+        const long long idx = e >> 1;
+        if ((idx & 1) == slab.lo[d]) *reinterpret_cast<double2*>(slab.dst[d] + (idx >> 1) * 2) = yv;
+      } else {
+        slab.dst[d][e >> 1] = slab.lo[d] ? yv.y : yv.x;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(slab.ticket, 1u);
+    if (prev == gridDim.x - 1) {
+      *slab.ticket = 0u;
+      __threadfence_system();
+      for (int d = 0; d < slab.n; ++d) st_release_sys_u64(slab.flag[d], slab.seq);
+    }
+  }
+}
+
+int slab_push(cmb_ctx* ctx, const double* w, const SlabPush& slab, const int* halt) {
+  if (slab.n <= 0) return CMB_OK;
+  LaunchScope ls(ctx, "slab_push");
+  const int grid = int(std::max<long long>(1, std::min<long long>((slab.nd / 2 + 255) / 256, (long long)ctx->num_sms * 8)));
+  slab_push_kernel<<<grid, 256, 0, ctx->stream>>>(w, slab, halt);
+  CMB_CUDA(cudaGetLastError());
+  return CMB_OK;
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 template <int CG, int WC, bool CPLX, int MODE>
 static int launch_cfg(cmb_ctx* ctx, const CgsPass& a, int cg) {
@@ -387,7 +459,7 @@ static int launch_cfg(cmb_ctx* ctx, const CgsPass& a, int cg) {
     LaunchScope ls(ctx, a.family ? a.family : fam[MODE]);
     kern<<<grid, kThreads, smem, ctx->stream>>>(tm, a.x, a.y, a.hin, a.hout, ctx->d_partial, ctx->d_ticket, a.halt,
                                                 a.ncols, cg, ntiles, stages, a.pull, a.push, a.norm_trick, a.retry, a.retry_tag,
-                                                a.norm_guard);
+                                                a.norm_guard, a.slab);
   }
   CMB_CUDA(cudaGetLastError());
   return CMB_OK;

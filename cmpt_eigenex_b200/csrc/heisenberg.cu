@@ -403,6 +403,8 @@ struct HeisenbergOp : cmb_op {
   size_t p2p_tot = 0;                           // doubles per receive buffer of this rank
   std::vector<size_t> peer_off, peer_tot;       // per remote bond: where my slab goes in the partner's buffer / its size
   unsigned long long xseq = 0;                  // exchanges enqueued so far (same on every rank)
+  const double* pushed_w = nullptr;             // slab_push_begin(): the producer of this w pushes exchange pushed_x
+  unsigned long long pushed_x = 0;
   unsigned long long* h_seq = nullptr;          // pinned source words of the flag copies
   static constexpr int kMaxSplit = 4;            // a slab travels as up to 4 concurrent copies (one copy engine each)
   int nsplit = 2;
@@ -642,9 +644,78 @@ struct HeisenbergOp : cmb_op {
     return CMB_OK;
   }
 
+  // Destinations of this rank's slabs for the next exchange (see SlabPush, kernels.cuh): the kernel that writes w stores
+  // them through NVLink while it runs, so the exchange costs no time of its own.  Peer-memory exchange only.
+  bool slab_push_begin(const double* w, SlabPush* out) override {
+    if (plan.p == 0 || !p2p || getenv("CMPT_B200_NO_FUSED_SLAB")) return false;
+    const size_t es = cplx ? 2 : 1;
+    const size_t slab = size_t(n_local) * es, half = slab / 2;
+    const int rb0 = plan.rank & 1, rt = (plan.rank >> (plan.p - 1)) & 1;
+    const unsigned long long x = ++xseq;
+    const size_t par = size_t(x & 1ull);
+    SlabPush sp;
+    sp.es = int(es);
+    sp.nd = (long long)slab;
+    sp.seq = x;
+    sp.ticket = ctx->d_ticket + 3;
+    for (size_t k = 0; k < plan.remote.size(); ++k) {
+      const HeisRemote& r = plan.remote[k];
+      if (!r.needed) continue;
+      if (sp.n >= kMaxSlabDst) return false;
+      char* pbase = static_cast<char*>(p2p_mapped[r.partner]);
+      const int d = sp.n++;
+      sp.dst[d] = reinterpret_cast<double*>(pbase + kFlagBytes) + par * peer_tot[k] + peer_off[k];
+      sp.flag[d] = reinterpret_cast<unsigned long long*>(pbase) + k;
+      if (r.kind == 2) {  // straddle: the half whose top local bit differs from my rank bit 0
+        sp.kind[d] = 0;
+        sp.lo[d] = (long long)(size_t(1 - rb0) * half);
+        sp.hi[d] = sp.lo[d] + (long long)half;
+      } else if (r.kind == 3) {  // rank-rank bond: the whole slab
+        sp.kind[d] = 0;
+        sp.lo[d] = 0;
+        sp.hi[d] = (long long)slab;
+      } else {  // periodic wrap: the elements whose bit 0 differs from my top rank bit, packed
+        sp.kind[d] = 1;
+        sp.lo[d] = 1 - rt;
+        sp.hi[d] = 0;
+      }
+    }
+    pushed_w = w;
+    pushed_x = x;
+    *out = sp;
+    return true;
+  }
+  void slab_push_cancel() override { pushed_w = nullptr; }
+
   int apply(const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) override {
     HeisArgs a = base_args();
     if (plan.p > 0) {
+      if (p2p && pushed_w == w && pushed_w != nullptr) {
+        // the kernel that produced w has pushed the slabs and raised the flags of exchange pushed_x
+        pushed_w = nullptr;
+      if (p2p && (ctx->vgroup || getenv("CMPT_B200_SM_SLAB_PUSH"))) {
+        // virtual ranks (and on request): the exchange of this apply as SM stores from a stand-alone kernel in stream
+        // order — same destinations, flags and parity as the fused push
+        SlabPush sp;
+        if (slab_push_begin(w, &sp)) {
+          CMB_TRY(slab_push(ctx, w, sp, sc.halt));
+          return apply(w, ucol, v, shr, shi, sc);
+        }
+      }
+        unsigned mask = 0;
+        for (size_t k = 0; k < plan.remote.size(); ++k)
+          if (plan.remote[k].needed) mask |= 1u << k;
+        const size_t par = size_t(pushed_x & 1ull);
+        const double* recv = reinterpret_cast<const double*>(static_cast<char*>(p2p_base) + kFlagBytes) + par * p2p_tot;
+        remote_args(a, recv);
+        a.flag = static_cast<const unsigned long long*>(p2p_base);
+        a.seq = pushed_x;
+        a.flag_mask = mask;
+        a.error = ctx->d_mail_error;
+        a.timeout = ctx->spin_timeout;
+        return launch(a, w, ucol, v, shr, shi, sc);
+      }
+      pushed_w = nullptr;
       const size_t es = cplx ? 2 : 1;
       const size_t slab = size_t(n_local) * es, half = slab / 2;
       // what each partner needs from me: straddle -> my half whose top local bit != my rank bit 0 (the partner's

@@ -5,6 +5,23 @@
 namespace cmb {
 
 // ---- cgs.cu ------------------------------------------------------------------------------------------
+// Fused compute + exchange for the matrix-free Heisenberg operator: the UPDATE_NORM pass that produces the next
+// Krylov vector w also stores the parts of w its partner ranks need straight into their receive buffers (NVLink
+// stores), tile by tile while it streams the basis, and the CTA that finishes last raises the partners' flags.  The
+// operator apply that follows then finds its remote slabs in place instead of waiting for a copy-engine exchange.
+constexpr int kMaxSlabDst = 8;
+struct SlabPush {
+  int n = 0;                              // destinations
+  int es = 1;                             // doubles per element
+  long long nd = 0;                       // valid doubles of the local vector (the rest of ld is padding)
+  int kind[kMaxSlabDst];                  // 0: contiguous range of doubles [lo, hi)   1: every other element, parity lo
+  long long lo[kMaxSlabDst], hi[kMaxSlabDst];
+  double* dst[kMaxSlabDst];               // where double lo (kind 0) / packed element 0 (kind 1) goes in the peer's buffer
+  unsigned long long* flag[kMaxSlabDst];  // the peer's flag word of this bond
+  unsigned long long seq = 0;             // exchange number published in the flags
+  unsigned* ticket = nullptr;             // device counter of finished CTAs
+};
+
 struct CgsPass {
   const double* V = nullptr;  // first column of the chunk
   int64_t ld = 0;             // padded column length in doubles (multiple of 512)
@@ -29,8 +46,11 @@ struct CgsPass {
   int* retry = nullptr;
   int retry_tag = 0;
   double norm_guard = 1e-8;
+  SlabPush slab;  // UPDATE_NORM only: n > 0 pushes the output to peer ranks (see SlabPush)
 };
 enum { CGS_DOT = 0, CGS_UPDATE_DOT = 1, CGS_UPDATE_NORM = 2 };
+// stand-alone version of the slab push (the first apply of a run has no producing pass): w -> the peers' buffers
+int slab_push(cmb_ctx* ctx, const double* w, const SlabPush& slab, const int* halt);
 inline int cgs_max_cols(bool cplx) { return cplx ? 64 : 128; }
 int cgs_pass(cmb_ctx* ctx, bool cplx, int mode, const CgsPass& a);
 

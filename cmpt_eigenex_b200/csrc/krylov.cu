@@ -49,6 +49,7 @@ struct cmb_krylov {
   size_t h_stage_elems = 0;
   bool started = false;
   unsigned long long nrm2_seq = 0;  // non-zero: ||w||^2 is the mailbox reduction with this sequence number
+  bool w_pushed = false;            // the pass that wrote w also pushed it to the partner ranks (SlabPush)
   bool resume_norm_ready = false;   // w is orthogonalised and scal[0] holds its explicitly reduced norm (guard retry)
   double residue = 0.0;  // Arnoldi: last residual norm (host copy)
   double bytes = 0.0;
@@ -148,7 +149,7 @@ static int total_cols(const std::vector<Chunk>& ch) {
 // so no collective kernel runs in between.  *nrm2_seq receives the sequence number under which ||y||^2 will be
 // found by the consumer (the operator apply).
 static int gram_schmidt2_mailed(cmb_krylov* K, const Chunk& c, const double* x, double* y,
-                                unsigned long long* nrm2_seq, int retry_tag) {
+                                unsigned long long* nrm2_seq, int retry_tag, cmb_op* push_op = nullptr) {
   cmb_ctx* ctx = K->ctx;
   CgsPass p;
   p.ld = K->ld;
@@ -189,12 +190,13 @@ static int gram_schmidt2_mailed(cmb_krylov* K, const Chunk& c, const double* x, 
     p.push = mail_next_push(ctx);
     *nrm2_seq = p.push.seq;
   }
+  if (push_op && y == K->w && push_op->slab_push_begin(y, &p.slab)) K->w_pushed = true;  // this pass also pushes y to the partners
   CMB_TRY(cgs_pass(ctx, K->cplx, CGS_UPDATE_NORM, p));
   return CMB_OK;
 }
 
 static int gram_schmidt2(cmb_krylov* K, const std::vector<Chunk>& chunks, const double* x, double* y,
-                         double* nrm2_out) {
+                         double* nrm2_out, cmb_op* push_op = nullptr) {
   cmb_ctx* ctx = K->ctx;
   const int es = K->es;
   const int nch = int(chunks.size());
@@ -254,6 +256,7 @@ static int gram_schmidt2(cmb_krylov* K, const std::vector<Chunk>& chunks, const 
     p.y = y;
     p.hin = K->h2 + off * es;
     p.hout = (i == nch - 1) ? nrm2_out : K->scal + 1;
+    if (i == nch - 1 && push_op && y == K->w && push_op->slab_push_begin(y, &p.slab)) K->w_pushed = true;
     CMB_TRY(cgs_pass(ctx, K->cplx, CGS_UPDATE_NORM, p));
     off += chunks[i].ncols;
   }
@@ -285,6 +288,13 @@ static int subtract_cols(cmb_krylov* K, const std::vector<Chunk>& chunks, const 
   return CMB_OK;
 }
 
+// Operator apply on K->w.  A push announced for w is honoured only if the Krylov state says w still is what was pushed.
+static int apply_w(cmb_krylov* K, cmb_op* op, double* ucol, double shr, double shi, const StepScalars& sc) {
+  if (!K->w_pushed) op->slab_push_cancel();
+  K->w_pushed = false;
+  return op->apply(K->w, ucol, K->v, shr, shi, sc);
+}
+
 static void add_step_bytes(cmb_krylov* K, const cmb_op* op, int c) {
   // B_step(c) = B_op + (3c + 7) n s
   K->bytes += op->bytes + (3.0 * c + 7.0) * double(K->n_local) * (K->cplx ? 16.0 : 8.0);
@@ -300,7 +310,7 @@ static int check_pair(const cmb_krylov* K, const cmb_op* op) {
 }
 
 // Enqueue the orthogonalisation part of Lanczos step k (k = index of the newest Krylov vector).
-static int enqueue_lanczos_orth(cmb_krylov* K, int64_t interval, int retry_tag) {
+static int enqueue_lanczos_orth(cmb_krylov* K, int64_t interval, int retry_tag, cmb_op* push_op) {
   const int k = K->nk - 1;
   std::vector<Chunk> chunks;
   if (interval == 1) {
@@ -309,8 +319,8 @@ static int enqueue_lanczos_orth(cmb_krylov* K, int64_t interval, int retry_tag) 
     contiguous_chunks(K, 0, K->ndefl + k + 1, chunks);
     K->nrm2_seq = 0;
     if (K->ctx->mail_ok && chunks.size() == 1)
-      return gram_schmidt2_mailed(K, chunks[0], K->v, K->w, &K->nrm2_seq, retry_tag);
-    return gram_schmidt2(K, chunks, K->v, K->w, K->scal);
+      return gram_schmidt2_mailed(K, chunks[0], K->v, K->w, &K->nrm2_seq, retry_tag, push_op);
+    return gram_schmidt2(K, chunks, K->v, K->w, K->scal, push_op);
   }
   K->nrm2_seq = 0;
   // explicit recurrence w = v - alpha_k u_k - beta_{k-1} u_{k-1} (lanczos.hpp:402-408)
@@ -426,6 +436,7 @@ int cmb_krylov_clear(cmb_krylov* K) {
   K->nk = 0;
   K->started = false;
   K->nrm2_seq = 0;
+  K->w_pushed = false;
   K->residue = 0.0;
   K->bytes = 0.0;
   CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int) * 4, K->ctx->stream));
@@ -455,6 +466,7 @@ int cmb_krylov_start(cmb_krylov* K, const void* init, double threshold, int* sta
   K->nk = 0;
   K->started = false;
   K->nrm2_seq = 0;
+  K->w_pushed = false;
   K->residue = 0.0;
   CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int) * 4, ctx->stream));
   CMB_CUDA(cudaMemcpyAsync(K->w, init, sizeof(double) * K->nd_local, cudaMemcpyHostToDevice, ctx->stream));
@@ -517,7 +529,7 @@ int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, d
       sc.threshold = -1.0;
       sc.beta_slot = K->scal + 3;
       sc.alpha_slot = K->alpha_dev;
-      CMB_TRY(op->apply(K->w, K->col(K->ndefl), K->v, shift, 0.0, sc));
+      CMB_TRY(apply_w(K, op, K->col(K->ndefl), shift, 0.0, sc));
       if (interval != 1) CMB_TRY(allreduce_sum_f64(ctx, K->alpha_dev, 1));
       K->bytes += op->bytes + 3.0 * double(K->n_local) * (K->cplx ? 16.0 : 8.0);
       K->nk = 1;  // the first call cannot break down on the device side
@@ -533,7 +545,7 @@ int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, d
       K->resume_norm_ready = false;
       K->nrm2_seq = 0;
     } else {
-      rc = enqueue_lanczos_orth(K, interval, enq);
+      rc = enqueue_lanczos_orth(K, interval, enq, op);
     }
     const int c = orth_cols_count(K, interval);
     K->nk = nk_save;
@@ -545,7 +557,7 @@ int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, d
     }
     sc.beta_slot = K->beta_dev + k;
     sc.alpha_slot = K->alpha_dev + size_t(k + 1) * 2;
-    CMB_TRY(op->apply(K->w, K->col(K->ndefl + k + 1), K->v, shift, 0.0, sc));
+    CMB_TRY(apply_w(K, op, K->col(K->ndefl + k + 1), shift, 0.0, sc));
     // with full reorthogonalisation alpha is only read by the host: one allreduce for the whole chain (below)
     if (interval != 1) CMB_TRY(allreduce_sum_f64(ctx, K->alpha_dev + size_t(k + 1) * 2, 1));
     add_step_bytes(K, op, c);
@@ -568,6 +580,7 @@ int cmb_lanczos_run(cmb_krylov* K, cmb_op* op, double shift, int64_t interval, d
   CMB_TRY(check_peer_wait(ctx));
   int ok_steps = enq;
   bool guard_retry = false;
+  if (halted) K->w_pushed = false;  // pushes announced after the halt never ran
   if (halted) {
     int flags[3] = {0, 0, 0};
     CMB_TRY(d2h_sync(ctx, flags, K->halt, sizeof(flags)));
@@ -807,7 +820,7 @@ int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double thresho
     sc.beta_slot = K->scal + 3;
     sc.alpha_slot = K->scal + 4;
     // q_k = w / residue ; v = (A + shift) q_k        (arnoldi.hpp:361-372)
-    rc = op->apply(K->w, K->col(K->ndefl + k), K->v, shr, shi, sc);
+    rc = apply_w(K, op, K->col(K->ndefl + k), shr, shi, sc);
     if (rc != CMB_OK) break;
     // CGS2 of v against deflation vectors and q_0..q_k ; h(:,k) = h1 + h2 ; residue = ||w||   (:373-385)
     std::vector<Chunk> chunks;
@@ -817,9 +830,9 @@ int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double thresho
       // row-partitioned fast path: the coefficient reductions go through the peer-memory mailboxes (reduced h1, h2
       // are written back to K->h1 / K->h2, ||w||^2 to K->scal[0]) — no collective kernel inside the chain
       unsigned long long norm_seq = 0;  // stays 0 without deflation vectors: the norm is in K->scal[0]
-      rc = gram_schmidt2_mailed(K, chunks[0], K->v, K->w, &norm_seq, int(s));
+      rc = gram_schmidt2_mailed(K, chunks[0], K->v, K->w, &norm_seq, int(s), op);
     } else {
-      rc = gram_schmidt2(K, chunks, K->v, K->w, K->scal);
+      rc = gram_schmidt2(K, chunks, K->v, K->w, K->scal, op);
     }
     if (rc != CMB_OK) break;
     double* slot = hist + size_t(s) * (2 * hstride + 1);
@@ -848,6 +861,7 @@ int cmb_arnoldi_run(cmb_krylov* K, cmb_op* op, const void* shift, double thresho
   CMB_TRY(rc);
   CMB_TRY(check_peer_wait(ctx));
   int guard_step = -1;
+  if (halted) K->w_pushed = false;  // pushes announced after the halt never ran
   if (halted) {
     int flags[3] = {0, 0, 0};
     CMB_TRY(d2h_sync(ctx, flags, K->halt, sizeof(flags)));

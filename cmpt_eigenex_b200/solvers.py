@@ -206,6 +206,23 @@ class DeviceOperator:
         return DeviceOperator(ctx, h)
 
     @staticmethod
+    def linear(ctx, ops, coefs):
+        """sum_i coefs[i] * ops[i] as one operator that stays in HBM (cmb_op_linear_create); the terms must outlive it."""
+        dt = ops[0].dtype
+        c = np.ascontiguousarray(coefs, dtype=dt)
+        arr = (C.c_void_p * len(ops))(*[o.h for o in ops])
+        h = C.c_void_p()
+        check(lib().cmb_op_linear_create(ctx.h, len(ops), arr, ptr(c), C.byref(h)))
+        return DeviceOperator(ctx, h, keep=list(ops))
+
+    @staticmethod
+    def product(ctx, outer, inner):
+        """outer * inner (inner acts first) as one operator that stays in HBM (cmb_op_product_create)."""
+        h = C.c_void_p()
+        check(lib().cmb_op_product_create(ctx.h, outer.h, inner.h, C.byref(h)))
+        return DeviceOperator(ctx, h, keep=[outer, inner])
+
+    @staticmethod
     def from_callback(ctx, fn, n, dtype=np.float64):
         cb, code = _make_callback(fn, n, dtype)
         h = C.c_void_p()

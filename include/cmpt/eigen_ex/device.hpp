@@ -143,6 +143,31 @@ class DeviceOperator {
     return op;
   }
 
+  /// sum_i coefs[i] * ops[i] as one operator that stays in HBM (device-resident counterpart of VectorMap's operator+,
+  /// scalarMultiple: vector_map.hpp:207-245 of the reference); the terms are kept alive by the result
+  static DeviceOperator linear(const std::vector<DeviceOperator>& ops, const std::vector<Scalar>& coefs) {
+    if (ops.empty() || ops.size() != coefs.size()) throw LanczosException("DeviceOperator::linear: bad argument");
+    DeviceOperator op;
+    op.ctx_ = ops.front().ctx_;
+    std::vector<cmb_op*> raw;
+    for (const auto& o : ops) raw.push_back(o.get());
+    cmb_op* h = nullptr;
+    detail::check(cmb_op_linear_create(op.ctx_->get(), static_cast<std::int64_t>(raw.size()), raw.data(), coefs.data(), &h),
+                  "cmb_op_linear_create");
+    op.reset(h, ops);
+    return op;
+  }
+  /// outer * inner (inner acts first) as one operator that stays in HBM (vector_map.hpp:247-266 of the reference)
+  static DeviceOperator product(const DeviceOperator& outer, const DeviceOperator& inner) {
+    if (!outer || !inner) throw LanczosException("DeviceOperator::product: empty operand");
+    DeviceOperator op;
+    op.ctx_ = inner.ctx_;
+    cmb_op* h = nullptr;
+    detail::check(cmb_op_product_create(op.ctx_->get(), outer.get(), inner.get(), &h), "cmb_op_product_create");
+    op.reset(h, {outer, inner});
+    return op;
+  }
+
   /// non-owning view of an operator created through the C-ABI (the caller keeps it alive)
   static DeviceOperator borrow(cmb_op* h) {
     DeviceOperator op;
@@ -163,6 +188,14 @@ class DeviceOperator {
  private:
   void reset(cmb_op* h) {
     op_ = std::shared_ptr<cmb_op>(h, [](cmb_op* p) { cmb_op_destroy(p); });
+  }
+  // a composition holds its children: they are released after the composed operator is destroyed
+  void reset(cmb_op* h, const std::vector<DeviceOperator>& children) {
+    auto keep = std::make_shared<std::vector<DeviceOperator>>(children);
+    op_ = std::shared_ptr<cmb_op>(h, [keep](cmb_op* p) {
+      cmb_op_destroy(p);
+      keep->clear();
+    });
   }
   std::shared_ptr<DeviceContext> ctx_;
   std::shared_ptr<cmb_op> op_;

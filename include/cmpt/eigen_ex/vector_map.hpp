@@ -8,6 +8,12 @@
 // device operators can be fed to the solvers as well (each application then costs the host round trip of the
 // callback path; a single DeviceOperator should be handed to the solver directly).
 //
+// Device-resident algebra (additive): a map built with setFromDeviceOperator remembers the operator, and sums,
+// differences, scalar multiples and products of such maps compose the operators ON THE DEVICE (DeviceOperator::linear /
+// ::product, cmb_op_linear_create / cmb_op_product_create): hasDeviceOperator() is then true and
+// es.setMatrixMultiplication(vm.deviceOperator()) runs every Krylov step without touching the host.  As soon as a
+// host-only map takes part, the result falls back to the callback path.
+//
 // Independent implementation; the reference's quirks that are bugs are not reproduced: its composition size check
 // compares every map with itself (vector_map.hpp:78-88) and operator*= has no return statement (:261-263).
 #ifndef CMPT_EIGEN_EX_VECTOR_MAP_HPP_
@@ -20,6 +26,7 @@
 #include <vector>
 
 #include "detail/dense.hpp"
+#include "device.hpp"
 
 namespace cmpt {
 namespace EigenEx {
@@ -49,8 +56,14 @@ class VectorMap {
     function_ = func;
     sizeIn_ = size_in;
     sizeOut_ = size_out;
+    device_ = DeviceOperator<Scalar>();  // an arbitrary host function has no device form
     return *this;
   }
+
+  /// additive: true when the whole map is a composition of device operators
+  bool hasDeviceOperator() const { return static_cast<bool>(device_); }
+  /// additive: the map as one operator in HBM (empty when a host-only map takes part in it)
+  const DeviceOperator<Scalar>& deviceOperator() const { return device_; }
 
   /// the maps act in list order: out = vmaps.back()( ... vmaps.front()(in) ); an empty list is the 0 x 0 identity
   VectorMap& setFromComposition(const std::vector<VectorMap>& vmaps) {
@@ -103,6 +116,13 @@ class VectorMap {
     const Op held(op);
     return setFromFunction([held](Scalar const* in, Scalar* out) { held.apply(in, out); }, held.height(), held.height());
   }
+  /// the device operator is remembered, so that the algebra below can stay on the device
+  VectorMap& setFromDeviceOperator(const DeviceOperator<Scalar>& op) {
+    const DeviceOperator<Scalar> held(op);
+    setFromFunction([held](Scalar const* in, Scalar* out) { held.apply(in, out); }, held.height(), held.height());
+    device_ = held;
+    return *this;
+  }
 
   VectorType makeOperated(const VectorType& v_in) const {
     if (static_cast<Index>(v_in.size()) != sizeIn()) throw VectorMapException("makeOperated: v_in.size() != sizeIn()");
@@ -113,6 +133,15 @@ class VectorMap {
 
   /// appends x -> c x after the map; c == 0 replaces the map by the zero map (the inner map is no longer called)
   void scalarMultiple(const Scalar& c) {
+    const Index so = sizeOut();
+    const DeviceOperator<Scalar> dev = device_ ? DeviceOperator<Scalar>::linear({device_}, {c}) : DeviceOperator<Scalar>();
+    scalarMultipleHost_(c);
+    device_ = dev;
+    (void)so;
+  }
+
+ protected:
+  void scalarMultipleHost_(const Scalar& c) {
     const Index so = sizeOut();
     if (c == Scalar(0)) {
       setFromFunction(
@@ -130,6 +159,8 @@ class VectorMap {
         },
         sizeIn(), so);
   }
+
+ public:
   VectorMap scalarMultipled(const Scalar& c) const {
     VectorMap vm(*this);
     vm.scalarMultiple(c);
@@ -150,19 +181,26 @@ class VectorMap {
       g(in, t.data());
       for (Index i = 0; i < so; ++i) out[i] += t[static_cast<std::size_t>(i)];
     };
+    device_ = (device_ && other.device_) ? DeviceOperator<Scalar>::linear({device_, other.device_}, {Scalar(1), Scalar(1)})
+                                         : DeviceOperator<Scalar>();
     return *this;
   }
   VectorMap& operator-=(const VectorMap& other) { return *this += (-other); }
   /// (*this) <- (*this) o other, i.e. other acts first
   VectorMap& operator*=(const VectorMap& other) {
     const VectorMap self(*this);
-    return setFromComposition({other, self});
+    const DeviceOperator<Scalar> dev = (self.device_ && other.device_) ? DeviceOperator<Scalar>::product(self.device_, other.device_)
+                                                                        : DeviceOperator<Scalar>();
+    setFromComposition({other, self});
+    device_ = dev;
+    return *this;
   }
 
  protected:
   FunctionType function_;
   Index sizeIn_;
   Index sizeOut_;
+  DeviceOperator<Scalar> device_;  // non-empty: the whole map as one operator in HBM
 };
 
 template <class S>

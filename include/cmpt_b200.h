@@ -106,6 +106,11 @@ int cmb_heisenberg_plan(int L, int pbc, int nranks, int rank, int* kind, int* pa
  * slabs (single-rank contexts only).  Costs one D2H + one H2D of an n-vector per Krylov step. */
 typedef void (*cmb_matmul_fn)(const void* in, void* out, void* user);
 int cmb_op_callback_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n, cmb_matmul_fn fn, void* user, cmb_op** out);
+/* Device-resident operator algebra (the reference composes operators on the host, vector_map.hpp:38-266):
+ * sum_i coefs[i] * ops[i] (coefs: nterms dtype elements) and outer * inner, as operators of their own.  The children
+ * stay owned by the caller and must outlive the composition; all must share context, dtype, shape and row range. */
+int cmb_op_linear_create(cmb_ctx* ctx, int64_t nterms, cmb_op* const* ops, const void* coefs, cmb_op** out);
+int cmb_op_product_create(cmb_ctx* ctx, cmb_op* outer, cmb_op* inner, cmb_op** out);
 /* collective on multi-rank contexts when the operator exchanges halos through peer memory: every rank must call it */
 int cmb_op_destroy(cmb_op* op);
 cmb_ctx* cmb_op_context(const cmb_op* op);

@@ -29,21 +29,43 @@ int main() {
 
   Vector<double> x0(n);
   for (int i = 0; i < n; ++i) x0[i] = std::sin(0.05 * i) + 0.3;
-  double ev[2][3];
-  for (int mode = 0; mode < 2; ++mode) {
+  double ev[3][3];
+  if (!h.hasDeviceOperator()) {
+    std::printf("FAIL: the composed map lost its device operator\n");
+    return 1;
+  }
+  for (int mode = 0; mode < 3; ++mode) {
     LanczosEigenSolver<double> es;
     if (mode == 0)
       es.setMatrixMultiplication(h.function(), h.sizeIn());
-    else
+    else if (mode == 1)
       es.setMatrixMultiplication(H.makeDeviceOperator());
+    else
+      es.setMatrixMultiplication(h.deviceOperator());
     es.setInitialVector(x0).setMinIterations(150).setMaxIterations(150).setMaxEigenvalues(3);
     es.compute();
     for (int k = 0; k < 3; ++k) ev[mode][k] = es.eigenvalues()[k];
-    std::printf("%s: %.12f %.12f %.12f\n", mode == 0 ? "vector map" : "assembled ", ev[mode][0], ev[mode][1], ev[mode][2]);
+    std::printf("%s: %.12f %.12f %.12f\n", mode == 0 ? "vector map" : (mode == 1 ? "assembled " : "device map"), ev[mode][0],
+                ev[mode][1], ev[mode][2]);
   }
-  double d = 0;
+  double d = 0, dd = 0;
   for (int k = 0; k < 3; ++k) d = std::max(d, std::abs(ev[0][k] - ev[1][k]));
+  for (int k = 0; k < 3; ++k) dd = std::max(dd, std::abs(ev[2][k] - ev[1][k]));
   std::printf("max |vector map - assembled| = %.3e\n", d);
-  std::printf("%s\n", d < 1e-10 ? "PASS" : "FAIL");
-  return d < 1e-10 ? 0 : 1;
+  std::printf("max |device map - assembled| = %.3e\n", dd);
+  // product on the device: the lowest eigenvalue of T*T is the square of the lowest eigenvalue of T
+  const VectorMap<double> tt = t * t;
+  double e_t = 0, e_tt = 0;
+  for (int mode = 0; mode < 2; ++mode) {
+    LanczosEigenSolver<double> es;
+    es.setMatrixMultiplication(mode == 0 ? t.deviceOperator() : tt.deviceOperator());
+    es.setInitialVector(x0).setMinIterations(399).setMaxIterations(399).setMaxEigenvalues(1).setComputeEigenvectorsOn(false);
+    es.compute();
+    (mode == 0 ? e_t : e_tt) = es.eigenvalues()[0];
+  }
+  const double dp = std::abs(e_tt - e_t * e_t);
+  std::printf("lowest of T*T on the device %.12e vs (lowest of T)^2 %.12e, difference %.3e\n", e_tt, e_t * e_t, dp);
+  const bool ok = d < 1e-10 && dd < 1e-10 && dp < 1e-10 && tt.hasDeviceOperator();
+  std::printf("%s\n", ok ? "PASS" : "FAIL");
+  return ok ? 0 : 1;
 }

@@ -660,3 +660,41 @@ def test_invalid_csr_is_rejected_on_the_device(ctx):
     op = pkg.DeviceOperator.from_csr(ctx, rp, c, v)
     x = syn.start_vector(100, seed=1)
     np.testing.assert_allclose(op.apply(x), core.Operator.csr(rp, c, v).apply(x), atol=1e-14)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_device_resident_operator_algebra(ctx, dtype):
+    """cmb_op_linear_create / cmb_op_product_create: sums, scalar multiples and products of operators in HBM applied on the
+    device (the reference composes them on the host, vector_map.hpp:38-266), alone and under the Lanczos driver."""
+    rng = np.random.default_rng(2)
+    N = 18
+    n = N * N
+    rp, c, v = syn.laplacian2d_csr(N)
+    A = _csr_dense(rp, c, v, n).astype(dtype)
+    Bd = rng.normal(size=(n, n)).astype(dtype)
+    if dtype == np.complex128:
+        Bd = Bd + 1j * rng.normal(size=(n, n))
+    Bd = 0.05 * (Bd + Bd.conj().T)  # Hermitian
+    opA = pkg.DeviceOperator.from_csr(ctx, rp, c, v.astype(dtype))
+    opB = pkg.DeviceOperator.from_dense(ctx, Bd)
+    ca, cb = (2.0, -0.5) if dtype == np.float64 else (2.0 + 0.0j, -0.5 + 0.0j)
+    lin = pkg.DeviceOperator.linear(ctx, [opA, opB], [ca, cb])
+    prod = pkg.DeviceOperator.product(ctx, opA, opB)
+    x = syn.start_vector(n, seed=4, dtype=dtype)
+    np.testing.assert_allclose(lin.apply(x), ca * (A @ x) + cb * (Bd @ x), atol=1e-12)
+    np.testing.assert_allclose(prod.apply(x), A @ (Bd @ x), atol=1e-12)
+    if dtype == np.complex128:
+        lz = pkg.DeviceOperator.linear(ctx, [opA, opB], [1.0 + 0.5j, 0.25 - 1.0j])
+        np.testing.assert_allclose(lz.apply(x), (1.0 + 0.5j) * (A @ x) + (0.25 - 1.0j) * (Bd @ x), atol=1e-12)
+        lz.close()
+    # under the solver: the linear combination is Hermitian; compare with the assembled dense operator and the oracle
+    H = ca * A + cb * Bd
+    m = 40
+    es = pkg.LanczosEigenSolver(dtype)
+    es.setMatrixMultiplication(lin).setInitialVector(x).setMinIterations(m).setMaxIterations(m).setMaxEigenvalues(3).setEigenvalueShift(0.3)
+    es.compute()
+    ref = _oracle_lanczos(core.Operator.dense(H), x, m, 3, prefix="z" if dtype == np.complex128 else "d", shift=0.3)
+    _compare_lanczos(es, ref)
+    es.close()
+    for o in (lin, prod, opA, opB):
+        o.close()

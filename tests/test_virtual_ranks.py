@@ -18,12 +18,11 @@ from cmpt_eigenex_b200 import synthetic as syn
 
 pytestmark = pytest.mark.gpu
 
-# Every section of the shared checks except the matrix-free Heisenberg slab exchange: between real GPUs the slabs travel
-# by copy engines over NVLink while the window passes run; on ONE device a slab copy needs SMs, which the peers'
-# spinning persistent kernels hold, so that overlap scheme cannot make progress there.  Its packing, offsets and
-# parity logic are covered on one GPU by test_heisenberg_partitioned_virtual_ranks (tests/test_gpu_parity.py, the ranks
-# run one after the other) and end to end by tests/dist_worker.py on real GPUs.
-SECTIONS = ["laplacian", "heisenberg", "convdiff_arnoldi", "exhaust", "breakdown_at_k", "deflation", "one_directional"]
+# Every section of the shared checks.  The matrix-free Heisenberg operator exchanges its slabs between virtual ranks with
+# SM stores (the fused push of the Gram-Schmidt pass that produces w, and a stand-alone push kernel for the first apply);
+# the copy-engine exchange real ranks use for applies without a producing pass needs SMs on one device and is not taken.
+SECTIONS = ["laplacian", "heisenberg", "convdiff_arnoldi", "exhaust", "breakdown_at_k", "deflation", "one_directional",
+            "heisenberg_mf"]
 
 
 def _expected(which):
