@@ -43,6 +43,12 @@ struct HeisPass {
   int wrapb;  // ... and, when set, the periodic bond joining tile bits tb-1 and 0 (single rank only)
   int main;   // the contiguous pass, run last: writes u, adds the remote bonds and the shift, computes the alpha dot
   int rmw;    // adds to the v of the earlier passes (the first pass of an apply just writes v)
+  // Sibling passes (XB = 3): besides the bonds inside its tile a CTA serves the three bonds that involve the three index
+  // bits directly above the tile — (top tile bit, x0), (x0, x1), (x1, x2).  Their partner elements lie in the seven
+  // "sibling" tiles that differ in those bits; the work order keeps the eight siblings on neighbouring CTAs at the
+  // same time, so the partner elements are read straight from global memory and hit in L2 (no second DRAM read).
+  int xmask;  // which of these three bonds this pass serves (bit e = bond e)
+  int xwrap;  // ... and the periodic bond joining x2 (the top index bit) with tile bit 0 (single rank only)
 };
 
 constexpr int kHeisConsumers = 512;  // 16 warps (128 registers each); thread 0 also feeds the ring
@@ -98,6 +104,42 @@ struct HeisPair {
       *reinterpret_cast<double2*>(base + t0) = make_double2(r0, r1);
     }
   }
+  // streaming variants (L2 evict-first): data that is touched once per pass
+  __device__ __forceinline__ static HeisPair load_cs(const double* base, long long t0) {
+    HeisPair p;
+    if constexpr (CPLX) {
+      const double2 e0 = __ldcs(reinterpret_cast<const double2*>(base) + t0);
+      const double2 e1 = __ldcs(reinterpret_cast<const double2*>(base) + t0 + 1);
+      p.r0 = e0.x, p.i0 = e0.y, p.r1 = e1.x, p.i1 = e1.y;
+    } else {
+      const double2 e = __ldcs(reinterpret_cast<const double2*>(base + t0));
+      p.r0 = e.x, p.r1 = e.y, p.i0 = 0.0, p.i1 = 0.0;
+    }
+    return p;
+  }
+  __device__ __forceinline__ void store_cs(double* base, long long t0) const {
+    if constexpr (CPLX) {
+      __stcs(reinterpret_cast<double2*>(base) + t0, make_double2(r0, i0));
+      __stcs(reinterpret_cast<double2*>(base) + t0 + 1, make_double2(r1, i1));
+    } else {
+      __stcs(reinterpret_cast<double2*>(base + t0), make_double2(r0, r1));
+    }
+  }
+  // this += f * o
+  __device__ __forceinline__ void axpy(double f, const HeisPair& o) {
+    r0 = fma(f, o.r0, r0), r1 = fma(f, o.r1, r1);
+    if constexpr (CPLX) i0 = fma(f, o.i0, i0), i1 = fma(f, o.i1, i1);
+  }
+  // element 0 += f * o.element 1   /   element 1 += f * o.element 0
+  __device__ __forceinline__ void axpy_cross(double f, const HeisPair& o, bool into0) {
+    if (into0) {
+      r0 = fma(f, o.r1, r0);
+      if constexpr (CPLX) i0 = fma(f, o.i1, i0);
+    } else {
+      r1 = fma(f, o.r0, r1);
+      if constexpr (CPLX) i1 = fma(f, o.i0, i1);
+    }
+  }
   __device__ __forceinline__ void add(const HeisPair& o) {
     r0 += o.r0, r1 += o.r1;
     if constexpr (CPLX) i0 += o.i0, i1 += o.i1;
@@ -119,7 +161,7 @@ struct HeisPair {
 };
 
 // MAIN / RMW: role of the pass (compile time, so that the unrolled pair loop carries no uniform branches for them)
-template <bool CPLX, bool MAIN, bool RMW>
+template <bool CPLX, bool MAIN, bool RMW, int XB>
 __global__ void __launch_bounds__(kHeisThreads, 1)
 heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap tm, const double* __restrict__ w,
                   double* __restrict__ ucol, double* __restrict__ v, double shr, double shi, StepScalars sc,
@@ -141,6 +183,9 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
       const long long t0 = clock64();
       while (ld_acquire_sys_u64(a.flag + threadIdx.x) < a.seq) {
         if (clock64() - t0 > a.timeout) {  // bounded: a missing partner raises the error flag and halts the chain
+          if (blockIdx.x == 0)
+            printf("[cmpt_b200] Heisenberg slab wait timed out: bond %d, exchange %llu expected, flag holds %llu\n",
+                   int(threadIdx.x), a.seq, ld_acquire_sys_u64(a.flag + threadIdx.x));
           *a.error = 1;
           *sc.halt = 1;
           break;
@@ -160,19 +205,41 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
   // ring feeder (thread 0): one TMA per tile into stage `s`, signalled on full[s]
   const uint32_t tile_bytes = uint32_t(sizeof(double) * ES) << tb;
   const bool contiguous = (ps.a == tb);
-  auto feed = [&](long long tile, int s) {
+  // linear work index q -> tile.  In a sibling pass the three low bits of q select among the eight sibling tiles, i.e.
+  // they must land on the three index bits directly above the tile: for a contiguous tile those are the low bits of
+  // the tile number anyway, for a window tile they are the low bits of its "high" part.
+  auto tile_of = [&](long long q) -> long long {
+    if (!XB || contiguous) return q;
+    const long long rest = q >> XB;
+    const long long mid = rest & ((1ll << nmid) - 1), high = rest >> nmid;
+    return mid | (((high << XB) | (long long)(q & ((1 << XB) - 1))) << nmid);
+  };
+  // sibling passes: w is read twice (own tile through TMA, partner elements through L2) while v and u stream by once,
+  // so w's lines are kept in L2 (evict-last) and the others marked evict-first
+  const uint64_t keep = XB ? l2_policy_evict_last() : 0ull;
+  auto feed = [&](long long q, int s) {
+    const long long tile = tile_of(q);
     mbar_arrive_expect_tx(&full[s], tile_bytes);
-    void* dst = heis_smem + size_t(s) * kHeisTileBytes;
-    if (contiguous)
-      bulk_load_1d(dst, w + (size_t(tile) << tb) * ES, tile_bytes, &full[s]);
-    else
-      tma_load_3d(dst, &tm, 0, int(tile & ((1ll << nmid) - 1)), int((tile >> nmid) << (tb - ps.a)), &full[s]);
+    char* dst = reinterpret_cast<char*>(heis_smem) + size_t(s) * kHeisTileBytes;
+    if (contiguous) {
+      if (XB) bulk_load_1d_hint(dst, w + (size_t(tile) << tb) * ES, tile_bytes, &full[s], keep);
+      else bulk_load_1d(dst, w + (size_t(tile) << tb) * ES, tile_bytes, &full[s]);
+    } else {
+      // the window goes as boxes of at most 256 window positions (the limit of a TMA box dimension)
+      const int wpos = 1 << (tb - ps.a), nbox = wpos > 256 ? wpos / 256 : 1;
+      const uint32_t box_bytes = tile_bytes / uint32_t(nbox);
+      for (int b = 0; b < nbox; ++b) {
+        const int c1 = int(tile & ((1ll << nmid) - 1)), c2 = int((tile >> nmid) << (tb - ps.a)) + b * 256;
+        if (XB) tma_load_3d_hint(dst + size_t(b) * box_bytes, &tm, 0, c1, c2, &full[s], keep);
+        else tma_load_3d(dst + size_t(b) * box_bytes, &tm, 0, c1, c2, &full[s]);
+      }
+    }
   };
   if (threadIdx.x == 0) {
     if (!contiguous) prefetch_tmap(&tm);
     for (int s = 0; s < kHeisStages; ++s) {
-      const long long tile = blockIdx.x + (long long)s * gridDim.x;
-      if (tile < ntiles) feed(tile, s);
+      const long long q = blockIdx.x + (long long)s * gridDim.x;
+      if (q < ntiles) feed(q, s);
     }
   }
   {
@@ -182,7 +249,10 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
     const int kfirst = ps.k0 > 1 ? ps.k0 : 1;
     const int kmask = ((1 << (tb - 1)) - 1) & ~((1 << kfirst) - 1);  // gray-code bits of the bonds k >= kfirst
     const bool bond0 = (ps.k0 == 0 && tb >= 2);
-    const int nlocal = (tb - 1 - ps.k0) + ps.wrapb;
+    const int x0b = XB ? (ps.xmask & 1) : 0, x1b = XB ? ((ps.xmask >> 1) & 1) : 0, x2b = XB ? ((ps.xmask >> 2) & 1) : 0;
+    const int xwrap = XB ? ps.xwrap : 0;
+    const int nlocal = (tb - 1 - ps.k0) + ps.wrapb + x0b + x1b + x2b + xwrap;
+    const int xb0 = ps.h + tb - ps.a;  // global position of sibling bit 0
     // bonds whose diagonal term this pass accounts for (the remote bonds ride with the first pass)
     const bool remote = (a.n_full | a.has_straddle | a.has_wrap) != 0;
     const int nb_pass = nlocal + (MAIN ? a.aligned_uniform + a.n_full + a.has_straddle + a.has_wrap : 0);
@@ -197,16 +267,46 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
       const int tj = j << 10;
       return (long long)(tj & lowmask) | ((long long)(tj >> ps.a) << ps.h);
     };
-    int st = 0;
+    int st = 0, it = 0;
     uint32_t ph = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long q = blockIdx.x; q < ntiles; q += gridDim.x, ++it) {
+      const long long tile = tile_of(q);
       const long long base =
           (((tile & ((1ll << nmid) - 1)) << ps.a) | ((tile >> nmid) << (ps.h + tb - ps.a))) + s_tid;
+      // Before waiting for the tile: what this tile's result is added to (the earlier passes' v) and the sibling bonds'
+      // partner elements, both from global memory.  yold = v_old + (J/2)/beta * (sum of the sibling partners).
+      const unsigned crank = XB ? unsigned(q & ((1 << XB) - 1)) : 0u;
+      const bool x1anti = x1b && (((crank ^ (crank >> 1)) & 1u) != 0u);         // sibling bits 0, 1 differ: uniform per tile
+      const bool x2anti = x2b && ((((crank >> 1) ^ (crank >> 2)) & 1u) != 0u);  // sibling bits 1, 2 differ
       Pair yold[PPT];
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         yold[j] = Pair::zero();
-        if (RMW && int(threadIdx.x) + kHeisConsumers * j < npairs) yold[j] = Pair::load(v, base + s_iter(j));
+        if (RMW && int(threadIdx.x) + kHeisConsumers * j < npairs)
+          yold[j] = XB ? Pair::load_cs(v, base + s_iter(j)) : Pair::load(v, base + s_iter(j));
+      }
+      if (XB) {  // tiles are full here (tb = TB).  One loop per bond: its PPT loads are independent and go out together
+        const double f = hJ * inv;
+        if (x1anti) {
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) yold[j].axpy(f, Pair::load(w, (base + s_iter(j)) ^ (3ll << xb0)));
+        }
+        if (x2anti) {
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) yold[j].axpy(f, Pair::load(w, (base + s_iter(j)) ^ (3ll << (xb0 + 1))));
+        }
+        if (x0b) {
+          const int c0 = int(crank & 1u);
+#pragma unroll
+          for (int j = 0; j < PPT; ++j)
+            if ((((tl | (j << 10)) >> (tb - 1)) & 1) != c0)
+              yold[j].axpy(f, Pair::load(w, (base + s_iter(j)) ^ (3ll << (xb0 - 1))));
+        }
+        if (xwrap) {
+#pragma unroll
+          for (int j = 0; j < PPT; ++j)
+            yold[j].axpy_cross(f, Pair::load(w, (base + s_iter(j)) ^ (1ll << (xb0 + 2))), (crank & 4u) != 0u);
+        }
       }
       mbar_wait(&full[st], ph);
       const double* sm = reinterpret_cast<const double*>(heis_smem + size_t(st) * kHeisTileBytes);
@@ -266,6 +366,17 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
             anti0 += bt;
             anti1 += 1 - bt;
           }
+          if (XB) {  // sibling bonds: the partner elements are in yold already, here only the diagonal counts
+            const int bt = (t0 >> (tb - 1)) & 1;
+            const int ax = ((x0b && bt != int(crank & 1u)) ? 1 : 0) + (x1anti ? 1 : 0) + (x2anti ? 1 : 0);
+            anti0 += ax;
+            anti1 += ax;
+            if (xwrap) {  // periodic bond: sibling bit 2 (the top index bit) and index bit 0
+              const int c2 = int((crank >> 2) & 1u);
+              anti0 += c2;
+              anti1 += 1 - c2;
+            }
+          }
           if (MAIN && remote) {
             anti0 += a.n_full;
             anti1 += a.n_full;
@@ -308,10 +419,12 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
               y.r0 -= shi * u.i0, y.r1 -= shi * u.i1;
               y.i0 += shr * u.i0 + shi * u.r0, y.i1 += shr * u.i1 + shi * u.r1;
             }
-            u.store(ucol, s0);
+            if (XB) u.store_cs(ucol, s0);
+            else u.store(ucol, s0);
           }
-          if (RMW) y.add(yold[j]);
-          y.store(v, s0);
+          if (RMW || XB) y.add(yold[j]);
+          if (XB) y.store_cs(v, s0);
+          else y.store(v, s0);
           if (MAIN) {
             d0 = fma(u.r0, y.r0, d0);
             d0 = fma(u.r1, y.r1, d0);
@@ -325,10 +438,10 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
       __syncwarp();
       if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[st]);
       if (threadIdx.x == 0) {  // refill this stage with the tile kHeisStages ahead once all 16 warps released it
-        const long long nt = tile + (long long)kHeisStages * gridDim.x;
-        if (nt < ntiles) {
+        const long long nq = q + (long long)kHeisStages * gridDim.x;
+        if (nq < ntiles) {
           mbar_wait(&empty[st], ph);
-          feed(nt, st);
+          feed(nq, st);
         }
       }
       if (++st == kHeisStages) {
@@ -391,6 +504,8 @@ struct HeisenbergOp : cmb_op {
   double* d_pack = nullptr;  // packed parity half for the wrap bond
   std::vector<size_t> recv_off;
   std::vector<HeisPass> passes;
+  const bool trace_slab = getenv("CMPT_B200_TRACE_SLAB") != nullptr;
+  bool use_siblings = false;  // passes also serve the three bonds above the tile from the sibling tiles (see HeisPass)
   // peer-memory exchange (CUDA IPC + copy engines): every rank owns [flags | receive buffer 0 | receive buffer 1],
   // mapped into its partners, which copy their slabs into it (cudaMemcpyAsync on side streams, overlapping the window
   // passes) and then publish the exchange number in the flag of that bond.  NCCL send/recv is the fallback.
@@ -448,23 +563,47 @@ struct HeisenbergOp : cmb_op {
   // keep runs of 256 bytes and move an 8-bit window (box rows of a TMA tensor map are limited to 256).
   void plan_passes() {
     passes.clear();
-    const int Ll = plan.Ll, TB = cplx ? 12 : 13, arun = cplx ? 4 : 5, wb = TB - arun;
+    const int Ll = plan.Ll, TB = cplx ? 12 : 13;
     const bool local_wrap = (plan.p == 0 && plan.nb == plan.L);
-    HeisPass m;  // the contiguous pass: bonds 0 .. tb-2; runs last because it also consumes the remote slabs
+    // Sibling passes (CMPT_B200_HEIS_SIBLINGS=1, off by default) need three index bits above the 2^TB tile; their window
+    // passes use 128-byte runs so that window + sibling bits reach 12 bits: two passes up to 27 local bits instead of
+    // three.  Measured on B200 at 27 bits the two passes move 1/3 fewer DRAM bytes but are bound by the latency of the
+    // partner loads (2.0 ms per apply against 1.7 ms for the three HBM-bound passes; profiles/r2/heis_two_pass.md), so
+    // the default keeps every pass inside its own tiles (256-byte runs).
+    const char* sib = getenv("CMPT_B200_HEIS_SIBLINGS");
+    use_siblings = (Ll >= TB + 3) && sib && atoi(sib) != 0;
+    const int XB = use_siblings ? 3 : 0;
+    const int arun = use_siblings ? (cplx ? 3 : 4) : (cplx ? 4 : 5);
+    const int wbl = TB - arun;  // window bits inside one tile
+    const int wb = wbl + XB;    // index bits a window pass spans above h
+    HeisPass m;  // the contiguous pass: bonds 0 .. tb-2 (+ the sibling bonds); runs last because it also consumes the remote slabs
     memset(&m, 0, sizeof(m));
     m.tb = std::min(Ll, TB);
     m.a = m.h = m.tb;
     m.wrapb = (Ll <= TB && local_wrap) ? 1 : 0;
     m.main = 1;
     int next = m.tb - 1;  // first bond not served yet (bond b joins bits b and b+1)
+    if (use_siblings) {
+      m.xmask = 7;  // bonds tb-1, tb, tb+1
+      m.xwrap = (m.tb + XB == Ll && local_wrap) ? 1 : 0;
+      next = m.tb + XB - 1;
+    }
     while (next <= Ll - 2) {
       HeisPass q;
       memset(&q, 0, sizeof(q));
       q.tb = TB;
       q.a = arun;
       q.h = std::min(next, Ll - wb);  // the last window is pulled down so that it ends at the top bit
-      q.k0 = q.a + (next - q.h);
-      q.wrapb = (q.h + wb == Ll && local_wrap) ? 1 : 0;
+      q.k0 = q.a + (next - q.h);      // tile bit of the first bond to serve (may lie beyond the tile's own window)
+      if (q.k0 > q.tb - 1) q.k0 = q.tb - 1;
+      if (use_siblings) {
+        // sibling bond e joins index bits h + wbl - 1 + e and h + wbl + e: served when it is not below `next`
+        for (int e = 0; e < XB; ++e)
+          if (q.h + wbl - 1 + e >= next) q.xmask |= 1 << e;
+        q.xwrap = (q.h + wb == Ll && local_wrap) ? 1 : 0;
+      } else {
+        q.wrapb = (q.h + wb == Ll && local_wrap) ? 1 : 0;
+      }
       q.rmw = passes.empty() ? 0 : 1;
       next = q.h + wb - 1;
       passes.push_back(q);
@@ -478,7 +617,7 @@ struct HeisenbergOp : cmb_op {
     const int es = cplx ? 2 : 1;
     cuuint64_t gdim[3] = {cuuint64_t(es) << ps.a, cuuint64_t(1) << (ps.h - ps.a), cuuint64_t(1) << (plan.Ll - ps.h)};
     cuuint64_t gstr[2] = {(cuuint64_t(8 * es) << ps.a), (cuuint64_t(8 * es) << ps.h)};
-    cuuint32_t box[3] = {cuuint32_t(es) << ps.a, 1u, 1u << (ps.tb - ps.a)};
+    cuuint32_t box[3] = {cuuint32_t(es) << ps.a, 1u, std::min<cuuint32_t>(1u << (ps.tb - ps.a), 256u)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult cr = get_encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(w), gdim, gstr, box,
                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -598,17 +737,17 @@ struct HeisenbergOp : cmb_op {
       if (ps.a != ps.tb) CMB_TRY(window_map(ps, w, &tm));
       LaunchScope ls(ctx, "heisenberg_mf");
       const long long ntiles = 1ll << (plan.Ll - ps.tb);
-      const int grid = int(std::min<long long>(ntiles, (long long)ctx->num_sms));
+      int grid = int(std::min<long long>(ntiles, (long long)ctx->num_sms));
 #define CMB_HEIS_LAUNCH(C, M, R)                                                                                     \
   do {                                                                                                               \
-    static bool attr[64] = {};  /* function attributes are per device */                                            \
-    if (!attr[ctx->device & 63]) {                                                                                   \
-      CMB_CUDA(cudaFuncSetAttribute(heis_apply_kernel<C, M, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                    kHeisSmem));                                                                     \
-      attr[ctx->device & 63] = true;                                                                                 \
+    auto kern = use_siblings ? heis_apply_kernel<C, M, R, 3> : heis_apply_kernel<C, M, R, 0>;                        \
+    static bool attr[2][64] = {};  /* function attributes are per device */                                         \
+    if (!attr[use_siblings ? 1 : 0][ctx->device & 63]) {                                                             \
+      CMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeisSmem));                  \
+      attr[use_siblings ? 1 : 0][ctx->device & 63] = true;                                                           \
     }                                                                                                                \
-    heis_apply_kernel<C, M, R><<<grid, kHeisThreads, kHeisSmem, ctx->stream>>>(a, ps, tm, w, ucol, v, shr, shi, sc,  \
-                                                                               ctx->d_partial, ctx->d_ticket + 1);   \
+    kern<<<grid, kHeisThreads, kHeisSmem, ctx->stream>>>(a, ps, tm, w, ucol, v, shr, shi, sc, ctx->d_partial,        \
+                                                         ctx->d_ticket + 1);                                         \
   } while (0)
       const int role = (ps.main ? 2 : 0) | (ps.rmw ? 1 : 0);
       if (cplx) {
@@ -683,6 +822,7 @@ struct HeisenbergOp : cmb_op {
     pushed_w = w;
     pushed_x = x;
     *out = sp;
+    if (trace_slab) fprintf(stderr, "[slab] rank %d announces exchange %llu of %p to %d partners\n", plan.rank, x, (const void*)w, sp.n);
     return true;
   }
   void slab_push_cancel() override { pushed_w = nullptr; }
@@ -690,18 +830,16 @@ struct HeisenbergOp : cmb_op {
   int apply(const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) override {
     HeisArgs a = base_args();
     if (plan.p > 0) {
-      if (p2p && pushed_w == w && pushed_w != nullptr) {
-        // the kernel that produced w has pushed the slabs and raised the flags of exchange pushed_x
-        pushed_w = nullptr;
-      if (p2p && (ctx->vgroup || getenv("CMPT_B200_SM_SLAB_PUSH"))) {
+      const bool fused = p2p && pushed_w == w && pushed_w != nullptr;
+      if (p2p && !fused && (ctx->vgroup || getenv("CMPT_B200_SM_SLAB_PUSH"))) {
         // virtual ranks (and on request): the exchange of this apply as SM stores from a stand-alone kernel in stream
         // order — same destinations, flags and parity as the fused push
         SlabPush sp;
-        if (slab_push_begin(w, &sp)) {
-          CMB_TRY(slab_push(ctx, w, sp, sc.halt));
-          return apply(w, ucol, v, shr, shi, sc);
-        }
+        if (slab_push_begin(w, &sp)) CMB_TRY(slab_push(ctx, w, sp, sc.halt));
       }
+      if (p2p && pushed_w == w && pushed_w != nullptr) {
+        // the kernel that produced w (or the push kernel above) stores the slabs and raises the flags of exchange pushed_x
+        pushed_w = nullptr;
         unsigned mask = 0;
         for (size_t k = 0; k < plan.remote.size(); ++k)
           if (plan.remote[k].needed) mask |= 1u << k;
@@ -711,6 +849,7 @@ struct HeisenbergOp : cmb_op {
         a.flag = static_cast<const unsigned long long*>(p2p_base);
         a.seq = pushed_x;
         a.flag_mask = mask;
+        if (trace_slab) fprintf(stderr, "[slab] rank %d consumes exchange %llu (mask %x)\n", plan.rank, pushed_x, mask);
         a.error = ctx->d_mail_error;
         a.timeout = ctx->spin_timeout;
         return launch(a, w, ucol, v, shr, shi, sc);
@@ -870,6 +1009,9 @@ int cmb_op_heisenberg_create(cmb_ctx* ctx, cmb_dtype dtype, int L, double J, int
     return rc;
   }
   op->bytes = 2.0 * double(nloc) * (op->cplx ? 16.0 : 8.0);  // B_mf = 2 n s
+  // Virtual ranks share one device: the allocations above synchronise it, so a rank that already launched its first
+  // (spinning) apply would stall the ranks still allocating.  Everybody leaves the constructor together.
+  if (ctx->vgroup && ctx->nranks > 1) CMB_TRY(rank_barrier(ctx));
   *out = op;
   return CMB_OK;
 }

@@ -1,23 +1,29 @@
-"""Tiny driver for profiling the matrix-free Heisenberg apply: L sites on one GPU, a few Lanczos steps.
-usage: heis_probe.py [L] [m]"""
+"""Times the matrix-free Heisenberg apply (cfg 5 operator) per launch family, with and without the sibling bonds.
+
+usage: python scripts/heis_probe.py [L] [mode ...]   (0 = passes stay inside their tiles, 1 = sibling bonds)
+"""
 import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import cmpt_eigenex_b200 as pkg  # noqa: E402
-from cmpt_eigenex_b200 import synthetic as syn  # noqa: E402
+import numpy as np  # noqa: E402
 
-L = int(sys.argv[1]) if len(sys.argv) > 1 else 26
-m = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+import cmpt_eigenex_b200 as pkg  # noqa: E402
+
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 27
+settings = [int(a) for a in sys.argv[2:]] or [0, 1]
 ctx = pkg.Context(0)
-op = pkg.DeviceOperator.heisenberg(ctx, L)
-es = pkg.LanczosEigenSolver()
-es.setMatrixMultiplication(op).setInitialVector(syn.start_vector(1 << L, seed=7))
-es.setMinIterations(m).setMaxIterations(m).setMaxEigenvalues(1).setComputeEigenvectorsOn(False).setReserveSize(m + 1)
-es.compute()
-ctx.sync()
-print("lowest ritz", float(es.eigenvalues()[0]))
-es.close()
-op.close()
-ctx.close()
+x = np.random.default_rng(1).standard_normal(1 << L)
+x /= np.linalg.norm(x)
+for ncl in settings:
+    os.environ["CMPT_B200_HEIS_SIBLINGS"] = "1" if ncl else "0"
+    op = pkg.DeviceOperator.heisenberg(ctx, L)
+    op.apply(x)  # plans the passes, warms up
+    ctx.profile(True)
+    for _ in range(3):
+        op.apply(x)
+    ms, n = ctx.profile_get("heisenberg_mf")
+    ctx.profile(False)
+    print("L=%d siblings=%s: %d launches, %.3f ms per apply, %.3f ms per launch" % (L, "on" if ncl else "off", n, ms / 3, ms / max(n, 1)), flush=True)
+    op.close()

@@ -556,13 +556,18 @@ def test_cfg2_full_size_properties(ctx):
 
 
 # ------------------------------------------------------------------------------------------------
-# matrix-free Heisenberg apply beyond one shared-memory tile: window passes (2 passes from L = 14 real / 13 complex,
-# 3 passes from L = 21 / 20), open and periodic chains
+# matrix-free Heisenberg apply beyond one shared-memory tile, open and periodic chains: 2 passes from L = 14 real / 13
+# complex, 3 passes from L = 21 / 20.  With CMPT_B200_HEIS_SIBLINGS=1 a pass also serves the three bonds above its tile
+# from the sibling tiles (from 16 / 15 local bits; 2 passes up to 27 bits) — an opt-in variant, same results.
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("L,pbc,dtype", [(14, True, np.float64), (16, False, np.float64), (20, True, np.float64),
-                                         (21, True, np.float64), (22, False, np.float64), (23, True, np.float64),
-                                         (13, True, np.complex128), (17, False, np.complex128),
-                                         (20, True, np.complex128), (21, True, np.complex128)])
+HEIS_MULTI_PASS = [(14, True, np.float64), (16, False, np.float64), (16, True, np.float64), (17, True, np.float64),
+                   (19, False, np.float64), (20, True, np.float64), (21, True, np.float64), (22, False, np.float64),
+                   (23, True, np.float64), (13, True, np.complex128), (15, True, np.complex128),
+                   (16, False, np.complex128), (17, False, np.complex128), (20, True, np.complex128),
+                   (21, True, np.complex128)]
+
+
+@pytest.mark.parametrize("L,pbc,dtype", HEIS_MULTI_PASS)
 def test_heisenberg_multi_pass_apply(ctx, L, pbc, dtype):
     x = syn.start_vector(1 << L, seed=31, dtype=dtype)
     op = pkg.DeviceOperator.heisenberg(ctx, L, 1.0, pbc, dtype=dtype)
@@ -570,6 +575,36 @@ def test_heisenberg_multi_pass_apply(ctx, L, pbc, dtype):
     yo = core.Operator.heisenberg(L, 1.0, pbc, prefix="z" if dtype == np.complex128 else "d").apply(x)
     np.testing.assert_allclose(y, yo, atol=1e-14)
     op.close()
+
+
+@pytest.mark.parametrize("L,pbc,dtype", [(16, True, np.float64), (17, True, np.float64), (19, False, np.float64),
+                                         (21, True, np.float64), (23, False, np.float64), (23, True, np.float64),
+                                         (15, True, np.complex128), (16, False, np.complex128),
+                                         (21, True, np.complex128)])
+def test_heisenberg_multi_pass_apply_with_sibling_bonds(ctx, monkeypatch, L, pbc, dtype):
+    monkeypatch.setenv("CMPT_B200_HEIS_SIBLINGS", "1")  # read when the operator plans its passes (first apply)
+    x = syn.start_vector(1 << L, seed=32, dtype=dtype)
+    op = pkg.DeviceOperator.heisenberg(ctx, L, 1.0, pbc, dtype=dtype)
+    y = op.apply(x)
+    yo = core.Operator.heisenberg(L, 1.0, pbc, prefix="z" if dtype == np.complex128 else "d").apply(x)
+    np.testing.assert_allclose(y, yo, atol=1e-14)
+    op.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_heisenberg_sibling_passes_lanczos_matches_oracle(ctx, monkeypatch, dtype):
+    # the u column, the 1/beta scaling and the alpha dot ride in the contiguous pass next to the sibling bonds: whole solver steps
+    monkeypatch.setenv("CMPT_B200_HEIS_SIBLINGS", "1")
+    L, m = 17, 12
+    pre = "z" if dtype == np.complex128 else "d"
+    x0 = syn.start_vector(1 << L, seed=5, dtype=dtype)
+    es = pkg.LanczosEigenSolver(dtype)
+    es.setMatrixMultiplication(pkg.DeviceOperator.heisenberg(ctx, L, dtype=dtype)).setInitialVector(x0)
+    es.setMinIterations(m).setMaxIterations(m).setMaxEigenvalues(3).setIndicesForConvergence([0, 1, 2])
+    es.compute()
+    ref = _oracle_lanczos(core.Operator.heisenberg(L, 1.0, True, prefix=pre), x0, m, 3, indices_for_convergence=[0, 1, 2],
+                          prefix=pre)
+    _compare_lanczos(es, ref)
 
 
 # ------------------------------------------------------------------------------------------------
