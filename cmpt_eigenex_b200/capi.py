@@ -102,6 +102,7 @@ def _declare(L):
         "cmb_krylov_combine": (i32, [vp, vp, i64, vp]),
         "cmb_debug_cgs_pass": (i32, [vp, i32, i32, i32, P(dbl)]),
         "cmb_debug_op_exchange_count": (i32, [vp, P(C.c_longlong)]),
+        "cmb_debug_op_sell_stats": (i32, [vp, P(C.c_longlong), P(C.c_longlong), P(i32)]),
         "cmb_vgroup_create": (i32, [i32, i32, P(vp)]),
         "cmb_vgroup_destroy": (i32, [vp]),
         "cmb_vgroup_info": (i32, [vp, P(i32), P(i32), P(i32)]),

@@ -47,12 +47,11 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
            const double* __restrict__ hin, double* __restrict__ hout, double* __restrict__ partial,
            unsigned* __restrict__ ticket, const int* __restrict__ halt, int ncols, int cg, int ntiles, int stages,
            MailPull pull, MailPush push, int norm_trick, int* retry, int retry_tag, double norm_guard,
-           const __grid_constant__ SlabPush slab) {
+           const __grid_constant__ SlabPush slab, int v_stable) {
   using Cfg = CgsCfg<WC>;
   constexpr int T = Cfg::T, WR = Cfg::WR;
   constexpr int ES = CPLX ? 2 : 1;  // doubles per coefficient
   constexpr int NCMAX = CG * WC;
-  if (*halt) return;
   const int nc = cg * WC;                  // columns in the TMA box (>= ncols)
   const int stage_doubles = nc * T + T;    // V tile + x tile
 
@@ -80,24 +79,54 @@ cgs_kernel(const __grid_constant__ CUtensorMap tmV, const double* __restrict__ x
     if (lane == 0) {
       prefetch_tmap(&tmV);
       const uint32_t bytes = uint32_t(nc) * T * 8 + (x ? Cfg::X_BYTES : 0);
-      int s = 0;
-      uint32_t ph = 0;  // stage index / ring phase kept incrementally (no integer division per tile)
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full[s], bytes);
+      auto load_v = [&](int tile, int s) {
         double* vs = stage_base + size_t(s) * stage_doubles;
 #pragma unroll
         for (int b = 0; b < Cfg::NBOX; ++b)
           tma_load_2d(vs + size_t(b) * nc * Cfg::BOXR, &tmV, tile * T + b * Cfg::BOXR, 0, &full[s]);
+      };
+      auto load_x = [&](int tile, int s) {
+        double* vs = stage_base + size_t(s) * stage_doubles;
         if (x) bulk_load_1d(vs + nc * T, x + size_t(tile) * T, Cfg::X_BYTES, &full[s]);
+      };
+      // The basis tiles of the first ring round do not depend on the kernel before this one (v_stable): they are
+      // fetched while it drains.  Everything else waits for it.
+      int npre = 0;
+      if (v_stable)
+        for (int tile = blockIdx.x; tile < ntiles && npre < stages; tile += gridDim.x, ++npre) {
+          mbar_arrive_expect_tx(&full[npre], bytes);
+          load_v(tile, npre);
+        }
+      grid_dependency_wait();
+      grid_launch_dependents();
+      const bool halted = *halt != 0;
+      int tile = blockIdx.x;
+      for (int i = 0; i < npre; ++i, tile += gridDim.x) load_x(tile, i);  // (stale on a halted chain, never read)
+      if (halted) {
+        for (int i = 0; i < npre; ++i) mbar_wait(&full[i], 0);  // no copy may be in flight when the CTA leaves
+        return;
+      }
+      int s = npre == stages ? 0 : npre;
+      uint32_t ph = npre == stages ? 1u : 0u;  // stage index / ring phase kept incrementally
+      for (; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], bytes);
+        load_v(tile, s);
+        load_x(tile, s);
         if (++s == stages) {
           s = 0;
           ph ^= 1u;
         }
       }
+    } else {
+      grid_dependency_wait();
+      grid_launch_dependents();
     }
     return;
   }
+  grid_dependency_wait();
+  grid_launch_dependents();
+  if (*halt) return;
 
   // ===== consumers =====
   const int gc = warp % WC;  // column group
@@ -457,9 +486,10 @@ static int launch_cfg(cmb_ctx* ctx, const CgsPass& a, int cg) {
   static const char* fam[3] = {"cgs_dot", "cgs_update_dot", "cgs_update_norm"};
   {
     LaunchScope ls(ctx, a.family ? a.family : fam[MODE]);
-    kern<<<grid, kThreads, smem, ctx->stream>>>(tm, a.x, a.y, a.hin, a.hout, ctx->d_partial, ctx->d_ticket, a.halt,
-                                                a.ncols, cg, ntiles, stages, a.pull, a.push, a.norm_trick, a.retry, a.retry_tag,
-                                                a.norm_guard, a.slab);
+    const bool overlap = pdl_wanted(8.0 * double(a.ld) * double(a.ncols + 1), false);
+    CMB_CUDA(launch_pdl(overlap, kern, grid, kThreads, smem, ctx->stream, tm, a.x, a.y, a.hin, a.hout, ctx->d_partial, ctx->d_ticket,
+                        a.halt, a.ncols, cg, ntiles, stages, a.pull, a.push, a.norm_trick, a.retry, a.retry_tag,
+                        a.norm_guard, a.slab, a.v_stable ? 1 : 0));
   }
   CMB_CUDA(cudaGetLastError());
   return CMB_OK;

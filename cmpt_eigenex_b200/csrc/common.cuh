@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -180,6 +181,44 @@ struct LaunchScope {
   ~LaunchScope();
 };
 int resolve_profile(cmb_ctx* ctx);
+#ifdef __CUDACC__
+// Launch with programmatic stream serialization (see grid_dependency_wait) when `overlap` is set, normally otherwise.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(bool overlap, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(grid));
+  cfg.blockDim = dim3(unsigned(block));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = overlap ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+// Policy: which launches overlap with their predecessor.  `bytes` = what the kernel streams.  CMPT_B200_PDL=0 none,
+// =1 all; CMPT_B200_PDL_MAX_MB limits it to kernels that stream less than that (their duration is comparable with the
+// launch latency the overlap hides); CMPT_B200_PDL_APPLY=0/1 excludes/includes the operator kernels.
+inline bool pdl_wanted(double bytes, bool is_apply) {
+  struct Policy {
+    int mode = -1;  // -1 by size
+    double max_bytes = 16.0 * 1048576.0;
+    int apply = -1;  // -1: same rule as the Gram-Schmidt passes
+    Policy() {
+      if (const char* e = getenv("CMPT_B200_PDL")) mode = atoi(e) != 0 ? 1 : 0;
+      if (const char* e = getenv("CMPT_B200_PDL_MAX_MB")) max_bytes = atof(e) * 1048576.0;
+      if (const char* e = getenv("CMPT_B200_PDL_APPLY")) apply = atoi(e) != 0 ? 1 : 0;
+    }
+  };
+  static const Policy p;
+  if (p.mode == 0) return false;
+  if (is_apply && p.apply == 0) return false;
+  if (p.mode == 1 || (is_apply && p.apply == 1)) return true;
+  return bytes < p.max_bytes;
+}
+#endif
 
 int allreduce_sum_f64(cmb_ctx* ctx, double* dev_ptr, size_t count);  // no-op when nranks == 1
 int allreduce_min_u64(cmb_ctx* ctx, unsigned long long* dev_ptr, size_t count);
@@ -342,6 +381,14 @@ __device__ __forceinline__ void bulk_load_1d_hint(void* dst, const void* src, ui
       "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+// Programmatic dependent launch.  A kernel launched with launch_pdl() may start while the kernel before it on the
+// stream is still draining: everything it does before grid_dependency_wait() must not depend on that kernel's output
+// (or on anything older kernels wrote that the previous one could still be writing).  Every CTA of such a kernel calls
+// grid_dependency_wait() before it reads or writes global memory other than read-only operator/basis data, and before
+// it exits.  grid_launch_dependents() lets the scheduler start the next kernel's CTAs as SMs free up; it is issued
+// after the kernel's own wait, so that a dependent's early work never overlaps the kernel two places back.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

@@ -172,6 +172,8 @@ heis_apply_kernel(HeisArgs a, HeisPass ps, const __grid_constant__ CUtensorMap t
   extern __shared__ __align__(128) unsigned char heis_smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(heis_smem + kHeisStages * kHeisTileBytes);
   uint64_t* empty = full + kHeisStages;
+  grid_dependency_wait();  // w, v of the earlier passes, the step scalars and the halt flag come from earlier kernels
+  grid_launch_dependents();
   double inv;
   if (!step_prologue(sc, inv)) return;  // idempotent: every pass of one apply takes the same decision
   const int tb = ps.tb;
@@ -746,8 +748,8 @@ struct HeisenbergOp : cmb_op {
       CMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeisSmem));                  \
       attr[use_siblings ? 1 : 0][ctx->device & 63] = true;                                                           \
     }                                                                                                                \
-    kern<<<grid, kHeisThreads, kHeisSmem, ctx->stream>>>(a, ps, tm, w, ucol, v, shr, shi, sc, ctx->d_partial,        \
-                                                         ctx->d_ticket + 1);                                         \
+    CMB_CUDA(launch_pdl(pdl_wanted(bytes, true), kern, grid, kHeisThreads, kHeisSmem, ctx->stream, a, ps, tm, w, ucol, v, shr, shi, sc,        \
+                        ctx->d_partial, ctx->d_ticket + 1));                                                         \
   } while (0)
       const int role = (ps.main ? 2 : 0) | (ps.rmw ? 1 : 0);
       if (cplx) {

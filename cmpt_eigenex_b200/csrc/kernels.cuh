@@ -47,6 +47,9 @@ struct CgsPass {
   int retry_tag = 0;
   double norm_guard = 1e-8;
   SlabPush slab;  // UPDATE_NORM only: n > 0 pushes the output to peer ranks (see SlabPush)
+  // The stream operation before this launch does not write the chunk's columns (it is another pass over the same
+  // basis): the kernel may fetch its first V tiles while that operation is still running (programmatic dependent launch).
+  bool v_stable = false;
 };
 enum { CGS_DOT = 0, CGS_UPDATE_DOT = 1, CGS_UPDATE_NORM = 2 };
 // stand-alone version of the slab push (the first apply of a run has no producing pass): w -> the peers' buffers

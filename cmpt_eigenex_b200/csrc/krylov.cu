@@ -162,6 +162,7 @@ static int gram_schmidt2_mailed(cmb_krylov* K, const Chunk& c, const double* x, 
   p.push = mail_next_push(ctx);
   const unsigned long long s1 = p.push.seq;
   CMB_TRY(cgs_pass(ctx, K->cplx, CGS_DOT, p));
+  p.v_stable = true;  // the passes below follow a pass over the same columns
   // pass 2: h1 = sum of partials ; y = x - V h1 ; partial h2 -> mailboxes
   // (also ||y||^2, so that the third pass needs no reduction of its own: ||y - V h2||^2 = ||y||^2 - |h2|^2)
   // The identity needs orthonormal columns: the Krylov vectors are (to rounding), user-supplied deflation vectors
@@ -218,6 +219,7 @@ static int gram_schmidt2(cmb_krylov* K, const std::vector<Chunk>& chunks, const 
     p.hin = nullptr;
     p.hout = K->h1 + off * es;
     CMB_TRY(cgs_pass(ctx, K->cplx, CGS_DOT, p));
+    p.v_stable = true;  // every later pass follows a pass (or a reduction) that leaves the basis alone
     off += chunks[i].ncols;
   }
   CMB_TRY(allreduce_sum_f64(ctx, K->h1, size_t(ctot) * es));
@@ -282,6 +284,7 @@ static int subtract_cols(cmb_krylov* K, const std::vector<Chunk>& chunks, const 
     p.hin = hin + off * K->es;
     p.hout = (i == nch - 1) ? nrm2_out : K->scal + 1;
     CMB_TRY(cgs_pass(K->ctx, K->cplx, CGS_UPDATE_NORM, p));
+    p.v_stable = true;
     off += chunks[i].ncols;
   }
   CMB_TRY(allreduce_sum_f64(K->ctx, nrm2_out, 1));

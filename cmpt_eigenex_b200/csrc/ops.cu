@@ -2,7 +2,8 @@
 // Lanczos alpha dot.  These replace the user `matmul` callback and the three lines around it
 // (lanczos.hpp:439-448, arnoldi.hpp:365-372): u = w/beta ; v = A u ; v += shift u ; alpha = <u|v>.
 //   - CSR input converted on the device to SELL-32 (32-row slices, column-major inside a slice):
-//     thread-per-row, fully coalesced value/index streams, x gathered through L1/L2;
+//     thread-per-row, fully coalesced value/index streams, x gathered through L1/L2; on request the rows of every
+//     1024-row window are sorted by length first (SELL-32-1024: almost no padding, but scattered gathers);
 //   - dense row-major GEMV (cfg 1), warp per row;
 //   - matrix-free spin-1/2 Heisenberg chain (cfg 5): heisenberg.cu;
 //   - legacy host callback (reference signature), staged through pinned host memory.
@@ -57,12 +58,17 @@ __device__ __forceinline__ bool sell_dist_prologue(const HaloPush& hpush, const 
   return true;
 }
 
-template <bool CPLX, bool DIST>
+// PERM: lane l of slice s works on row perm[32 s + l] (rows sorted by length inside 1024-row windows; -1 = no row).  The
+// vectors keep their natural order: the lanes of a warp read w and write u, v at 32 places of one 8 KB window.
+template <bool CPLX, bool DIST, bool PERM>
 __global__ void __launch_bounds__(256, 8)
 spmv_sell_kernel(const long long* __restrict__ slice_ptr, const int* __restrict__ col, const double* __restrict__ val,
-                 long long nrows, int nslices, const double* __restrict__ w, HaloPush hpush, HaloPull hp,
+                 const int* __restrict__ perm, long long nrows, int nslices, const double* __restrict__ w,
+                 HaloPush hpush, HaloPull hp,
                  const int* __restrict__ order, int n_interior, double* __restrict__ ucol, double* __restrict__ v,
                  double shr, double shi, StepScalars sc, double* partial, unsigned* ticket) {
+  grid_dependency_wait();  // w, the step scalars and the halt flag come from the kernels before this one
+  grid_launch_dependents();
   double inv;
   if (!step_prologue(sc, inv)) return;
   SellDist dist{0ull, 0, false};
@@ -74,7 +80,11 @@ spmv_sell_kernel(const long long* __restrict__ slice_ptr, const int* __restrict_
   auto body = [&](long long slice, const double* halo) {
     const long long base = slice_ptr[slice];
     const int width = int((slice_ptr[slice + 1] - base) >> 5);
-    const long long r = slice * 32 + lane;
+    long long r = slice * 32 + lane;
+    if (PERM) {
+      r = perm[r];
+      if (r < 0) r = nrows;
+    }
     const int* cp = col + base + lane;
     if (CPLX) {
       const double2* vp = reinterpret_cast<const double2*>(val) + base + lane;
@@ -145,6 +155,8 @@ spmv_sell_uniform_kernel(const int* __restrict__ col, const double* __restrict__
                          const double* __restrict__ w, HaloPush hpush, HaloPull hp, const int* __restrict__ order,
                          int n_interior, double* __restrict__ ucol, double* __restrict__ v, double shr,
                          StepScalars sc, double* partial, unsigned* ticket) {
+  grid_dependency_wait();  // w, the step scalars and the halt flag come from the kernels before this one
+  grid_launch_dependents();
   double inv;
   if (!step_prologue(sc, inv)) return;
   SellDist dist{0ull, 0, false};
@@ -204,12 +216,13 @@ __global__ void sell_halo_flag_kernel(const long long* __restrict__ slice_ptr, c
 
 // bad[0] is raised when the CSR arrays are inconsistent (decreasing rowptr, row longer than 2^31, column index outside
 // [0, ncols)): the build then fails with CMB_ERR_INVALID instead of leaving an operator that reads out of bounds.
-__global__ void sell_width_kernel(const long long* __restrict__ rowptr, long long nrows, long long nslices,
-                                  int* __restrict__ width, int* __restrict__ bad) {
+__global__ void sell_width_kernel(const long long* __restrict__ rowptr, const int* __restrict__ perm, long long nrows,
+                                  long long nslices, int* __restrict__ width, int* __restrict__ bad) {
   const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gwarp >= nslices) return;
-  const long long r = gwarp * 32 + lane;
+  long long r = gwarp * 32 + lane;
+  if (perm) r = perm[r] < 0 ? nrows : perm[r];
   const long long len64 = (r < nrows) ? rowptr[r + 1] - rowptr[r] : 0;
   if (len64 < 0 || len64 > 0x7fffffffll) *bad = 1;
   int len = (len64 < 0 || len64 > 0x7fffffffll) ? 0 : int(len64);
@@ -218,15 +231,36 @@ __global__ void sell_width_kernel(const long long* __restrict__ rowptr, long lon
   if (lane == 0) width[gwarp] = len;
 }
 
+// SELL-32-1024: one CTA sorts the rows of one 1024-row window by length, longest first, ties in row order (a stable
+// rank: every thread counts the rows that go before its own).  perm[position] = row, -1 behind the last row.
+constexpr int kSellSigma = 1024;
+__global__ void __launch_bounds__(kSellSigma)
+sell_sort_window_kernel(const long long* __restrict__ rowptr, long long nrows, int* __restrict__ perm) {
+  __shared__ int s_len[kSellSigma];
+  const long long r = (long long)blockIdx.x * kSellSigma + threadIdx.x;
+  long long len64 = (r < nrows) ? rowptr[r + 1] - rowptr[r] : -1;
+  if (len64 > 0x7fffffffll) len64 = 0x7fffffffll;  // reported as an error by sell_width_kernel
+  const int len = len64 < -1 ? -1 : int(len64);
+  s_len[threadIdx.x] = len;
+  __syncthreads();
+  int rank = 0;
+  for (int j = 0; j < kSellSigma; ++j) {
+    const int lj = s_len[j];
+    rank += (lj > len || (lj == len && j < int(threadIdx.x))) ? 1 : 0;
+  }
+  perm[(long long)blockIdx.x * kSellSigma + rank] = (r < nrows) ? int(r) : -1;
+}
+
 template <int ES>
 __global__ void sell_fill_kernel(const long long* __restrict__ rowptr, const int* __restrict__ col,
-                                 const double* __restrict__ val, long long nrows, long long nslices,
-                                 const long long* __restrict__ slice_ptr, int* __restrict__ scol,
+                                 const double* __restrict__ val, const int* __restrict__ perm, long long nrows,
+                                 long long nslices, const long long* __restrict__ slice_ptr, int* __restrict__ scol,
                                  double* __restrict__ sval, long long ncols, int* __restrict__ bad) {
   const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gwarp >= nslices) return;
-  const long long r = gwarp * 32 + lane;
+  long long r = gwarp * 32 + lane;
+  if (perm) r = perm[r] < 0 ? nrows : perm[r];
   const long long base = slice_ptr[gwarp];
   const int width = int((slice_ptr[gwarp + 1] - base) >> 5);
   long long p0 = 0;
@@ -258,6 +292,7 @@ struct SellOp : cmb_op {
   int* d_col = nullptr;
   double* d_val = nullptr;
   HaloExchange* halo = nullptr;  // row-partitioned shards only
+  int* d_perm = nullptr;         // SELL-32-1024: row handled by each lane of each slice (nullptr: natural order)
   int* d_order = nullptr;        // peer-memory halo: slices that touch no remote column first
   long long n_interior = 0;
   int resident_ctas = 0;         // CTAs of the SpMV kernel that fit on the GPU at once (queried on first use)
@@ -268,6 +303,7 @@ struct SellOp : cmb_op {
     pool_free(ctx, d_col);
     pool_free(ctx, d_val);
     pool_free(ctx, d_order);
+    pool_free(ctx, d_perm);
     delete halo;
   }
   int apply(const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) override {
@@ -289,7 +325,7 @@ struct SellOp : cmb_op {
           // start before others finish would never push): cap the grid by the measured occupancy.
           if (resident_ctas == 0) {
             int per_sm = 0;
-            CMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_sell_kernel<true, true>, 256, 0));
+            CMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_sell_kernel<true, true, true>, 256, 0));
             resident_ctas = std::max(1, per_sm) * ctx->num_sms;
           }
           grid = std::min(grid, resident_ctas);
@@ -306,14 +342,13 @@ struct SellOp : cmb_op {
 #define CMB_SELL_UNIFORM(W)                                                                                        \
   case W:                                                                                                          \
     if (halo)                                                                                                      \
-      spmv_sell_uniform_kernel<W, true><<<grid, 256, 0, ctx->stream>>>(d_col, d_val, n_local, int(nslices), w, d_push,  \
-                                                                       d_halo, d_order, int(n_interior), ucol, v, shr,  \
-                                                                       sc, ctx->d_partial, ctx->d_ticket + 1);     \
+      CMB_CUDA(launch_pdl(pdl_wanted(bytes, true), spmv_sell_uniform_kernel<W, true>, grid, 256, 0, ctx->stream, d_col, d_val, n_local,     \
+                          int(nslices), w, d_push, d_halo, d_order, int(n_interior), ucol, v, shr, sc,             \
+                          ctx->d_partial, ctx->d_ticket + 1));                                                     \
     else                                                                                                           \
-      spmv_sell_uniform_kernel<W, false><<<grid, 256, 0, ctx->stream>>>(d_col, d_val, n_local, int(nslices), w, d_push, \
-                                                                        d_halo, d_order, int(n_interior), ucol, v, shr, \
-                                                                        sc, ctx->d_partial, ctx->d_ticket + 1);    \
-    CMB_CUDA(cudaGetLastError());                                                                                  \
+      CMB_CUDA(launch_pdl(pdl_wanted(bytes, true), spmv_sell_uniform_kernel<W, false>, grid, 256, 0, ctx->stream, d_col, d_val, n_local,    \
+                          int(nslices), w, d_push, d_halo, d_order, int(n_interior), ucol, v, shr, sc,             \
+                          ctx->d_partial, ctx->d_ticket + 1));                                                     \
     return CMB_OK;
     if (!cplx && shi == 0.0) {
       switch (uniform_width) {
@@ -332,9 +367,16 @@ struct SellOp : cmb_op {
     }
 #undef CMB_SELL_UNIFORM
 #define CMB_SELL_GENERIC(C, D)                                                                                    \
-  spmv_sell_kernel<C, D><<<grid, 256, 0, ctx->stream>>>(d_slice_ptr, d_col, d_val, n_local, int(nslices), w, d_push,    \
-                                                        d_halo, d_order, int(n_interior), ucol, v, shr, shi, sc,        \
-                                                        ctx->d_partial, ctx->d_ticket + 1)
+  do {                                                                                                            \
+    if (d_perm)                                                                                                   \
+      CMB_CUDA(launch_pdl(pdl_wanted(bytes, true), spmv_sell_kernel<C, D, true>, grid, 256, 0, ctx->stream, d_slice_ptr, d_col, d_val,     \
+                          d_perm, n_local, int(nslices), w, d_push, d_halo, d_order, int(n_interior), ucol, v,    \
+                          shr, shi, sc, ctx->d_partial, ctx->d_ticket + 1));                                      \
+    else                                                                                                          \
+      CMB_CUDA(launch_pdl(pdl_wanted(bytes, true), spmv_sell_kernel<C, D, false>, grid, 256, 0, ctx->stream, d_slice_ptr, d_col, d_val,    \
+                          d_perm, n_local, int(nslices), w, d_push, d_halo, d_order, int(n_interior), ucol, v,    \
+                          shr, shi, sc, ctx->d_partial, ctx->d_ticket + 1));                                      \
+  } while (0)
     if (cplx) {
       if (halo)
         CMB_SELL_GENERIC(true, true);
@@ -405,31 +447,63 @@ static int build_sell(SellOp* op, const CsrOnDevice& csr, long long ncols) {
     const int threads = 256;
     const long long nthreads = op->nslices * 32;
     const int grid = int((nthreads + threads - 1) / threads);
-    if (op->nslices > 0) {
-      LaunchScope ls(ctx, "sell_build");
-      sell_width_kernel<<<grid, threads, 0, ctx->stream>>>(d_rowptr, n, op->nslices, d_width, d_bad);
-    }
-    CMB_CUDA(cudaGetLastError());
     std::vector<int> width(op->nslices);
-    int bad = 0;
-    CMB_CUDA(cudaMemcpyAsync(width.data(), d_width, sizeof(int) * op->nslices, cudaMemcpyDeviceToHost, ctx->stream));
-    CMB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (bad) {
-      set_error("CSR rowptr is not non-decreasing (or a row is longer than 2^31 entries)");
-      return CMB_ERR_INVALID;
-    }
+    // slice widths for the current row order (op->d_perm), validated; fills `width` and returns the padded size
+    auto measure = [&](long long* padded) -> int {
+      if (op->nslices > 0) {
+        LaunchScope ls(ctx, "sell_build");
+        sell_width_kernel<<<grid, threads, 0, ctx->stream>>>(d_rowptr, op->d_perm, n, op->nslices, d_width, d_bad);
+      }
+      CMB_CUDA(cudaGetLastError());
+      int bad = 0;
+      CMB_CUDA(cudaMemcpyAsync(width.data(), d_width, sizeof(int) * op->nslices, cudaMemcpyDeviceToHost, ctx->stream));
+      CMB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (bad) {
+        set_error("CSR rowptr is not non-decreasing (or a row is longer than 2^31 entries)");
+        return CMB_ERR_INVALID;
+      }
+      *padded = 0;
+      for (long long s = 0; s < op->nslices; ++s) *padded += (long long)width[s] * 32;
+      return CMB_OK;
+    };
+    long long padded = 0;
+    CMB_TRY(measure(&padded));
     // stencil-like matrices: pad every slice to the maximum width when that costs < 5 % extra entries, which
     // enables the fully unrolled uniform-width kernel
     int maxw = 0;
     for (long long s = 0; s < op->nslices; ++s) maxw = std::max(maxw, width[s]);
-    if (maxw >= 1 && maxw <= 9 && double(maxw) * 32.0 * double(op->nslices) <= 1.05 * double(std::max<long long>(nnz, 1)))
+    const bool stencil =
+        maxw >= 1 && maxw <= 9 && double(maxw) * 32.0 * double(op->nslices) <= 1.05 * double(std::max<long long>(nnz, 1));
+    if (stencil) {
       for (long long s = 0; s < op->nslices; ++s) width[s] = maxw;
+    } else if (double(padded) > 1.05 * double(std::max<long long>(nnz, 1)) && getenv("CMPT_B200_SELL_SORT") &&
+               atoi(getenv("CMPT_B200_SELL_SORT")) != 0) {
+      // Irregular rows, on request (CMPT_B200_SELL_SORT=1): sort every 1024-row window by length and keep the order if
+      // it saves padding.  Off by default: for the Heisenberg ring (cfg 4) it cuts the stored entries from 1.25 nnz to
+      // 1.02 nnz but the SpMV gets 19 % slower (1.23 ms against 1.03 ms at L = 24), because neighbouring lanes no
+      // longer gather neighbouring entries of x — that kernel is bound by the gathers, not by the matrix stream.
+      const long long nwin = (n + kSellSigma - 1) / kSellSigma;
+      CMB_TRY(pool_alloc(ctx, &op->d_perm, sizeof(int) * size_t(std::max<long long>(nwin * kSellSigma, op->nslices * 32))));
+      {
+        LaunchScope ls(ctx, "sell_build");
+        sell_sort_window_kernel<<<unsigned(nwin), kSellSigma, 0, ctx->stream>>>(d_rowptr, n, op->d_perm);
+      }
+      CMB_CUDA(cudaGetLastError());
+      const long long natural = padded;
+      std::vector<int> natural_width = width;
+      CMB_TRY(measure(&padded));
+      if (padded >= natural) {
+        pool_free(ctx, op->d_perm);
+        op->d_perm = nullptr;
+        width = natural_width;
+      }
+    }
     std::vector<long long> sp(op->nslices + 1);
     sp[0] = 0;
     for (long long s = 0; s < op->nslices; ++s) sp[s + 1] = sp[s] + (long long)width[s] * 32;
     op->padded_nnz = sp[op->nslices];
-    op->uniform_width = (op->nslices > 0) ? width[0] : 0;
+    op->uniform_width = (op->nslices > 0 && !op->d_perm) ? width[0] : 0;
     for (long long s = 0; s < op->nslices; ++s)
       if (width[s] != op->uniform_width) {
         op->uniform_width = 0;
@@ -443,13 +517,14 @@ static int build_sell(SellOp* op, const CsrOnDevice& csr, long long ncols) {
     if (op->nslices > 0) {
       LaunchScope ls(ctx, "sell_build");
       if (es == 2)
-        sell_fill_kernel<2><<<grid, threads, 0, ctx->stream>>>(d_rowptr, d_ccol, d_cval, n, op->nslices,
+        sell_fill_kernel<2><<<grid, threads, 0, ctx->stream>>>(d_rowptr, d_ccol, d_cval, op->d_perm, n, op->nslices,
                                                                op->d_slice_ptr, op->d_col, op->d_val, ncols, d_bad);
       else
-        sell_fill_kernel<1><<<grid, threads, 0, ctx->stream>>>(d_rowptr, d_ccol, d_cval, n, op->nslices,
+        sell_fill_kernel<1><<<grid, threads, 0, ctx->stream>>>(d_rowptr, d_ccol, d_cval, op->d_perm, n, op->nslices,
                                                                op->d_slice_ptr, op->d_col, op->d_val, ncols, d_bad);
     }
     CMB_CUDA(cudaGetLastError());
+    int bad = 0;
     CMB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CMB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (bad) {
@@ -789,6 +864,16 @@ int cmb_op_dtype(const cmb_op* op) { return op ? op->dtype : -1; }
 double cmb_op_bytes(const cmb_op* op) { return op ? op->bytes : 0.0; }
 
 // diagnostic (cmpt_b200_debug.h): number of halo exchanges this rank's CSR shard has completed (-1: no peer-memory halo)
+int cmb_debug_op_sell_stats(cmb_op* op, long long* nnz, long long* padded, int* sorted) {
+  CMB_REQUIRE(op && nnz && padded && sorted, "null argument");
+  SellOp* s = dynamic_cast<SellOp*>(op);
+  CMB_REQUIRE(s, "not a CSR (SELL) operator");
+  *nnz = s->nnz;
+  *padded = s->padded_nnz;
+  *sorted = s->d_perm ? 1 : 0;
+  return CMB_OK;
+}
+
 int cmb_debug_op_exchange_count(cmb_op* op, long long* count) {
   CMB_REQUIRE(op && count, "null argument");
   *count = -1;

@@ -245,6 +245,12 @@ class DeviceOperator:
     def bytes(self):
         return float(lib().cmb_op_bytes(self.h))
 
+    def sell_stats(self):
+        """CSR operators: (nnz, stored entries incl. padding, rows sorted inside 1024-row windows?)"""
+        nnz, padded, srt = C.c_longlong(), C.c_longlong(), C.c_int()
+        check(lib().cmb_debug_op_sell_stats(self.h, C.byref(nnz), C.byref(padded), C.byref(srt)))
+        return int(nnz.value), int(padded.value), bool(srt.value)
+
     def apply(self, x):
         x = np.ascontiguousarray(x, dtype=self.dtype)
         y = np.empty_like(x)

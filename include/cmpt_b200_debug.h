@@ -41,6 +41,9 @@ int cmb_ctx_set_spin_timeout(cmb_ctx* ctx, double seconds);
  * kernels and packing as real ranks, the NVLink exchange replaced by device copies); x, y: full 2^L host vectors */
 int cmb_debug_heisenberg_virtual(cmb_ctx* ctx, cmb_dtype dtype, int L, double J, int pbc, int nranks, const void* x,
                                  void* y);
+/* storage of a CSR operator after the conversion to SELL-32: entries of the matrix, entries stored (with padding), and
+ * whether the rows were sorted by length inside 1024-row windows (SELL-32-1024) */
+int cmb_debug_op_sell_stats(cmb_op* op, long long* nnz, long long* padded, int* sorted);
 /* number of halo exchanges the CSR shard of this rank has completed (-1 when it has no peer-memory halo) */
 int cmb_debug_op_exchange_count(cmb_op* op, long long* count);
 /* mean device time of one Gram-Schmidt pass (mode 0 DOT, 1 UPDATE_DOT, 2 UPDATE_NORM) over the first ncols columns

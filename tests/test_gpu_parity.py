@@ -62,6 +62,66 @@ def test_csr_apply_matches_oracle(ctx, name):
     assert op.bytes == syn.csr_bytes(n, rp[-1], v.dtype.itemsize)
 
 
+# SELL-32-1024 (CMPT_B200_SELL_SORT=1): rows sorted by length inside 1024-row windows when the natural order would pad
+# more than 5 %.  Opt-in: it removes the padding but scatters the gathers (slower on the Heisenberg matrices).
+@pytest.mark.parametrize("case", ["heisenberg14", "heisenberg13_open", "ragged_real", "ragged_complex", "short_tail"])
+def test_csr_rows_sorted_by_length_inside_windows(ctx, monkeypatch, case):
+    rng = np.random.default_rng(17)
+    if case == "heisenberg14":
+        rp, c, v = syn.heisenberg_csr(14)
+    elif case == "heisenberg13_open":
+        rp, c, v = syn.heisenberg_csr(13, pbc=False)
+    else:
+        n = {"ragged_real": 5000 + 3, "ragged_complex": 2048 + 31, "short_tail": 1024 + 1}[case]
+        lens = rng.integers(0, 40, size=n)
+        lens[rng.integers(0, n, size=5)] = 200
+        rp = np.zeros(n + 1, np.int64)
+        np.cumsum(lens, out=rp[1:])
+        c = rng.integers(0, n, size=rp[-1]).astype(np.int32)
+        v = rng.normal(size=rp[-1])
+        if case == "ragged_complex":
+            v = v + 1j * rng.normal(size=rp[-1])
+    n = rp.size - 1
+    x = syn.start_vector(n, seed=4, dtype=v.dtype)
+    yr = core.Operator.csr(rp, c, v).apply(x)
+    monkeypatch.setenv("CMPT_B200_SELL_SORT", "1")
+    op = pkg.DeviceOperator.from_csr(ctx, rp, c, v)
+    nnz, padded, srt = op.sell_stats()
+    assert nnz == rp[-1] and srt
+    y = op.apply(x)
+    np.testing.assert_allclose(y, yr, rtol=0, atol=1e-14 * max(1.0, np.abs(yr).max()) * 8)
+    a_sorted = None
+    if case.startswith("heisenberg"):  # whole solver steps on the sorted operator
+        es = pkg.LanczosEigenSolver()
+        es.setMatrixMultiplication(op).setInitialVector(x).setMinIterations(8).setMaxIterations(8).setMaxEigenvalues(1)
+        es.compute()
+        a_sorted = es.alpha().copy()
+        es.close()
+    op.close()
+    monkeypatch.delenv("CMPT_B200_SELL_SORT")
+    op2 = pkg.DeviceOperator.from_csr(ctx, rp, c, v)
+    nnz2, padded2, srt2 = op2.sell_stats()
+    assert not srt2 and padded < padded2
+    np.testing.assert_allclose(op2.apply(x), yr, rtol=0, atol=1e-14 * max(1.0, np.abs(yr).max()) * 8)
+    if a_sorted is not None:  # the same Lanczos coefficients either way
+        es = pkg.LanczosEigenSolver()
+        es.setMatrixMultiplication(op2).setInitialVector(x).setMinIterations(8).setMaxIterations(8).setMaxEigenvalues(1)
+        es.compute()
+        np.testing.assert_allclose(es.alpha(), a_sorted, atol=1e-12)
+        es.close()
+    op2.close()
+    if case.startswith("heisenberg"):
+        assert padded <= 1.03 * nnz < padded2  # natural order pads ~20 %; the window sort leaves the odd slice per window
+
+
+def test_csr_stencils_keep_the_natural_row_order(ctx):
+    rp, c, v = syn.laplacian2d_csr(64)
+    op = pkg.DeviceOperator.from_csr(ctx, rp, c, v)
+    nnz, padded, srt = op.sell_stats()
+    assert not srt and padded <= 1.05 * nnz
+    op.close()
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128])
 def test_dense_and_matrix_free_apply(ctx, dtype):
     rng = np.random.default_rng(1)
