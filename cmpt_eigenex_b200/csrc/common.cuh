@@ -198,25 +198,21 @@ inline cudaError_t launch_pdl(bool overlap, void (*kern)(KArgs...), int grid, in
   cfg.numAttrs = overlap ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
-// Policy: which launches overlap with their predecessor.  `bytes` = what the kernel streams.  CMPT_B200_PDL=0 none,
-// =1 all; CMPT_B200_PDL_MAX_MB limits it to kernels that stream less than that (their duration is comparable with the
-// launch latency the overlap hides); CMPT_B200_PDL_APPLY=0/1 excludes/includes the operator kernels.
-inline bool pdl_wanted(double bytes, bool is_apply) {
+// Policy: which launches overlap with their predecessor.  Measured on B200 (profiles/r2/pdl_and_sell_sort.md): on the
+// Gram-Schmidt passes the overlap is worth +14 % when the kernels last ~10 us, +1.4 % at ~100 us and nothing at 1 ms; on
+// the operator kernels it costs 1-2 % (their early CTAs start ahead of the rest and unbalance the static slice split).
+// So: passes always, operator kernels only on request.  CMPT_B200_PDL=0 turns it off, CMPT_B200_PDL_APPLY=1 adds the
+// operator kernels.
+inline bool pdl_wanted(bool is_apply) {
   struct Policy {
-    int mode = -1;  // -1 by size
-    double max_bytes = 16.0 * 1048576.0;
-    int apply = -1;  // -1: same rule as the Gram-Schmidt passes
+    bool on = true, apply = false;
     Policy() {
-      if (const char* e = getenv("CMPT_B200_PDL")) mode = atoi(e) != 0 ? 1 : 0;
-      if (const char* e = getenv("CMPT_B200_PDL_MAX_MB")) max_bytes = atof(e) * 1048576.0;
-      if (const char* e = getenv("CMPT_B200_PDL_APPLY")) apply = atoi(e) != 0 ? 1 : 0;
+      if (const char* e = getenv("CMPT_B200_PDL")) on = atoi(e) != 0;
+      if (const char* e = getenv("CMPT_B200_PDL_APPLY")) apply = atoi(e) != 0;
     }
   };
   static const Policy p;
-  if (p.mode == 0) return false;
-  if (is_apply && p.apply == 0) return false;
-  if (p.mode == 1 || (is_apply && p.apply == 1)) return true;
-  return bytes < p.max_bytes;
+  return p.on && (!is_apply || p.apply);
 }
 #endif
 
