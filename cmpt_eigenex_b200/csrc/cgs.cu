@@ -486,7 +486,7 @@ static int launch_cfg(cmb_ctx* ctx, const CgsPass& a, int cg) {
   static const char* fam[3] = {"cgs_dot", "cgs_update_dot", "cgs_update_norm"};
   {
     LaunchScope ls(ctx, a.family ? a.family : fam[MODE]);
-    CMB_CUDA(launch_pdl(pdl_wanted(false), kern, grid, kThreads, smem, ctx->stream, tm, a.x, a.y, a.hin, a.hout, ctx->d_partial, ctx->d_ticket,
+    CMB_CUDA(launch_pdl(pdl_wanted(false, ctx->nranks), kern, grid, kThreads, smem, ctx->stream, tm, a.x, a.y, a.hin, a.hout, ctx->d_partial, ctx->d_ticket,
                         a.halt, a.ncols, cg, ntiles, stages, a.pull, a.push, a.norm_trick, a.retry, a.retry_tag,
                         a.norm_guard, a.slab, a.v_stable ? 1 : 0));
   }

@@ -201,18 +201,20 @@ inline cudaError_t launch_pdl(bool overlap, void (*kern)(KArgs...), int grid, in
 // Policy: which launches overlap with their predecessor.  Measured on B200 (profiles/r2/pdl_and_sell_sort.md): on the
 // Gram-Schmidt passes the overlap is worth +14 % when the kernels last ~10 us, +1.4 % at ~100 us and nothing at 1 ms; on
 // the operator kernels it costs 1-2 % (their early CTAs start ahead of the rest and unbalance the static slice split).
-// So: passes always, operator kernels only on request.  CMPT_B200_PDL=0 turns it off, CMPT_B200_PDL_APPLY=1 adds the
-// operator kernels.
-inline bool pdl_wanted(bool is_apply) {
+// Row-partitioned over 8 GPUs (cfg 2) the run with the overlap was 2 % slower than without (2 019 against 2 064 it/s).
+// So: single-rank passes always, operator kernels and multi-rank runs only on request.  CMPT_B200_PDL=0 turns it off,
+// CMPT_B200_PDL_APPLY=1 adds the operator kernels, CMPT_B200_PDL_RANKS=1 the row-partitioned runs.
+inline bool pdl_wanted(bool is_apply, int nranks) {
   struct Policy {
-    bool on = true, apply = false;
+    bool on = true, apply = false, ranks = false;
     Policy() {
       if (const char* e = getenv("CMPT_B200_PDL")) on = atoi(e) != 0;
       if (const char* e = getenv("CMPT_B200_PDL_APPLY")) apply = atoi(e) != 0;
+      if (const char* e = getenv("CMPT_B200_PDL_RANKS")) ranks = atoi(e) != 0;
     }
   };
   static const Policy p;
-  return p.on && (!is_apply || p.apply);
+  return p.on && (!is_apply || p.apply) && (nranks == 1 || p.ranks);
 }
 #endif
 

@@ -748,7 +748,7 @@ struct HeisenbergOp : cmb_op {
       CMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeisSmem));                  \
       attr[use_siblings ? 1 : 0][ctx->device & 63] = true;                                                           \
     }                                                                                                                \
-    CMB_CUDA(launch_pdl(pdl_wanted(true), kern, grid, kHeisThreads, kHeisSmem, ctx->stream, a, ps, tm, w, ucol, v, shr, shi, sc,        \
+    CMB_CUDA(launch_pdl(pdl_wanted(true, ctx->nranks), kern, grid, kHeisThreads, kHeisSmem, ctx->stream, a, ps, tm, w, ucol, v, shr, shi, sc,        \
                         ctx->d_partial, ctx->d_ticket + 1));                                                         \
   } while (0)
       const int role = (ps.main ? 2 : 0) | (ps.rmw ? 1 : 0);

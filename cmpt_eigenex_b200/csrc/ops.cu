@@ -342,11 +342,11 @@ struct SellOp : cmb_op {
 #define CMB_SELL_UNIFORM(W)                                                                                        \
   case W:                                                                                                          \
     if (halo)                                                                                                      \
-      CMB_CUDA(launch_pdl(pdl_wanted(true), spmv_sell_uniform_kernel<W, true>, grid, 256, 0, ctx->stream, d_col, d_val, n_local,     \
+      CMB_CUDA(launch_pdl(pdl_wanted(true, ctx->nranks), spmv_sell_uniform_kernel<W, true>, grid, 256, 0, ctx->stream, d_col, d_val, n_local,     \
                           int(nslices), w, d_push, d_halo, d_order, int(n_interior), ucol, v, shr, sc,             \
                           ctx->d_partial, ctx->d_ticket + 1));                                                     \
     else                                                                                                           \
-      CMB_CUDA(launch_pdl(pdl_wanted(true), spmv_sell_uniform_kernel<W, false>, grid, 256, 0, ctx->stream, d_col, d_val, n_local,    \
+      CMB_CUDA(launch_pdl(pdl_wanted(true, ctx->nranks), spmv_sell_uniform_kernel<W, false>, grid, 256, 0, ctx->stream, d_col, d_val, n_local,    \
                           int(nslices), w, d_push, d_halo, d_order, int(n_interior), ucol, v, shr, sc,             \
                           ctx->d_partial, ctx->d_ticket + 1));                                                     \
     return CMB_OK;
@@ -369,11 +369,11 @@ struct SellOp : cmb_op {
 #define CMB_SELL_GENERIC(C, D)                                                                                    \
   do {                                                                                                            \
     if (d_perm)                                                                                                   \
-      CMB_CUDA(launch_pdl(pdl_wanted(true), spmv_sell_kernel<C, D, true>, grid, 256, 0, ctx->stream, d_slice_ptr, d_col, d_val,     \
+      CMB_CUDA(launch_pdl(pdl_wanted(true, ctx->nranks), spmv_sell_kernel<C, D, true>, grid, 256, 0, ctx->stream, d_slice_ptr, d_col, d_val,     \
                           d_perm, n_local, int(nslices), w, d_push, d_halo, d_order, int(n_interior), ucol, v,    \
                           shr, shi, sc, ctx->d_partial, ctx->d_ticket + 1));                                      \
     else                                                                                                          \
-      CMB_CUDA(launch_pdl(pdl_wanted(true), spmv_sell_kernel<C, D, false>, grid, 256, 0, ctx->stream, d_slice_ptr, d_col, d_val,    \
+      CMB_CUDA(launch_pdl(pdl_wanted(true, ctx->nranks), spmv_sell_kernel<C, D, false>, grid, 256, 0, ctx->stream, d_slice_ptr, d_col, d_val,    \
                           d_perm, n_local, int(nslices), w, d_push, d_halo, d_order, int(n_interior), ucol, v,    \
                           shr, shi, sc, ctx->d_partial, ctx->d_ticket + 1));                                      \
   } while (0)
