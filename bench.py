@@ -568,19 +568,25 @@ def run_ours(args):
             barrier()
             t0 = time.perf_counter()
             op2 = wl.make_operator(pkg, ctx, host, r0)
+            t1 = time.perf_counter()
             es2.setMatrixMultiplication(op2).setInitialVector(px.array)
+            t2 = time.perf_counter()
             es2.compute()
+            t3 = time.perf_counter()
             ev = es2.eigenvalues()
             X = es2.eigenvectors(copy=False)
             chk = complex(X[0, 0]) + complex(ev[0])  # touch the host results
+            t4 = time.perf_counter()
             op2.close()
             ctx.sync()
             dt = time.perf_counter() - t0
             barrier()
             if i >= args.warmup:
                 times.append(dt)
-            if os.environ.get("BENCH_DEBUG"):
-                print("e2e iter %d: %.1f ms" % (i, dt * 1e3), file=sys.stderr, flush=True)
+            if os.environ.get("BENCH_DEBUG") and rank == 0:
+                print("e2e iter %d: %.1f ms = operator build %.1f + start vector %.1f + compute %.1f + results to host %.1f "
+                      "+ close %.1f" % (i, dt * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3,
+                                        (dt - (t4 - t0)) * 1e3), file=sys.stderr, flush=True)
             del chk, X
         tot = max_over_ranks(sum(times))
         e2e = {"value": m * len(times) / tot, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -86,6 +86,7 @@ def _declare(L):
         "cmb_krylov_clear": (i32, [vp]),
         "cmb_krylov_set_deflation": (i32, [vp, i64, vp, i64]),
         "cmb_krylov_start": (i32, [vp, vp, dbl, P(i32)]),
+        "cmb_krylov_restart": (i32, [vp, dbl, P(i32)]),
         "cmb_krylov_ncols": (i64, [vp]),
         "cmb_krylov_rows": (i64, [vp]),
         "cmb_krylov_get_col": (i32, [vp, i64, vp]),

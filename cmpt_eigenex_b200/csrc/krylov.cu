@@ -49,6 +49,7 @@ struct cmb_krylov {
   size_t h_stage_elems = 0;
   bool started = false;
   unsigned long long nrm2_seq = 0;  // non-zero: ||w||^2 is the mailbox reduction with this sequence number
+  double* d_start = nullptr;        // the start vector of the last cmb_krylov_start (for cmb_krylov_restart)
   bool w_pushed = false;            // the pass that wrote w also pushed it to the partner ranks (SlabPush)
   bool resume_norm_ready = false;   // w is orthogonalised and scal[0] holds its explicitly reduced norm (guard retry)
   double residue = 0.0;  // Arnoldi: last residual norm (host copy)
@@ -414,6 +415,7 @@ int cmb_krylov_destroy(cmb_krylov* K) {
   dfree(K->ctx, K->w);
   pool_free(K->ctx, K->h1);
   pool_free(K->ctx, K->h2);
+  pool_free(K->ctx, K->d_start);
   cudaStreamSynchronize(K->ctx->stream);
   dfree(K->ctx, K->scal);
   dfree(K->ctx, K->halt);
@@ -462,8 +464,8 @@ int cmb_krylov_set_deflation(cmb_krylov* K, int64_t nvec, const void* vecs, int6
   return CMB_OK;
 }
 
-int cmb_krylov_start(cmb_krylov* K, const void* init, double threshold, int* status) {
-  CMB_REQUIRE(K && init && status, "null argument");
+// init: host vector, or nullptr = the copy of the previous start vector kept in K->d_start
+static int krylov_start(cmb_krylov* K, const void* init, double threshold, int* status) {
   cmb_ctx* ctx = K->ctx;
   CMB_CUDA(cudaSetDevice(ctx->device));
   K->nk = 0;
@@ -472,7 +474,11 @@ int cmb_krylov_start(cmb_krylov* K, const void* init, double threshold, int* sta
   K->w_pushed = false;
   K->residue = 0.0;
   CMB_CUDA(cudaMemsetAsync(K->halt, 0, sizeof(int) * 4, ctx->stream));
-  CMB_CUDA(cudaMemcpyAsync(K->w, init, sizeof(double) * K->nd_local, cudaMemcpyHostToDevice, ctx->stream));
+  if (init) {
+    if (!K->d_start) CMB_TRY(pool_alloc(ctx, &K->d_start, sizeof(double) * std::max<int64_t>(K->nd_local, 2)));
+    CMB_CUDA(cudaMemcpyAsync(K->d_start, init, sizeof(double) * K->nd_local, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CMB_CUDA(cudaMemcpyAsync(K->w, K->d_start, sizeof(double) * K->nd_local, cudaMemcpyDeviceToDevice, ctx->stream));
   if (K->ndefl > 0) {
     // lanczos.hpp:312-314: project the deflation vectors out of the start vector
     std::vector<Chunk> chunks;
@@ -493,6 +499,17 @@ int cmb_krylov_start(cmb_krylov* K, const void* init, double threshold, int* sta
   K->started = true;
   *status = CMB_STEP_OK;
   return CMB_OK;
+}
+
+int cmb_krylov_start(cmb_krylov* K, const void* init, double threshold, int* status) {
+  CMB_REQUIRE(K && init && status, "null argument");
+  return krylov_start(K, init, threshold, status);
+}
+
+int cmb_krylov_restart(cmb_krylov* K, double threshold, int* status) {
+  CMB_REQUIRE(K && status, "null argument");
+  CMB_REQUIRE(K->d_start, "cmb_krylov_restart needs an earlier cmb_krylov_start on this state");
+  return krylov_start(K, nullptr, threshold, status);
 }
 
 int64_t cmb_krylov_ncols(const cmb_krylov* K) { return K ? K->nk : 0; }

@@ -101,6 +101,7 @@ class ArnoldiBase {
   Scalar eigenvalueShift_;
   Index matrixHeight_;
   VectorType initialVector_;
+  std::uint64_t initialVersion_ = 1;  // bumped by every setInitialVector: the device keeps the last uploaded version
   RealScalar threshold_;
 
  public:
@@ -154,15 +155,18 @@ class ArnoldiBase {
   const VectorType& initialVector() const { return initialVector_; }
   ArnoldiBase& setInitialVector(const VectorType& inivec) {
     initialVector_ = inivec;
+    ++initialVersion_;
     return *this;
   }
   ArnoldiBase& setInitialVector(VectorType&& inivec) {
     initialVector_ = std::move(inivec);
+    ++initialVersion_;
     return *this;
   }
   /// additive: copy n scalars straight into the (pinned, reused) start-vector storage
   ArnoldiBase& setInitialVector(const Scalar* data, Index n) {
     detail::assign_upload(initialVector_, data, n);
+    ++initialVersion_;
     return *this;
   }
   ArnoldiBase& setInitialVector() {  // arnoldi.hpp:162-166
@@ -263,7 +267,7 @@ class ArnoldiBase {
       if (localHeight() != static_cast<Index>(initialVector_.size())) setInitialVector();
       dev_.setDeflation(orthogonalizingVectors_, localHeight());
       int st = 0;
-      detail::check(cmb_krylov_start(dev_.handle(), initialVector_.data(), threshold_, &st), "cmb_krylov_start");
+      dev_.start(initialVector_, initialVersion_, threshold_, &st);
       if (st != CMB_STEP_OK) return 0;
     } else if (arnoldiStepIsUtmost()) {
       return 0;

@@ -3,6 +3,7 @@
 #ifndef CMPT_EIGEN_EX_DETAIL_KRYLOV_DEVICE_HPP_
 #define CMPT_EIGEN_EX_DETAIL_KRYLOV_DEVICE_HPP_
 
+#include <cstdint>
 #include <exception>
 #include <functional>
 #include <memory>
@@ -32,6 +33,7 @@ class KrylovDevice {
   void release() {
     if (k_) cmb_krylov_destroy(k_);
     k_ = nullptr;
+    startVersion_ = 0;
     op_ = DeviceOperator<Scalar>();
     bridge_.reset();
   }
@@ -85,6 +87,18 @@ class KrylovDevice {
           "cmb_krylov_set_deflation");
   }
 
+  /// Starts the chain from `init`.  `version` identifies its contents (the solver bumps it whenever the start vector is
+  /// set): a state that already holds that version in HBM starts from its own copy, without a host-to-device transfer.
+  void start(const VectorType& init, std::uint64_t version, double threshold, int* status) {
+    if (version != 0 && version == startVersion_) {
+      check(cmb_krylov_restart(k_, threshold, status), "cmb_krylov_restart");
+      return;
+    }
+    startVersion_ = 0;
+    check(cmb_krylov_start(k_, init.data(), threshold, status), "cmb_krylov_start");
+    startVersion_ = version;
+  }
+
   void rethrowCallbackError() {
     if (bridge_ && bridge_->err) {
       std::exception_ptr e = bridge_->err;
@@ -112,6 +126,7 @@ class KrylovDevice {
   }
 
   cmb_krylov* k_ = nullptr;
+  std::uint64_t startVersion_ = 0;  // version of the start vector the device state holds (0: none)
   DeviceOperator<Scalar> op_;
   std::shared_ptr<Bridge> bridge_;
   cmb_ctx* ctxOf_ = nullptr;

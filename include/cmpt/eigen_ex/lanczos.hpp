@@ -125,6 +125,7 @@ class LanczosBase {
   Index matrixHeight_;
   Index reorthogonalizeInterval_;
   VectorType initialVector_;
+  std::uint64_t initialVersion_ = 1;  // bumped by every setInitialVector: the device keeps the last uploaded version
   RealScalar threshold_;
 
  public:
@@ -184,15 +185,18 @@ class LanczosBase {
   const VectorType& initialVector() const { return initialVector_; }
   LanczosBase& setInitialVector(const VectorType& inivec) {
     initialVector_ = inivec;
+    ++initialVersion_;
     return *this;
   }
   LanczosBase& setInitialVector(VectorType&& inivec) {
     initialVector_ = std::move(inivec);
+    ++initialVersion_;
     return *this;
   }
   /// additive: copy n scalars straight into the (pinned, reused) start-vector storage
   LanczosBase& setInitialVector(const Scalar* data, Index n) {
     detail::assign_upload(initialVector_, data, n);
+    ++initialVersion_;
     return *this;
   }
   /// initial vector of size matrixHeight with random contents, fixed seed (lanczos.hpp:214-218)
@@ -354,7 +358,7 @@ class LanczosBase {
     if (localHeight() != static_cast<Index>(initialVector_.size())) setInitialVector();
     dev_.setDeflation(orthogonalizingVectors_, localHeight());
     int status = 0;
-    detail::check(cmb_krylov_start(dev_.handle(), initialVector_.data(), threshold_, &status), "cmb_krylov_start");
+    dev_.start(initialVector_, initialVersion_, threshold_, &status);
     return status == CMB_STEP_OK;
   }
 };

@@ -135,6 +135,9 @@ int cmb_krylov_set_deflation(cmb_krylov* k, int64_t nvec, const void* vecs, int6
  * copy the local slab of the start vector, project the deflation vectors out, test the norm against
  * threshold and normalise.  *status is CMB_STEP_OK or CMB_STEP_NOSTART. */
 int cmb_krylov_start(cmb_krylov* k, const void* init, double threshold, int* status);
+/* starts again from the vector of the last cmb_krylov_start, which the state keeps in HBM: no host-to-device copy.
+ * CMB_ERR_INVALID when there was no such call since the state was created. */
+int cmb_krylov_restart(cmb_krylov* k, double threshold, int* status);
 int64_t cmb_krylov_ncols(const cmb_krylov* k); /* number of Krylov vectors */
 int64_t cmb_krylov_rows(const cmb_krylov* k);
 /* copy Krylov vector j (local slab) to host */

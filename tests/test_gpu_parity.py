@@ -244,6 +244,34 @@ def test_lanczos_fixed_m_matches_oracle(ctx, case):
     np.testing.assert_allclose(V.T @ V, np.eye(V.shape[1]), atol=1e-13)
 
 
+def test_repeated_compute_starts_from_the_device_copy_of_the_start_vector(ctx):
+    # compute() again with the same start vector restarts from the copy kept in HBM (cmb_krylov_restart); setting a
+    # new start vector — even one of the same size in the same storage — uploads again
+    N, m = 24, 30
+    rp, c, v = syn.laplacian2d_csr(N)
+    x0, x1 = syn.start_vector(N * N, seed=7), syn.start_vector(N * N, seed=8)
+    op = pkg.DeviceOperator.from_csr(ctx, rp, c, v)
+
+    def solve(es):
+        es.compute()
+        return es.alpha().copy(), es.beta().copy()
+
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(op).setInitialVector(x0).setMinIterations(m).setMaxIterations(m).setMaxEigenvalues(2)
+    a0, b0 = solve(es)
+    a0b, b0b = solve(es)
+    assert np.array_equal(a0, a0b) and np.array_equal(b0, b0b)
+    es.setInitialVector(x1)
+    a1, b1 = solve(es)
+    fresh = pkg.LanczosEigenSolver()
+    fresh.setMatrixMultiplication(op).setInitialVector(x1).setMinIterations(m).setMaxIterations(m).setMaxEigenvalues(2)
+    a1f, b1f = solve(fresh)
+    assert np.array_equal(a1, a1f) and np.array_equal(b1, b1f)
+    assert not np.array_equal(a0, a1)
+    ref = _oracle_lanczos(core.Operator.csr(rp, c, v), x1, m, 2)
+    _compare_lanczos(es, ref, check_vectors=False)
+
+
 def test_lanczos_complex_sample2(ctx):
     # src/samples/sample_lanczos2.cpp:19-59, exact settings, complex Scalar
     n = 200
