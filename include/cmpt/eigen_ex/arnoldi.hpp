@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "detail/hessenberg_eigen.hpp"
+#include "detail/convergence.hpp"
 #include "detail/krylov_device.hpp"
 #include "device.hpp"
 #include "lanczos.hpp"
@@ -596,7 +597,7 @@ class ArnoldiEigenSolver {
   Index mainCalculation_() {  // arnoldi.hpp:764-873
     bool set_initialvector_is_fail = false;
     while (true) {
-      updateConvergenceLog_();
+      recordTrip_();
       {
         if (set_initialvector_is_fail) {
           log_.push_back(headINFO() + "initial arnoldivector generation fail");
@@ -612,7 +613,7 @@ class ArnoldiEigenSolver {
             log_.push_back(headWARN() + "arnoldi steps achieved maxIterations");
             break;
           }
-          if (isConverged_()) {
+          if (watchedValuesSettled_()) {
             log_.push_back(headINFO() + "arnoldi steps converged with tolerance");
             break;
           }
@@ -728,7 +729,7 @@ class ArnoldiEigenSolver {
       std::vector<ComplexScalar> vals;
       for (Index t = 0; t < ntrips; ++t) {
         const std::vector<ComplexScalar>& ev = ritz[static_cast<std::size_t>(t)];
-        Index i = getFormalIndex(kv.first, static_cast<Index>(ev.size()));
+        Index i = detail::wrap_index(kv.first, static_cast<Index>(ev.size()));
         if (i < 0) continue;
         vals.push_back(ev[static_cast<std::size_t>(i)]);
       }
@@ -771,53 +772,24 @@ class ArnoldiEigenSolver {
     return indices;
   }
 
-  static Index getFormalIndex(Index i, Index n) {  // arnoldi.hpp:938-948
-    if (-n <= i && i < 0) {
-      return n - (-i - 1) % n - 1;
-    } else if (0 <= i && i < n) {
-      return i % n;
-    } else {
-      return -1;
-    }
+  /// one driver trip: the watched Ritz values join their histories
+  void recordTrip_() {
+    detail::record_trip(convergenceLog_, indicesForConvergence_, eigenvalues_, static_cast<Index>(eigenvalues_.size()));
   }
 
-  void updateConvergenceLog_() {  // arnoldi.hpp:954-964
-    for (auto& indexForConvergence : indicesForConvergence_) {
-      Index i = getFormalIndex(indexForConvergence, eigenvalues_.size());
-      if (i < 0) continue;
-      convergenceLog_[indexForConvergence].push_back(eigenvalues_[i]);
-    }
-  }
-
-  bool isConverged_() {  // arnoldi.hpp:969-996
+  /// stop rule (arnoldi.hpp:969-996): all watched Ritz values moved by at most tolerance * |first - last Ritz value|
+  bool watchedValuesSettled_() {
     resolvePending_();
-    if (eigenvalues_.size() < 2) return false;
-    RealScalar scale = std::abs(eigenvalues_[0] - eigenvalues_[eigenvalues_.size() - 1]);
-    for (auto& idxFroConvergence : indicesForConvergence_) {
-      auto itr = convergenceLog_.find(idxFroConvergence);
-      if (itr == convergenceLog_.end()) return false;
-      auto& edge = itr->second;
-      if (edge.size() < 2) return false;
-      ComplexScalar cur = edge[edge.size() - 1];
-      ComplexScalar old = edge[edge.size() - 2];
-      if (std::abs((cur - old) / scale) > tolerance_) return false;
-    }
-    return true;
+    const Index n = static_cast<Index>(eigenvalues_.size());
+    if (n < 2) return false;
+    const RealScalar spread = std::abs(eigenvalues_[0] - eigenvalues_[n - 1]);
+    return detail::histories_settled(convergenceLog_, indicesForConvergence_, spread, tolerance_);
   }
 
  public:
-  Index hasERROR() const {
-    Index count = 0;
-    for (const auto& str : log_)
-      if (str.find(headERROR()) == 0) ++count;
-    return count;
-  }
-  Index hasWARN() const {
-    Index count = 0;
-    for (const auto& str : log_)
-      if (str.find(headWARN()) == 0) ++count;
-    return count;
-  }
+  /// number of error / warning lines in the log
+  Index hasERROR() const { return detail::count_tagged(log_, headERROR()); }
+  Index hasWARN() const { return detail::count_tagged(log_, headWARN()); }
 };
 
 }  // namespace EigenEx

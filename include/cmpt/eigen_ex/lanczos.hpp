@@ -25,8 +25,10 @@
 #include <random>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
+#include "detail/convergence.hpp"
 #include "detail/krylov_device.hpp"
 #include "detail/tridiag_eigen.hpp"
 #include "device.hpp"
@@ -35,21 +37,14 @@
 namespace cmpt {
 namespace EigenEx {
 
-/// default value to judge the convergence (lanczos.hpp:62-83): double -> 1e-12, float -> 1e-4
+/// Default convergence tolerance / breakdown threshold (the reference's values, lanczos.hpp:62-83): 1e-4 in single
+/// precision, 1e-12 otherwise.
 template <class Scalar>
 class DefaultTolerance {
- protected:
-  template <class S, class AlwaysBool>
-  struct Dummy {
-    static constexpr S value() { return 1.0e-12; }
-  };
-  template <class AlwaysBool>
-  struct Dummy<float, AlwaysBool> {
-    static constexpr float value() { return 1.0e-4f; }
-  };
-
  public:
-  static constexpr Scalar value() { return Dummy<Scalar, bool>::value(); }
+  static constexpr Scalar value() {
+    return std::is_same<Scalar, float>::value ? static_cast<Scalar>(1.0e-4f) : static_cast<Scalar>(1.0e-12);
+  }
 };
 
 /// Stand-in for Eigen::SelfAdjointEigenSolver restricted to computeFromTridiagonal (lanczos.hpp:637).
@@ -610,7 +605,7 @@ class LanczosEigenSolver {
     solveTridiagonal_(0, false);
     bool set_initialvector_is_fail = false;
     while (true) {
-      updateConvergenceLog_();
+      recordTrip_();
       {
         if (set_initialvector_is_fail) {
           log_.push_back(headINFO() + "initial lanczosvector generation fail");
@@ -626,7 +621,7 @@ class LanczosEigenSolver {
             log_.push_back(headWARN() + "lanczos steps achieved maxIterations");
             break;
           }
-          if (isConverged_()) {
+          if (watchedValuesSettled_()) {
             log_.push_back(headINFO() + "lanczos steps converged with tolerance");
             break;
           }
@@ -702,7 +697,7 @@ class LanczosEigenSolver {
     pendingReplay_.clear();
   }
   /// Ritz values of each skipped T_j on a few host threads, inserted in trip order at the recorded positions —
-  /// exactly the entries updateConvergenceLog_ would have appended trip by trip.
+  /// exactly the entries recordTrip_ would have appended trip by trip.
   void replayTrips_(const PendingReplay& pr) const {
     const Index before = pr.before, ntrips = pr.done - 1;
     if (ntrips <= 0) return;
@@ -730,7 +725,7 @@ class LanczosEigenSolver {
       std::vector<RealScalar> vals;
       for (Index t = 0; t < ntrips; ++t) {
         const std::vector<RealScalar>& ev = ritz[static_cast<std::size_t>(t)];
-        Index i = getFormalIndex(kv.first, static_cast<Index>(ev.size()));
+        Index i = detail::wrap_index(kv.first, static_cast<Index>(ev.size()));
         if (i < 0) continue;
         vals.push_back(ev[static_cast<std::size_t>(i)]);
       }
@@ -740,59 +735,26 @@ class LanczosEigenSolver {
     }
   }
 
-  /// index for eigenvalues in [0,n); negative i counts from the end; -1 when invalid (lanczos.hpp:837-847)
-  static Index getFormalIndex(Index i, Index n) {
-    if (-n <= i && i < 0) {
-      return n - (-i - 1) % n - 1;
-    } else if (0 <= i && i < n) {
-      return i % n;
-    } else {
-      return -1;
-    }
+  /// one driver trip: the watched Ritz values of the current T_j join their histories
+  void recordTrip_() {
+    const RealVectorType& ritz = es_tri_.eigenvalues();
+    detail::record_trip(convergenceLog_, indicesForConvergence_, ritz, static_cast<Index>(ritz.size()));
   }
 
-  /// append convergence log with current es_tri_ (lanczos.hpp:853-864)
-  void updateConvergenceLog_() {
-    const RealVectorType& trieivals = es_tri_.eigenvalues();
-    for (auto& indexForConvergence : indicesForConvergence_) {
-      Index i = getFormalIndex(indexForConvergence, trieivals.size());
-      if (i < 0) continue;
-      convergenceLog_[indexForConvergence].push_back(trieivals[i]);
-    }
-  }
-
-  /// judge convergence with current convergenceLog_ (lanczos.hpp:869-896)
-  bool isConverged_() {
+  /// stop rule: all watched Ritz values moved by at most tolerance * (spread of the Ritz values) in the last trip
+  bool watchedValuesSettled_() {
     resolvePending_();
-    if (es_tri_.eigenvalues().size() < 2) return false;
-    RealScalar scale = es_tri_.eigenvalues()[0] - es_tri_.eigenvalues()[es_tri_.eigenvalues().size() - 1];
-    for (auto& idxFroConvergence : indicesForConvergence_) {
-      auto itr = convergenceLog_.find(idxFroConvergence);
-      if (itr == convergenceLog_.end()) return false;
-      auto& edge = itr->second;
-      if (edge.size() < 2) return false;
-      RealScalar cur = edge[edge.size() - 1];
-      RealScalar old = edge[edge.size() - 2];
-      if (std::abs((cur - old) / scale) > tolerance_) return false;
-    }
-    return true;
+    const RealVectorType& ritz = es_tri_.eigenvalues();
+    const Index n = static_cast<Index>(ritz.size());
+    if (n < 2) return false;
+    const RealScalar spread = ritz[0] - ritz[n - 1];
+    return detail::histories_settled(convergenceLog_, indicesForConvergence_, spread, tolerance_);
   }
 
  public:
-  /// number of error log lines (lanczos.hpp:903-911)
-  Index hasERROR() const {
-    Index count = 0;
-    for (const auto& str : log_)
-      if (str.find(headERROR()) == 0) ++count;
-    return count;
-  }
-  /// number of warning log lines (lanczos.hpp:914-922)
-  Index hasWARN() const {
-    Index count = 0;
-    for (const auto& str : log_)
-      if (str.find(headWARN()) == 0) ++count;
-    return count;
-  }
+  /// number of error / warning lines in the log (lanczos.hpp:903-922)
+  Index hasERROR() const { return detail::count_tagged(log_, headERROR()); }
+  Index hasWARN() const { return detail::count_tagged(log_, headWARN()); }
 };
 
 /// exp(xA)|ket> with the Lanczos method or a Taylor expansion (lanczos.hpp:1002-1164), A Hermitian.

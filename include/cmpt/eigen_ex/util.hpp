@@ -7,6 +7,7 @@
 
 #include <complex>
 #include <random>
+#include <type_traits>
 #include <vector>
 
 #include "detail/dense.hpp"
@@ -31,19 +32,14 @@ class ComplexNormalDistribution {
   void reset() { norm.reset(); }
 };
 
-/// selects the normal distribution type by Scalar
+/// The normal distribution that draws a Scalar: std::normal_distribution for real scalars, the complex one above
+/// otherwise (util.hpp:132-148 of the reference names the same two types).
 template <class Scalar_>
 struct NormalDistributionGen {
-  template <class S>
-  struct Dummy {
-    using Type = std::normal_distribution<S>;
-  };
-  template <class RS>
-  struct Dummy<std::complex<RS>> {
-    using Type = ComplexNormalDistribution<RS>;
-  };
   using Scalar = Scalar_;
-  using Type = typename Dummy<Scalar>::Type;
+  using Real = typename RealOf<Scalar>::type;
+  using Type = typename std::conditional<std::is_same<Scalar, Real>::value, std::normal_distribution<Real>,
+                                         ComplexNormalDistribution<Real>>::type;
 };
 
 /// permutes the COLUMNS of db: new column c = old column shuffle[c]
