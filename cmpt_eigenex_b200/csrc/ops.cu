@@ -572,33 +572,88 @@ static int build_slice_order(SellOp* op) {
 // ======================================================================================================
 // dense row-major GEMV (single rank)
 // ======================================================================================================
+// K warps share a row (K = 1 by default; 2, 4, 8 for measurements).  A warp takes a contiguous even-length piece of the
+// row, reads it with four independent 16-byte loads per lane in flight, and the first warp of the row adds the K
+// partial sums in a fixed order.
 template <bool CPLX>
 __global__ void __launch_bounds__(256)
 dense_apply_kernel(const double* __restrict__ A, long long n, const double* __restrict__ w, double* __restrict__ ucol,
-                   double* __restrict__ v, double shr, double shi, StepScalars sc, double* partial, unsigned* ticket) {
+                   double* __restrict__ v, double shr, double shi, StepScalars sc, double* partial, unsigned* ticket,
+                   int K) {
   double inv;
   if (!step_prologue(sc, inv)) return;
-  const int lane = threadIdx.x & 31;
-  const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  __shared__ double s_part[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rows_per_cta = 8 / K, sub = warp % K, rloc = warp / K;
+  const long long seg = ((n + K - 1) / K + 1) & ~1ll;  // even, so that every piece starts on a 16-byte boundary
+  const long long c0 = std::min<long long>(n, sub * seg), c1 = std::min<long long>(n, c0 + seg);
   double d0 = 0.0, d1 = 0.0;
-  for (long long r = gwarp; r < n; r += nwarps) {
-    if (CPLX) {
-      const double2* row = reinterpret_cast<const double2*>(A) + r * n;
-      const double2* wz = reinterpret_cast<const double2*>(w);
-      double ar = 0.0, ai = 0.0;
-      for (long long c = lane; c < n; c += 32) {
-        const double2 a = __ldg(row + c);
-        const double2 xv = wz[c];
-        ar = fma(a.x, xv.x, ar);
-        ar = fma(-a.y, xv.y, ar);
-        ai = fma(a.x, xv.y, ai);
-        ai = fma(a.y, xv.x, ai);
+  for (long long rbase = (long long)blockIdx.x * rows_per_cta; rbase < n; rbase += (long long)gridDim.x * rows_per_cta) {
+    const long long r = rbase + rloc;
+    double ar = 0.0, ai = 0.0;
+    if (r < n) {
+      if (CPLX) {
+        const double2* row = reinterpret_cast<const double2*>(A) + r * n;
+        const double2* wz = reinterpret_cast<const double2*>(w);
+        double br = 0.0, bi = 0.0;
+        long long c = c0 + lane;
+        for (; c + 32 < c1; c += 64) {
+          const double2 a0 = __ldg(row + c), a1 = __ldg(row + c + 32);
+          const double2 x0 = wz[c], x1 = wz[c + 32];
+          ar = fma(a0.x, x0.x, ar), ar = fma(-a0.y, x0.y, ar), ai = fma(a0.x, x0.y, ai), ai = fma(a0.y, x0.x, ai);
+          br = fma(a1.x, x1.x, br), br = fma(-a1.y, x1.y, br), bi = fma(a1.x, x1.y, bi), bi = fma(a1.y, x1.x, bi);
+        }
+        if (c < c1) {
+          const double2 a0 = __ldg(row + c), x0 = wz[c];
+          ar = fma(a0.x, x0.x, ar), ar = fma(-a0.y, x0.y, ar), ai = fma(a0.x, x0.y, ai), ai = fma(a0.y, x0.x, ai);
+        }
+        ar += br, ai += bi;
+      } else if ((n & 1) == 0) {
+        const double2* row = reinterpret_cast<const double2*>(A + r * n + c0);
+        const double2* wz = reinterpret_cast<const double2*>(w + c0);
+        const long long cnt = (c1 - c0) >> 1;
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
+        for (long long i = lane; i < cnt; i += 128) {
+          double2 m[4], x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool ok = i + 32 * u < cnt;
+            m[u] = ok ? __ldg(row + i + 32 * u) : make_double2(0.0, 0.0);
+            x[u] = ok ? wz[i + 32 * u] : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) a[u] = fma(m[u].y, x[u].y, fma(m[u].x, x[u].x, a[u]));
+        }
+        ar = (a[0] + a[1]) + (a[2] + a[3]);
+      } else {  // odd n: rows are not 16-byte aligned
+        const double* row = A + r * n;
+        double b = 0.0;
+        long long c = c0 + lane;
+        for (; c + 32 < c1; c += 64) {
+          ar = fma(__ldg(row + c), w[c], ar);
+          b = fma(__ldg(row + c + 32), w[c + 32], b);
+        }
+        if (c < c1) ar = fma(__ldg(row + c), w[c], ar);
+        ar += b;
       }
-      ar = warp_sum(ar);
-      ai = warp_sum(ai);
+    }
+    ar = warp_sum(ar);
+    if (CPLX) ai = warp_sum(ai);
+    if (K > 1) {
       if (lane == 0) {
-        const double2 wi = wz[r];
+        s_part[0][warp] = ar;
+        s_part[1][warp] = ai;
+      }
+      __syncthreads();
+      if (sub == 0 && lane == 0) {
+        ar = 0.0, ai = 0.0;
+        for (int k = 0; k < K; ++k) ar += s_part[0][warp + k], ai += s_part[1][warp + k];
+      }
+      __syncthreads();
+    }
+    if (sub == 0 && lane == 0 && r < n) {
+      if (CPLX) {
+        const double2 wi = reinterpret_cast<const double2*>(w)[r];
         const double ur = wi.x * inv, ui = wi.y * inv;
         const double yr = ar * inv + (shr * ur - shi * ui);
         const double yi = ai * inv + (shr * ui + shi * ur);
@@ -606,15 +661,9 @@ dense_apply_kernel(const double* __restrict__ A, long long n, const double* __re
         reinterpret_cast<double2*>(v)[r] = make_double2(yr, yi);
         d0 += ur * yr + ui * yi;
         d1 += ur * yi - ui * yr;
-      }
-    } else {
-      const double* row = A + r * n;
-      double acc = 0.0;
-      for (long long c = lane; c < n; c += 32) acc = fma(__ldg(row + c), w[c], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) {
+      } else {
         const double ui = w[r] * inv;
-        const double y = acc * inv + shr * ui;
+        const double y = ar * inv + shr * ui;
         ucol[r] = ui;
         v[r] = y;
         d0 = fma(ui, y, d0);
@@ -628,15 +677,24 @@ struct DenseOp : cmb_op {
   double* d_a = nullptr;
   ~DenseOp() override { cudaFree(d_a); }
   int apply(const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) override {
-    int grid = int(std::min<long long>((n_local + 7) / 8, (long long)ctx->num_sms * 8));
+    // One warp per row.  Splitting a row over K = 2, 4, 8 warps fills more of the GPU at n = 2000 but measured slower
+    // (16.5 us per launch with K = 1, 19.4 with 2, 21.0 with 8): the launch is bound by its fixed costs — the K-fold
+    // number of CTAs in the final reduction outweighs the shorter rows.  CMPT_B200_DENSE_K overrides (measurements).
+    int K = 1;
+    if (const char* e = getenv("CMPT_B200_DENSE_K")) {
+      const int k = atoi(e);
+      if (k == 1 || k == 2 || k == 4 || k == 8) K = k;
+    }
+    const int rows_per_cta = 8 / K;
+    int grid = int(std::min<long long>((n_local + rows_per_cta - 1) / rows_per_cta, (long long)ctx->num_sms * 8));
     if (grid < 1) grid = 1;
     LaunchScope ls(ctx, "gemv_dense");
     if (cplx)
       dense_apply_kernel<true><<<grid, 256, 0, ctx->stream>>>(d_a, n_local, w, ucol, v, shr, shi, sc, ctx->d_partial,
-                                                              ctx->d_ticket + 1);
+                                                              ctx->d_ticket + 1, K);
     else
       dense_apply_kernel<false><<<grid, 256, 0, ctx->stream>>>(d_a, n_local, w, ucol, v, shr, shi, sc, ctx->d_partial,
-                                                               ctx->d_ticket + 1);
+                                                               ctx->d_ticket + 1, K);
     CMB_CUDA(cudaGetLastError());
     return CMB_OK;
   }

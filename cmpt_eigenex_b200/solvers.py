@@ -153,12 +153,22 @@ class Context:
 
     def close(self):
         if self.h:
-            for s in list(self._solvers):
-                s.close()
-            for o in list(self._ops):
-                o.close()
-            lib().cmb_ctx_destroy(self.h)
-            self.h = None
+            # a context that a peer timeout marked dead makes the solvers' and operators' destructors report errors:
+            # the context itself must still be destroyed, and only once
+            try:
+                for s in list(self._solvers):
+                    try:
+                        s.close()
+                    except Exception:
+                        pass
+                for o in list(self._ops):
+                    try:
+                        o.close()
+                    except Exception:
+                        pass
+            finally:
+                h, self.h = self.h, None
+                lib().cmb_ctx_destroy(h)
 
     def __del__(self):
         try:

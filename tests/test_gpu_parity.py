@@ -125,13 +125,14 @@ def test_csr_stencils_keep_the_natural_row_order(ctx):
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128])
 def test_dense_and_matrix_free_apply(ctx, dtype):
     rng = np.random.default_rng(1)
-    n = 203
-    A = rng.normal(size=(n, n)).astype(dtype)
-    if dtype == np.complex128:
-        A = A + 1j * rng.normal(size=(n, n))
-    x = syn.start_vector(n, seed=5, dtype=dtype)
-    y = pkg.DeviceOperator.from_dense(ctx, A).apply(x)
-    np.testing.assert_allclose(y, A @ x, atol=1e-13)
+    # one warp per row (small n), several warps per row with 16-byte loads (even n) and with 8-byte loads (odd n)
+    for n in (203, 1030, 1001, 2000):
+        A = rng.normal(size=(n, n)).astype(dtype)
+        if dtype == np.complex128:
+            A = A + 1j * rng.normal(size=(n, n))
+        x = syn.start_vector(n, seed=5, dtype=dtype)
+        y = pkg.DeviceOperator.from_dense(ctx, A).apply(x)
+        np.testing.assert_allclose(y, A @ x, atol=1e-13)
     L = 11
     xs = syn.start_vector(1 << L, seed=9, dtype=dtype)
     for pbc in (True, False):
