@@ -228,6 +228,8 @@ bool ipc_share(cmb_ctx* ctx, void* base, void** mapped);
 void ipc_unshare(cmb_ctx* ctx, void** mapped);
 // all ranks wait for each other (stream synchronised first); no-op on a single rank
 int rank_barrier(cmb_ctx* ctx);
+// collective: returns rc when rc is an error, an error when another rank reported one, CMB_OK when nobody did
+int agree_status(cmb_ctx* ctx, int rc, const char* what);
 // all-to-all of int32 device lists: the piece [send_off[q], send_off[q+1]) of d_send goes to rank q, the piece rank q
 // destined to this rank lands at d_recv + recv_off[q]
 int alltoallv_i32(cmb_ctx* ctx, const int32_t* d_send, const int64_t* send_off, int32_t* d_recv, const int64_t* recv_off);

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <string>
 #include <vector>
 
 #include <algorithm>
@@ -178,6 +179,32 @@ int rank_barrier(cmb_ctx* ctx) {
   if (ctx->vgroup) return vgroup_barrier(ctx);
   CMB_TRY(allreduce_sum_f64(ctx, ctx->d_partial, 1));  // scratch word; its value is never read
   CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CMB_OK;
+}
+
+// Collective: every rank reports its local outcome and all of them leave with an error if any of them has one, so that
+// no rank goes on to a collective step (or to a solve) that a failed peer will never join.
+int agree_status(cmb_ctx* ctx, int rc, const char* what) {
+  if (ctx->nranks == 1) return rc;
+  const std::string mine = rc != CMB_OK ? std::string(cmb_last_error()) : std::string();
+  double flag = rc == CMB_OK ? 0.0 : 1.0;
+  double* word = ctx->d_partial;  // scratch
+  if (cudaMemcpyAsync(word, &flag, sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    set_error("%s: agreement between the ranks failed: %s", what, cudaGetErrorString(cudaGetLastError()));
+    return CMB_ERR_CUDA;
+  }
+  CMB_TRY(allreduce_sum_f64(ctx, word, 1));
+  double failed = 0.0;
+  CMB_TRY(d2h_sync(ctx, &failed, word, sizeof(double)));
+  if (rc != CMB_OK) {
+    set_error("%s", mine.c_str());
+    return rc;
+  }
+  if (failed > 0.0) {
+    set_error("%s failed on %d other rank(s)", what, int(failed));
+    return CMB_ERR_INVALID;
+  }
   return CMB_OK;
 }
 

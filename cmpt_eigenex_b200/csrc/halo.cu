@@ -393,16 +393,21 @@ int HaloExchange::setup(cmb_ctx* ctx, int64_t n, int es_, const std::vector<int3
   dfree(ctx, d_need);
   CMB_TRY(rc);
   const int64_t nloc = partition_begin(n, P, rank + 1) - r0;
-  for (int64_t i = 0; i < nsend; ++i) {
-    const int64_t l = int64_t(sidx[i]) - r0;
-    if (l < 0 || l >= nloc) {
-      set_error("halo setup: peer asked for row %d which rank %d does not own", int(sidx[i]), rank);
-      return CMB_ERR_INVALID;
+  // rank-local checks and copies: their outcome is agreed on before the next collective step (the peer-memory mapping)
+  rc = [&]() -> int {
+    for (int64_t i = 0; i < nsend; ++i) {
+      const int64_t l = int64_t(sidx[i]) - r0;
+      if (l < 0 || l >= nloc) {
+        set_error("halo setup: peer asked for row %d which rank %d does not own", int(sidx[i]), rank);
+        return CMB_ERR_INVALID;
+      }
+      sidx[i] = int32_t(l);
     }
-    sidx[i] = int32_t(l);
-  }
-  CMB_CUDA(cudaMemcpyAsync(d_send_idx, sidx.data(), sizeof(int32_t) * nsend, cudaMemcpyHostToDevice, ctx->stream));
-  CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    CMB_CUDA(cudaMemcpyAsync(d_send_idx, sidx.data(), sizeof(int32_t) * nsend, cudaMemcpyHostToDevice, ctx->stream));
+    CMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CMB_OK;
+  }();
+  CMB_TRY(agree_status(ctx, rc, "halo setup"));
   CMB_TRY(setup_p2p(ctx, cnt));
   if (!p2p) {
     CMB_CUDA(cudaMalloc(&d_sendbuf, sizeof(double) * es * std::max<int64_t>(nsend, 1)));

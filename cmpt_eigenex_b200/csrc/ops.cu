@@ -821,6 +821,7 @@ int cmb_op_csr_create(cmb_ctx* ctx, cmb_dtype dtype, int64_t n_global, int64_t r
     lap("build_sell");
     if (rc == CMB_OK && op->halo->p2p) rc = build_slice_order(op);
     lap("slice_order");
+    rc = agree_status(ctx, rc, "cmb_op_csr_create");  // an operator exists on every rank or on none
   } else {
     CsrOnDevice csr;
     rc = upload_csr(op, rowptr, col, val, csr);

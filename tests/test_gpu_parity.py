@@ -273,6 +273,41 @@ def test_repeated_compute_starts_from_the_device_copy_of_the_start_vector(ctx):
     _compare_lanczos(es, ref, check_vectors=False)
 
 
+_OVERLAP_PROBE = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+import cmpt_eigenex_b200 as pkg
+from cmpt_eigenex_b200 import synthetic as syn
+ctx = pkg.Context(0)
+out = []
+for N, m in ((24, 60), (96, 40)):
+    rp, c, v = syn.laplacian2d_csr(N)
+    es = pkg.LanczosEigenSolver()
+    es.setMatrixMultiplication(pkg.DeviceOperator.from_csr(ctx, rp, c, v)).setInitialVector(syn.start_vector(N * N, seed=7))
+    es.setMinIterations(m).setMaxIterations(m).setMaxEigenvalues(3)
+    es.compute()
+    out += [es.alpha(), es.beta(), es.eigenvectors().ravel()]
+print(np.concatenate(out).tobytes().hex())
+"""
+
+
+def test_launch_overlap_does_not_change_a_single_bit():
+    # programmatic dependent launch (an UPDATE pass fetches basis tiles while its predecessor drains) against plain
+    # stream order: a kernel that touched data too early would show up as a difference (it did, once)
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env in ({"CMPT_B200_PDL": "0"}, {"CMPT_B200_PDL": "1", "CMPT_B200_PDL_APPLY": "1"}):
+        p = subprocess.run([sys.executable, "-c", _OVERLAP_PROBE, root], capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, **env))
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs.append(p.stdout.strip().splitlines()[-1])
+    assert len(outs[0]) > 1000 and outs[0] == outs[1]
+
+
 def test_lanczos_complex_sample2(ctx):
     # src/samples/sample_lanczos2.cpp:19-59, exact settings, complex Scalar
     n = 200

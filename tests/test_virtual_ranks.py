@@ -137,3 +137,28 @@ def test_peer_wait_timeout_is_reported_and_poisons_the_context():
 
     results, _ = pkg.run_virtual_ranks(2, work)
     assert results[0] == "error -4" and results[1] == "skipped"
+
+
+def test_a_bad_shard_on_one_rank_fails_the_operator_on_every_rank():
+    """Rank 1 hands in a column index outside the matrix: its build fails validation, and rank 0 — whose shard is fine —
+    gets an error too instead of an operator whose peer does not exist (it would hang in the first exchange)."""
+    from cmpt_eigenex_b200 import capi
+
+    n = 4096
+    full = syn.laplacian2d_csr(64)
+
+    def work(ctx, comm):
+        r0, r1 = comm.row_range(n)
+        rp, c, v = mc.shard_of(full, r0, r1)
+        if comm.rank == 1:
+            c = c.copy()
+            c[5] = n + 17
+        try:
+            pkg.DeviceOperator.from_csr(ctx, rp, c, v, n_global=n, row_begin=r0)
+            return "built"
+        except capi.CmbError as e:
+            return "error %d: %s" % (e.code, e)
+
+    results, _ = pkg.run_virtual_ranks(2, work)
+    assert results[0].startswith("error -1") and "other rank" in results[0]
+    assert results[1].startswith("error -1") and "column index" in results[1]
