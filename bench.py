@@ -510,6 +510,11 @@ def run_ours(args):
     ctx.profile(False)
     dev_ms_instr = max_over_ranks(dev_ms_instr)
     dev_ms = max_over_ranks(dev_ms)
+    if os.environ.get("BENCH_DEBUG") and dist is not None:  # per-rank view: which rank waits for which
+        table = dist.gather_objects({k: round(v[0] / max(v[1], 1) * 1e3, 1) for k, v in fams.items() if v[1]})
+        if rank == 0:
+            for r, row in enumerate(table):
+                print("rank %d us per launch: %s" % (r, row), file=sys.stderr, flush=True)
     if os.environ.get("BENCH_DEBUG") and rank == 0:
         print("device-leg: dev %.1f ms, host wall %.1f ms per solve; families %s" % (
             dev_ms / args.steps, host_ms / args.steps,

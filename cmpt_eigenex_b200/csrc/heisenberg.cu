@@ -520,6 +520,13 @@ struct HeisenbergOp : cmb_op {
   size_t p2p_tot = 0;                           // doubles per receive buffer of this rank
   std::vector<size_t> peer_off, peer_tot;       // per remote bond: where my slab goes in the partner's buffer / its size
   unsigned long long xseq = 0;                  // exchanges enqueued so far (same on every rank)
+  // Bonds whose slab travels by copy engine even when the other slabs are stored by the pass that produces w
+  // (CMPT_B200_SLAB_CE_SECOND=1, off by default).  A rank with two anti-aligned rank-rank bonds takes in 3 slabs' worth
+  // of NVLink stores during one pass — more than the links carry in that time; with this option its second full slab
+  // (and the partner's, for symmetry) waits for the end of the pass and travels while the window passes run.  Measured
+  // at L = 30 on 8 GPUs: UPDATE_NORM on those ranks drops from 5.3 to 4.4 ms, but their apply then waits as long for the
+  // copy (64.7 against 65.4 it/s) — the exchange is bound by what a rank can take in, whichever engine moves it.
+  unsigned ce_bonds = 0;
   const double* pushed_w = nullptr;             // slab_push_begin(): the producer of this w pushes exchange pushed_x
   unsigned long long pushed_x = 0;
   unsigned long long* h_seq = nullptr;          // pinned source words of the flag copies
@@ -705,6 +712,20 @@ struct HeisenbergOp : cmb_op {
       peer_off.push_back(off[k]);  // both partners enumerate the remote bonds in the same order
       peer_tot.push_back(std::max<size_t>(ptot, 2));
     }
+    // which full slabs go by copy engine (see ce_bonds): rank-rank bond b when this rank or its partner across that bond
+    // has another anti-aligned rank-rank bond below b.  Both partners evaluate the same predicate.  Virtual ranks have no
+    // copy engines to spare (same-device copies run on the SMs the peers spin on).
+    ce_bonds = 0;
+    if (!ctx->vgroup && getenv("CMPT_B200_SLAB_CE_SECOND")) {
+      auto differs = [](int r, int b) { return (((r >> b) ^ (r >> (b + 1))) & 1) != 0; };
+      for (size_t k = 0; k < plan.remote.size(); ++k) {
+        const HeisRemote& r = plan.remote[k];
+        if (r.kind != 3 || !r.needed) continue;
+        const int b = int(k) - 1;  // remote[0] is the straddle bond, remote[1 + b] joins rank bits b and b + 1
+        for (int lower = 0; lower < b; ++lower)
+          if (differs(plan.rank, lower) || differs(r.partner, lower)) ce_bonds |= 1u << k;
+      }
+    }
     return CMB_OK;
   }
 
@@ -801,7 +822,7 @@ struct HeisenbergOp : cmb_op {
     sp.ticket = ctx->d_ticket + 3;
     for (size_t k = 0; k < plan.remote.size(); ++k) {
       const HeisRemote& r = plan.remote[k];
-      if (!r.needed) continue;
+      if (!r.needed || (ce_bonds & (1u << k))) continue;
       if (sp.n >= kMaxSlabDst) return false;
       char* pbase = static_cast<char*>(p2p_mapped[r.partner]);
       const int d = sp.n++;
@@ -842,9 +863,8 @@ struct HeisenbergOp : cmb_op {
       if (p2p && pushed_w == w && pushed_w != nullptr) {
         // the kernel that produced w (or the push kernel above) stores the slabs and raises the flags of exchange pushed_x
         pushed_w = nullptr;
-        unsigned mask = 0;
-        for (size_t k = 0; k < plan.remote.size(); ++k)
-          if (plan.remote[k].needed) mask |= 1u << k;
+        const unsigned mask = needed_mask();
+        if (ce_bonds & mask) CMB_TRY(copy_bonds(w, pushed_x, ce_bonds & mask));
         const size_t par = size_t(pushed_x & 1ull);
         const double* recv = reinterpret_cast<const double*>(static_cast<char*>(p2p_base) + kFlagBytes) + par * p2p_tot;
         remote_args(a, recv);
@@ -854,7 +874,8 @@ struct HeisenbergOp : cmb_op {
         if (trace_slab) fprintf(stderr, "[slab] rank %d consumes exchange %llu (mask %x)\n", plan.rank, pushed_x, mask);
         a.error = ctx->d_mail_error;
         a.timeout = ctx->spin_timeout;
-        return launch(a, w, ucol, v, shr, shi, sc);
+        CMB_TRY(launch(a, w, ucol, v, shr, shi, sc));
+        return after_copies(ce_bonds & mask);
       }
       pushed_w = nullptr;
       const size_t es = cplx ? 2 : 1;
@@ -909,15 +930,16 @@ struct HeisenbergOp : cmb_op {
   // kernels are no-ops then, and every rank keeps the same exchange count).  Receive buffers alternate with the
   // exchange number: a partner can only start exchange x+2 after it consumed my exchange x+1, which I sent after my
   // contiguous pass of exchange x, so the buffer it overwrites is no longer being read.
-  int apply_p2p(HeisArgs& a, const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) {
+  // Copies the slabs of the bonds in `bonds` (bit k = remote bond k) of exchange x into the partners' receive buffers and
+  // raises their flags.  Virtual ranks (one device): same-device copies run on SMs, and the SMs a side stream could use
+  // are held by the peers' spinning kernels, so there the slabs are copied in stream order on the rank's own stream (no
+  // overlap, same buffers, flags and parity).  Real ranks: copy engines on side streams, overlapped with whatever the
+  // main stream does next (the window passes).
+  int copy_bonds(const double* w, unsigned long long x, unsigned bonds) {
     const size_t es = cplx ? 2 : 1;
     const size_t slab = size_t(n_local) * es, half = slab / 2;
     const int rb0 = plan.rank & 1;
-    const unsigned long long x = ++xseq;
     const size_t par = size_t(x & 1ull);
-    // Virtual ranks (one device): same-device copies run on SMs, and the SMs a side stream could use are held by the
-    // peers' spinning kernels, so there the slabs are copied in stream order on the rank's own stream (no overlap, same
-    // buffers, flags and parity).  Real ranks: copy engines on side streams, overlapped with the window passes.
     const bool inl = ctx->vgroup != nullptr;
     if ((x & 255ull) == 0) {  // keeps the pinned flag words of exchanges still in flight from being reused
       if (inl) CMB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -925,41 +947,58 @@ struct HeisenbergOp : cmb_op {
         for (size_t k = 0; k < plan.remote.size(); ++k) CMB_CUDA(cudaStreamSynchronize(xstream[k][0]));
     }
     if (!inl) CMB_CUDA(cudaEventRecord(ev_ready, ctx->stream));  // w (and the packed wrap half) are final
-    unsigned mask = 0;
-    {
-      for (size_t k = 0; k < plan.remote.size(); ++k) {
-        const HeisRemote& r = plan.remote[k];
-        if (!r.needed) continue;
-        mask |= 1u << k;
-        const double* src = w;
-        size_t count = slab;
-        if (r.kind == 2) {
-          src = w + size_t(1 - rb0) * half;
-          count = half;
-        } else if (r.kind == 4) {
-          src = d_pack;
-          count = half;
-        }
-        char* pbase = static_cast<char*>(p2p_mapped[r.partner]);
-        double* dst = reinterpret_cast<double*>(pbase + kFlagBytes) + par * peer_tot[k] + peer_off[k];
-        unsigned long long* word = h_seq + ((x * kMaxRemote + k) % kSeqSlots);
-        *word = x;
-        // the slab goes as nsplit concurrent copies; the flag follows on stream 0 once all of them are done
-        const int ns = (!inl && count >= (size_t(1) << 16)) ? nsplit : 1;
-        const size_t chunk = ((count + ns - 1) / ns + 1) & ~size_t(1);
-        for (int c = 0; c < ns; ++c) {
-          const size_t b = std::min(count, size_t(c) * chunk), e = std::min(count, b + chunk);
-          cudaStream_t cs = inl ? ctx->stream : xstream[k][c];
-          if (!inl) CMB_CUDA(cudaStreamWaitEvent(cs, ev_ready, 0));
-          if (e > b) CMB_CUDA(cudaMemcpyAsync(dst + b, src + b, sizeof(double) * (e - b), cudaMemcpyDefault, cs));
-          if (!inl && c > 0) CMB_CUDA(cudaEventRecord(ev_chunk[k][c], cs));
-        }
-        for (int c = 1; c < ns; ++c) CMB_CUDA(cudaStreamWaitEvent(xstream[k][0], ev_chunk[k][c], 0));
-        CMB_CUDA(cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(pbase) + k, word, sizeof(unsigned long long),
-                                 cudaMemcpyDefault, inl ? ctx->stream : xstream[k][0]));
-        if (!inl) CMB_CUDA(cudaEventRecord(ev_done[k], xstream[k][0]));
+    for (size_t k = 0; k < plan.remote.size(); ++k) {
+      const HeisRemote& r = plan.remote[k];
+      if (!(bonds & (1u << k))) continue;
+      const double* src = w;
+      size_t count = slab;
+      if (r.kind == 2) {
+        src = w + size_t(1 - rb0) * half;
+        count = half;
+      } else if (r.kind == 4) {
+        src = d_pack;
+        count = half;
       }
+      char* pbase = static_cast<char*>(p2p_mapped[r.partner]);
+      double* dst = reinterpret_cast<double*>(pbase + kFlagBytes) + par * peer_tot[k] + peer_off[k];
+      unsigned long long* word = h_seq + ((x * kMaxRemote + k) % kSeqSlots);
+      *word = x;
+      // the slab goes as nsplit concurrent copies; the flag follows on stream 0 once all of them are done
+      const int ns = (!inl && count >= (size_t(1) << 16)) ? nsplit : 1;
+      const size_t chunk = ((count + ns - 1) / ns + 1) & ~size_t(1);
+      for (int c = 0; c < ns; ++c) {
+        const size_t b = std::min(count, size_t(c) * chunk), e = std::min(count, b + chunk);
+        cudaStream_t cs = inl ? ctx->stream : xstream[k][c];
+        if (!inl) CMB_CUDA(cudaStreamWaitEvent(cs, ev_ready, 0));
+        if (e > b) CMB_CUDA(cudaMemcpyAsync(dst + b, src + b, sizeof(double) * (e - b), cudaMemcpyDefault, cs));
+        if (!inl && c > 0) CMB_CUDA(cudaEventRecord(ev_chunk[k][c], cs));
+      }
+      for (int c = 1; c < ns; ++c) CMB_CUDA(cudaStreamWaitEvent(xstream[k][0], ev_chunk[k][c], 0));
+      CMB_CUDA(cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(pbase) + k, word, sizeof(unsigned long long),
+                               cudaMemcpyDefault, inl ? ctx->stream : xstream[k][0]));
+      if (!inl) CMB_CUDA(cudaEventRecord(ev_done[k], xstream[k][0]));
     }
+    return CMB_OK;
+  }
+  // whoever overwrites w or the pack buffer next must come after the copies that read them
+  int after_copies(unsigned bonds) {
+    if (ctx->vgroup) return CMB_OK;
+    for (size_t k = 0; k < plan.remote.size(); ++k)
+      if (bonds & (1u << k)) CMB_CUDA(cudaStreamWaitEvent(ctx->stream, ev_done[k], 0));
+    return CMB_OK;
+  }
+  unsigned needed_mask() const {
+    unsigned mask = 0;
+    for (size_t k = 0; k < plan.remote.size(); ++k)
+      if (plan.remote[k].needed) mask |= 1u << k;
+    return mask;
+  }
+
+  int apply_p2p(HeisArgs& a, const double* w, double* ucol, double* v, double shr, double shi, const StepScalars& sc) {
+    const unsigned long long x = ++xseq;
+    const size_t par = size_t(x & 1ull);
+    const unsigned mask = needed_mask();
+    CMB_TRY(copy_bonds(w, x, mask));
     const double* recv = reinterpret_cast<const double*>(static_cast<char*>(p2p_base) + kFlagBytes) + par * p2p_tot;
     remote_args(a, recv);
     a.flag = static_cast<const unsigned long long*>(p2p_base);
@@ -968,11 +1007,7 @@ struct HeisenbergOp : cmb_op {
     a.error = ctx->d_mail_error;
     a.timeout = ctx->spin_timeout;
     CMB_TRY(launch(a, w, ucol, v, shr, shi, sc));
-    // whoever overwrites w or the pack buffer next must come after the copies that read them
-    if (!inl)
-      for (size_t k = 0; k < plan.remote.size(); ++k)
-        if (mask & (1u << k)) CMB_CUDA(cudaStreamWaitEvent(ctx->stream, ev_done[k], 0));
-    return CMB_OK;
+    return after_copies(mask);
   }
 };
 

@@ -60,6 +60,14 @@ def all_sum(x):
     return float(t.item())
 
 
+def gather_objects(obj):
+    """list over ranks of a small picklable object (diagnostics)"""
+    td = init()
+    out = [None] * td.get_world_size()
+    td.all_gather_object(out, obj)
+    return out
+
+
 def row_range(n, rank=None, world=None):
     td = init()
     rank = td.get_rank() if rank is None else rank

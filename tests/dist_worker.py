@@ -96,7 +96,8 @@ def gpu_main():
             return dist.row_range(n)
 
     exp = mc.expected(rs, core)
-    results = mc.run_checks(pkg, ctx, Comm(), exp)
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--only=")]
+    results = mc.run_checks(pkg, ctx, Comm(), exp, only=only[0] if only else None)
     td.barrier()
     ctx.close()
     if rank == 0:
