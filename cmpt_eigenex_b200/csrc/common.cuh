@@ -242,6 +242,7 @@ bool vgroup_share(cmb_ctx* c, void* base, void** mapped);
 int vgroup_barrier(cmb_ctx* c);
 int vgroup_alltoallv_i32(cmb_ctx* c, const int32_t* d_send, const int64_t* send_off, int32_t* d_recv, const int64_t* recv_off);
 int vgroup_attach(VGroup* g, cmb_ctx* c, int rank);
+void vgroup_detach(VGroup* g);
 int vgroup_size(const VGroup* g);
 int vgroup_device(const VGroup* g);
 

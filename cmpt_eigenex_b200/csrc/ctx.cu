@@ -529,6 +529,7 @@ int cmb_ctx_destroy(cmb_ctx* c) {
   }
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->vgroup) vgroup_detach(c->vgroup);
   delete c;
   return CMB_OK;
 }
@@ -544,6 +545,7 @@ int cmb_ctx_create_virtual(cmb_vgroup* vg, int rank, cmb_ctx** out) {
   int r = ctx_init_common(c, vgroup_device(g));
   if (r == CMB_OK) r = vgroup_attach(g, c, rank);
   if (r != CMB_OK) {
+    if (c->vgroup) vgroup_detach(c->vgroup);
     delete c;
     return r;
   }

@@ -232,7 +232,16 @@ int vgroup_alltoallv_i32(cmb_ctx* c, const int32_t* d_send, const int64_t* send_
   return rc;
 }
 
+void vgroup_detach(VGroup* g) {
+  std::lock_guard<std::mutex> lk(g->mu);
+  if (g->attached > 0) --g->attached;
+}
+
 int vgroup_attach(VGroup* g, cmb_ctx* c, int rank) {
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    ++g->attached;
+  }
   c->vgroup = g;
   c->rank = rank;
   c->nranks = g->P;
@@ -320,6 +329,13 @@ int cmb_vgroup_create(int device, int nranks, cmb_vgroup** out) {
 
 int cmb_vgroup_destroy(cmb_vgroup* vg) {
   if (!vg) return CMB_OK;
+  {
+    std::lock_guard<std::mutex> lk(vg->g.mu);
+    if (vg->g.attached > 0) {  // the contexts keep a pointer to the group and streams in its green contexts
+      set_error("cmb_vgroup_destroy: %d context(s) of the group still exist; destroy them first", vg->g.attached);
+      return CMB_ERR_INVALID;
+    }
+  }
   if (vg->g.green)
     for (auto c : vg->g.gctx) green_api().GreenCtxDestroy(c);
   delete vg;
