@@ -108,3 +108,77 @@ def test_mailbox_ring_of_four_slots_is_race_free(P):
         assert simulate_mailbox(P, nred=30, ring=2, seed=seed) is None  # two would already do; four is margin
     # a single slot is not enough: a fast rank overwrites a partial that a slow one has not summed yet
     assert any(simulate_mailbox(P, nred=30, ring=1, seed=seed) is not None for seed in range(60))
+
+
+def simulate_slab_push(P, partners, nsteps, nbuf, reductions, seed, steps_per_read=3):
+    """Slab exchange of the matrix-free Heisenberg operator, fused into the pass that produces w (csrc/cgs.cu SlabPush,
+    csrc/heisenberg.cu).  One Lanczos step of rank r:
+        apply x      : wait until every partner's flag >= x, then read receive buffer x % nbuf (takes several scheduler steps)
+        reductions   : `reductions` all-rank reductions (push a partial to everybody, then wait for everybody's) — the
+                       mailbox exchanges of DOT / UPDATE_DOT; 0 models back-to-back applies
+        UPDATE_NORM  : store the slabs of exchange x+1 into the partners' buffers (x+1) % nbuf, raise flag x+1 there
+    partners[r] is symmetric.  Returns None or the first violation."""
+    rng = random.Random(seed)
+    buf = [[{s: 0 for s in partners[r]} for _ in range(nbuf)] for r in range(P)]
+    flag = [[0] * P for _ in range(P)]
+    red = [[0] * P for _ in range(P)]  # red[r][s]: number of the last reduction partial rank s delivered to rank r
+    # exchange 1 is pushed by a stand-alone kernel before the first apply
+    pc = [[1, "push", 0, 0] for _ in range(P)]  # exchange, phase, reads left / reductions done, -
+    done = 0
+    while done < P:
+        r = rng.randrange(P)
+        x, ph, cnt, _ = pc[r]
+        if x > nsteps:
+            continue
+        if ph == "push":  # stores of exchange x, then the flags
+            for q in partners[r]:
+                buf[q][x % nbuf][r] = x
+                flag[q][r] = x
+            pc[r] = [x, "wait", 0, 0]
+        elif ph == "wait":
+            if all(flag[r][s] >= x for s in partners[r]):
+                pc[r] = [x, "read", steps_per_read, 0]
+        elif ph == "read":
+            for s, tag in buf[r][x % nbuf].items():
+                if tag != x:
+                    return "rank %d reading exchange %d found the slab of exchange %d from rank %d" % (r, x, tag, s)
+            pc[r] = [x, "read", cnt - 1, 0] if cnt > 1 else [x, "reduce_push", 0, 0]
+        elif ph == "reduce_push":
+            if cnt == reductions:
+                pc[r] = [x + 1, "push", 0, 0]  # UPDATE_NORM of step x carries exchange x + 1
+                if x + 1 > nsteps:
+                    done += 1
+            else:
+                k = (x - 1) * reductions + cnt + 1
+                for q in range(P):
+                    red[q][r] = k
+                pc[r] = [x, "reduce_pull", cnt, 0]
+        else:  # reduce_pull
+            k = (x - 1) * reductions + cnt + 1
+            if all(red[r][s] >= k for s in range(P)):
+                pc[r] = [x, "reduce_push", cnt + 1, 0]
+    return None
+
+
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_fused_slab_push_needs_two_receive_buffers_and_no_more(P):
+    import itertools
+
+    def heisenberg_partners(P):
+        p = P.bit_length() - 1
+        out = []
+        for r in range(P):
+            s = {r ^ 1, r ^ (1 << (p - 1))}  # straddle bond, periodic bond
+            for b in range(p - 1):
+                if ((r >> b) ^ (r >> (b + 1))) & 1:
+                    s.add(r ^ (3 << b))  # anti-aligned rank-rank bond
+            out.append(s - {r})
+        return out
+
+    patterns = {"heisenberg": heisenberg_partners(P), "all_to_all": [set(range(P)) - {r} for r in range(P)]}
+    for (name, partners), reductions in itertools.product(patterns.items(), (0, 2)):
+        assert all(r in partners[q] for r in range(P) for q in partners[r]), "partners must be symmetric"
+        for seed in range(40):
+            assert simulate_slab_push(P, partners, 12, nbuf=2, reductions=reductions, seed=seed) is None, (name, reductions, seed)
+    # one buffer is not enough: a partner that finished its apply stores the next exchange while I am still reading
+    assert any(simulate_slab_push(P, patterns["heisenberg"], 12, nbuf=1, reductions=0, seed=s) is not None for s in range(100))
