@@ -143,3 +143,45 @@ def test_thick_restart_two_lowest_states_of_the_heisenberg_ring():
     tr.close()
     op.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_thick_restart_lanczos_row_partitioned_on_virtual_ranks(nranks):
+    """The compress step (cmb_lanczos_thick_restart) and the restarted chain on a row-partitioned basis: every rank holds
+    a slab of the kept Ritz vectors; the projected arrowhead matrix and the stop decision are identical on all ranks."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import multirank_checks as mc
+
+    N = 40
+    n = N * N
+    full = syn.laplacian2d_csr(N)
+    x0 = syn.start_vector(n, seed=3)
+    ex = np.sort((4 - 2 * np.cos(np.arange(1, N + 1)[:, None] * np.pi / (N + 1))
+                  - 2 * np.cos(np.arange(1, N + 1)[None, :] * np.pi / (N + 1))).reshape(-1))
+
+    def work(ctx, comm):
+        r0, r1 = comm.row_range(n)
+        op = pkg.DeviceOperator.from_csr(ctx, *mc.shard_of(full, r0, r1), n_global=n, row_begin=r0)
+        tr = pkg.ThickRestartLanczos(np.float64)
+        tr.setMatrixMultiplication(op).setInitialVector(x0[r0:r1])
+        tr.setWanted(3).setMaxBasis(20).setTolerance(1e-11).setMaxRestarts(500)
+        tr.compute()
+        out = (tr.eigenvalues(), tr.converged(), tr.restarts(), tr.nvectors(), np.concatenate(comm.gather(tr.eigenvectors())))
+        tr.close()
+        op.close()
+        return out
+
+    results, _ = pkg.run_virtual_ranks(nranks, work)
+    import scipy.sparse as sp
+
+    A = sp.csr_matrix((full[2], full[1], full[0]), shape=(n, n))
+    for ev, conv, restarts, nvec, X in results:
+        assert conv == 3 and restarts > 0 and nvec <= 20
+        # the lowest level is simple, the next one is a degenerate pair of which a single Krylov sequence finds one member
+        np.testing.assert_allclose(ev[:2], ex[:2], atol=1e-9)
+        assert np.abs(ex - ev[2]).min() < 1e-9
+        assert np.all(np.linalg.norm(A @ X - X * ev, axis=0) < 1e-8)
+    assert all(np.array_equal(results[0][0], r[0]) for r in results[1:])
