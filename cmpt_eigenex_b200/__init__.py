@@ -11,7 +11,7 @@ The C++ drop-in headers live in include/cmpt/eigen_ex/.
 """
 from . import capi, synthetic  # noqa: F401
 from .solvers import (ArnoldiEigenSolver, Context, DeviceOperator, LanczosEigenSolver,  # noqa: F401
-                      ThickRestartArnoldi, ThickRestartLanczos, VirtualGroup, run_virtual_ranks, host_hessenberg_eigen, host_symmetric_eigen, host_tridiagonal_eigen)
+                      ThickRestartArnoldi, ThickRestartLanczos, VirtualGroup, run_virtual_ranks, host_general_eigen, host_hessenberg_eigen, host_symmetric_eigen, host_tridiagonal_eigen)
 
 __all__ = ["capi", "synthetic", "Context", "DeviceOperator", "LanczosEigenSolver", "ArnoldiEigenSolver", "ThickRestartLanczos", "ThickRestartArnoldi", "VirtualGroup", "run_virtual_ranks",
-           "host_tridiagonal_eigen", "host_hessenberg_eigen", "host_symmetric_eigen"]
+           "host_tridiagonal_eigen", "host_hessenberg_eigen", "host_general_eigen", "host_symmetric_eigen"]

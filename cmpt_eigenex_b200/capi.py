@@ -142,6 +142,7 @@ def _declare(L):
         "cmbs_exp_solve_with_taylor": (i32, [vp, dbl, dbl, dbl, i32, vp, vp]),
         "cmbs_host_tridiagonal_eigen": (i32, [i64, vp, vp, vp, vp]),
         "cmbs_host_hessenberg_eigen": (i32, [i64, vp, vp, vp]),
+        "cmbs_host_general_eigen": (i32, [i64, vp, vp, vp]),
         "cmbs_host_symmetric_eigen": (i32, [i64, vp, vp, vp]),
         "cmb_host_alloc": (i32, [C.c_size_t, P(vp)]),
         "cmb_host_free": (i32, [vp]),

@@ -780,6 +780,18 @@ int cmbs_host_hessenberg_eigen(int64_t n, const void* h, void* w, void* v) {
     return CMB_OK;
   });
 }
+int cmbs_host_general_eigen(int64_t n, const void* a, void* w, void* v) {
+  S_REQ(n >= 0 && (n == 0 || (a && w)), "bad argument");
+  return guarded([&]() -> int {
+    using C = std::complex<double>;
+    std::vector<C> ww, vv;
+    bool ok = detail::general_eigen<double>(int(n), static_cast<const C*>(a), ww, v ? &vv : nullptr);
+    std::copy(ww.begin(), ww.end(), static_cast<C*>(w));
+    if (v) std::copy(vv.begin(), vv.end(), static_cast<C*>(v));
+    S_REQ(ok, "QR iteration did not converge");
+    return CMB_OK;
+  });
+}
 
 int cmb_host_alloc(size_t bytes, void** out) {
   S_REQ(out, "null argument");

@@ -652,6 +652,16 @@ def host_symmetric_eigen(a):
     return w, z
 
 
+def host_general_eigen(a, vectors=True):
+    """The product's host solver for a general complex matrix (Householder reduction + Hessenberg QR); no GPU needed."""
+    ac = np.asfortranarray(a, dtype=np.complex128)
+    n = ac.shape[0]
+    w = np.empty(n, dtype=np.complex128)
+    v = np.empty((n, n), dtype=np.complex128, order="F") if vectors else None
+    check(lib().cmbs_host_general_eigen(n, ptr(ac), ptr(w), ptr(v) if vectors else None))
+    return (w, v) if vectors else w
+
+
 def host_hessenberg_eigen(h, vectors=True):
     """The product's host Hessenberg solver (detail/hessenberg_eigen.hpp); no GPU needed."""
     hc = np.asfortranarray(h, dtype=np.complex128)

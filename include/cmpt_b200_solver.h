@@ -83,6 +83,9 @@ int cmbs_exp_solve_with_taylor(cmbs_solver* s, double x_re, double x_im, double 
 /* host-side Ritz solvers, exposed for testing against LAPACK (no GPU needed) */
 int cmbs_host_tridiagonal_eigen(int64_t n, const double* alpha, const double* beta, double* w, double* z /*nullable*/);
 int cmbs_host_hessenberg_eigen(int64_t n, const void* h_complex, void* w_complex, void* v_complex /*nullable*/);
+/* general complex matrix (column-major): Householder reduction to Hessenberg form, then the solver above; the projected
+ * matrix of a thick-restarted Arnoldi run is not Hessenberg any more */
+int cmbs_host_general_eigen(int64_t n, const void* a_complex, void* w_complex, void* v_complex /*nullable*/);
 /* dense real symmetric n x n (column-major), cyclic Jacobi (detail/symmetric_eigen.hpp): the projected matrix of the
  * thick-restart driver.  w ascending, z column-major eigenvectors. */
 int cmbs_host_symmetric_eigen(int64_t n, const double* a, double* w, double* z);

@@ -73,6 +73,30 @@ def test_hessenberg_eigen_real_nonsymmetric_conjugate_pairs():
     assert np.abs(h @ v - v * w).max() < 1e-12
 
 
+@pytest.mark.parametrize("n,kind", [(1, "complex"), (2, "real"), (7, "complex"), (30, "real"), (45, "complex"), (30, "arrow")])
+def test_general_eigen_matches_lapack(n, kind):
+    """Householder reduction + Hessenberg QR (detail::general_eigen): what ThickRestartArnoldi solves after a restart,
+    when the projected matrix is a full block with a spike row, and what the Eigen stand-in's ComplexEigenSolver runs."""
+    rng = np.random.default_rng(500 + n)
+    a = rng.normal(size=(n, n)).astype(np.complex128)
+    if kind == "complex":
+        a = a + 1j * rng.normal(size=(n, n))
+    if kind == "arrow":  # kept Schur block (upper triangular) + spike row + fresh Hessenberg part
+        k = 8
+        a = np.triu(a, -1)
+        a[:k, :k] = np.triu(a[:k, :k])
+        a[k, :k] = rng.normal(size=k)
+    w, v = pkg.host_general_eigen(a)
+    wl = np.linalg.eigvals(a)
+    d = np.abs(w[:, None] - wl[None, :])
+    assert d.min(axis=1).max() < 1e-10 and d.min(axis=0).max() < 1e-10
+    np.testing.assert_allclose(np.linalg.norm(v, axis=0), 1.0, atol=1e-12)
+    assert np.linalg.norm(a @ v - v * w, axis=0).max() < 1e-9 * max(1.0, np.abs(a).max() * n)
+    w2 = pkg.host_general_eigen(a, vectors=False)
+    d2 = np.abs(w2[:, None] - wl[None, :])
+    assert d2.min(axis=1).max() < 1e-10 and d2.min(axis=0).max() < 1e-10
+
+
 def _declared_in_headers():
     names = set()
     for hdr in ("cmpt_b200.h", "cmpt_b200_solver.h", "cmpt_b200_debug.h"):
