@@ -105,3 +105,41 @@ def test_two_ranks_on_two_gpus_match_oracle():
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     p = _torchrun(2)
     assert p.returncode == 0 and "DIST_GPU_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-6000:]
+
+
+def test_bench_parity_gate_accepts_rounding_and_rejects_a_wrong_answer():
+    """The gate bench.py applies to every timed run (it exits 3 when `ok` is false): rounding-level differences pass,
+    a perturbation of 1e-8 in one coefficient or eigenvalue fails; for Arnoldi only the converged Ritz values count."""
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rng = np.random.default_rng(0)
+    want = {"alpha": rng.normal(size=101) + 4, "beta": np.abs(rng.normal(size=100)) + 1, "eigenvalues": np.sort(rng.normal(size=5))}
+    noise = lambda a, s: a + s * rng.normal(size=a.shape)  # noqa: E731
+    good = {k: noise(v, 1e-13) for k, v in want.items()}
+    p = bench.parity_against(good, want, "unit")
+    assert p["ok"] and p["worst"] < 1e-11 and p["iterations_compared"] == 100
+    bad = {k: v.copy() for k, v in good.items()}
+    bad["beta"][37] += 1e-8
+    assert not bench.parity_against(bad, want, "unit")["ok"]
+    bad = {k: v.copy() for k, v in good.items()}
+    bad["eigenvalues"][0] *= 1 + 1e-8
+    assert not bench.parity_against(bad, want, "unit")["ok"]
+    # a prefix comparison (live cpu_baseline run of the first iterations) ignores what lies beyond it
+    bad = {k: v.copy() for k, v in good.items()}
+    bad["alpha"][60] += 1.0
+    assert bench.parity_against(bad, want, "unit", count=20)["ok"]
+    # Arnoldi: the projected matrix and the converged Ritz values are gated, unconverged Ritz values are not
+    H = np.triu(rng.normal(size=(12, 12)), -1)
+    ev = rng.normal(size=5) + 1j * rng.normal(size=5)
+    want = {"hessenberg": H, "eigenvalues": ev}
+    got = {"hessenberg": H + 1e-14, "eigenvalues": ev * np.array([1, 1, 1, 1 + 1e-6, 1]), "ritz_residuals": np.array([1e-12, 1e-12, 1e-12, 1e-3, 1e-12])}
+    assert bench.parity_against(got, want, "unit")["ok"]
+    got["ritz_residuals"][3] = 1e-12
+    assert not bench.parity_against(got, want, "unit")["ok"]
+    got = {"hessenberg": H.copy(), "eigenvalues": ev, "ritz_residuals": np.full(5, 1e-12)}
+    got["hessenberg"][2, 3] += 1e-7
+    assert not bench.parity_against(got, want, "unit")["ok"]
